@@ -1,0 +1,103 @@
+"""Deterministic synthetic eye frames / iris label maps (numpy PCG64, stable across versions).
+
+Stands in for the licensed OpenEDS2019 (1,640,400) / OpenEDS2020 (1,400,640) frames the
+reference loads in data_preprocessing.py (out of scope): a smooth low-frequency
+background, a textured annulus "iris" (label 2), a dark pupil (label 3), a bright sclera
+(label 1) and a few saturated glint blobs (> 0.8) so that the glint mask of
+pipelines.py:143-144 is exercised.  The iris covers ~6-10 % of the frame like the two eye
+PNGs shipped with the reference.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _smooth_noise(rng: np.random.Generator, h: int, w: int, cells: int) -> np.ndarray:
+    """Bilinear up-sampling of a coarse random grid -> smooth field in [0,1]."""
+    gh, gw = max(2, h // cells + 2), max(2, w // cells + 2)
+    g = rng.random((gh, gw), dtype=np.float64)
+    ys = np.linspace(0, gh - 1.001, h)
+    xs = np.linspace(0, gw - 1.001, w)
+    y0 = np.floor(ys).astype(np.int64)
+    x0 = np.floor(xs).astype(np.int64)
+    fy = (ys - y0)[:, None]
+    fx = (xs - x0)[None, :]
+    a = g[y0][:, x0]
+    b = g[y0][:, x0 + 1]
+    c = g[y0 + 1][:, x0]
+    d = g[y0 + 1][:, x0 + 1]
+    return (a * (1 - fy) * (1 - fx) + b * (1 - fy) * fx + c * fy * (1 - fx) + d * fy * fx)
+
+
+def synthetic_eye(seed: int, h: int = 640, w: int = 400):
+    """Return (frame float32 [1,h,w] in [0,1], labels int64 [1,h,w] in {0,1,2,3})."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    cy = h * (0.45 + 0.1 * rng.random())
+    cx = w * (0.45 + 0.1 * rng.random())
+    r_iris = min(h, w) * (0.19 + 0.03 * rng.random())
+    r_pupil = r_iris * (0.30 + 0.1 * rng.random())
+    ecc = 0.85 + 0.15 * rng.random()
+    rr = np.sqrt(((yy - cy) / ecc) ** 2 + (xx - cx) ** 2)
+    theta = np.arctan2(yy - cy, xx - cx)
+
+    bg = 0.25 + 0.35 * _smooth_noise(rng, h, w, 64)
+    sclera = rr < r_iris * 2.2
+    img = bg.copy()
+    img[sclera] = 0.55 + 0.2 * _smooth_noise(rng, h, w, 32)[sclera]
+
+    # iris texture: radial streaks + fine noise
+    k = int(rng.integers(24, 48))
+    streak = 0.5 + 0.5 * np.sin(k * theta + 6.0 * _smooth_noise(rng, h, w, 16))
+    fine = rng.random((h, w))
+    iris_tex = 0.30 + 0.25 * streak + 0.15 * fine
+    iris = (rr < r_iris) & (rr >= r_pupil)
+    img[iris] = iris_tex[iris]
+    pupil = rr < r_pupil
+    img[pupil] = 0.04 + 0.04 * fine[pupil]
+
+    # eyelid: cut the top of the iris like a real eye
+    lid = yy < cy - r_iris * (0.55 + 0.25 * rng.random())
+    img[lid] = bg[lid]
+
+    labels = np.zeros((h, w), dtype=np.int64)
+    labels[sclera & ~lid] = 1
+    labels[iris & ~lid] = 2
+    labels[pupil & ~lid] = 3
+
+    # glints: saturated blobs, some inside the iris
+    for _ in range(int(rng.integers(3, 7))):
+        a = rng.random() * 2 * np.pi
+        rad = r_iris * rng.random()
+        gy, gx = cy + rad * np.sin(a), cx + rad * np.cos(a)
+        gr = 2.0 + 0.02 * min(h, w) * rng.random()
+        blob = ((yy - gy) ** 2 + (xx - gx) ** 2) < gr * gr
+        img[blob] = 0.85 + 0.15 * rng.random()
+
+    img = np.clip(img, 0.0, 1.0).astype(np.float32)
+    return img[None], labels[None]
+
+
+def synthetic_batch(seeds, h: int = 640, w: int = 400):
+    """Stack several synthetic eyes: (frames [B,1,h,w] float32, labels [B,1,h,w] int64)."""
+    frames, labels = zip(*(synthetic_eye(s, h, w) for s in seeds))
+    return np.stack(frames), np.stack(labels)
+
+
+def synthetic_iris_crops(seeds, size: int = 224):
+    """3-channel square iris crops as the drivers feed nst() (…2019.py:66-79): a textured
+    disc on a zero background, replicated to 3 channels.  float32 [B,3,size,size]."""
+    out = []
+    for s in seeds:
+        rng = np.random.default_rng(1000003 + s)
+        yy, xx = np.mgrid[0:size, 0:size].astype(np.float64)
+        c = (size - 1) / 2.0
+        rr = np.sqrt((yy - c) ** 2 + (xx - c) ** 2)
+        theta = np.arctan2(yy - c, xx - c)
+        k = int(rng.integers(24, 48))
+        tex = 0.30 + 0.25 * (0.5 + 0.5 * np.sin(k * theta + 6.0 * _smooth_noise(rng, size, size, 16)))
+        tex = tex + 0.15 * rng.random((size, size))
+        m = (rr < c) & (rr > c * 0.33)
+        img = np.where(m, tex, 0.0).astype(np.float32)
+        out.append(np.repeat(img[None], 3, axis=0))
+    return np.stack(out)
