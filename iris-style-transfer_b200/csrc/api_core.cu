@@ -1,0 +1,80 @@
+// Error plumbing, tensor-map encoding and device checks for libisx.
+#include <stdarg.h>
+
+#include "../../include/isx.h"
+#include "isx_common.cuh"
+#include "isx_internal.h"
+
+static thread_local char g_err[1024] = "";
+
+void isx_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* isx_last_error(void) { return g_err; }
+extern "C" int isx_version(void) { return ISX_VERSION; }
+
+extern "C" int isx_device_check(int device) {
+  int count = 0;
+  ISX_CHECK_CUDA(cudaGetDeviceCount(&count));
+  ISX_REQUIRE(device >= 0 && device < count, "isx_device_check: device %d not present (%d visible)", device, count);
+  cudaDeviceProp prop;
+  ISX_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  ISX_REQUIRE(prop.major == 10, "isx: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+              prop.major, prop.minor);
+  return 0;
+}
+
+// cuTensorMapEncodeTiled is fetched through the runtime so that libisx.so does not link libcuda
+// (the library must load -- symbols only -- on a box without a driver for the CPU test tier).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) {
+    isx_set_error("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int isx_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return 3;
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    isx_set_error("tensor map base %p is not 16-byte aligned", base);
+    return 3;
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    isx_set_error("cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u]",
+                  (int)r, rank, (unsigned long long)dims[0], rank > 1 ? (unsigned long long)dims[1] : 0ull,
+                  rank > 2 ? (unsigned long long)dims[2] : 0ull, rank > 3 ? (unsigned long long)dims[3] : 0ull, box[0],
+                  rank > 1 ? box[1] : 0u, rank > 2 ? box[2] : 0u, rank > 3 ? box[3] : 0u);
+    return 3;
+  }
+  return 0;
+}

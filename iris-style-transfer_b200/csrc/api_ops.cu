@@ -1,0 +1,130 @@
+// C-ABI wrappers (include/isx.h) over the kernel launchers.
+#include "../../include/isx.h"
+#include "isx_common.cuh"
+#include "isx_internal.h"
+#include "isx_kernels.h"
+
+using namespace isx;
+typedef __nv_bfloat16 bf16;
+
+static inline cudaStream_t S(isx_stream s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline const bf16* P(const isx_bf16* p) { return reinterpret_cast<const bf16*>(p); }
+static inline bf16* P(isx_bf16* p) { return reinterpret_cast<bf16*>(p); }
+
+// tile_cfg (test / tuning hook): BN*100 + MT*10 + stages, 0 = heuristic (e.g. 25623 = BN 256, MT 2, 3 stages)
+static void decode_tile_cfg(int cfg, ConvArgs* a) {
+  if (cfg > 0) {
+    a->force_bn = cfg / 100;
+    a->force_mt = (cfg % 100) / 10;
+    a->force_stages = cfg % 10;
+  }
+}
+
+extern "C" int isx_pack_conv3x3_weights(const float* w, int Cout, int Cin, isx_bf16* wf, isx_bf16* wd,
+                                        isx_stream stream) {
+  ISX_REQUIRE(w && (wf || wd) && Cout > 0 && Cin > 0, "isx_pack_conv3x3_weights: bad arguments");
+  return pack_conv_weights(w, Cout, Cin, P(wf), P(wd), S(stream));
+}
+
+extern "C" int isx_conv1_1_fwd(const float* x, int xc, const float* mask, int mask_b, const float* w,
+                               const float* bias, isx_bf16* out, int B, int H, int W, isx_stream stream) {
+  ISX_REQUIRE(x && w && out && B > 0 && H > 0 && W > 0, "isx_conv1_1_fwd: bad arguments");
+  ISX_REQUIRE(!mask || mask_b == 1 || mask_b == B, "isx_conv1_1_fwd: mask batch %d must be 1 or %d", mask_b, B);
+  return conv1_1_fwd(x, xc, mask, mask_b, w, bias, P(out), B, H, W, S(stream));
+}
+
+extern "C" int isx_conv1_1_dgrad(const isx_bf16* dy, const float* w, const float* mask, int mask_b, float* dx, int xc,
+                                 int B, int H, int W, isx_stream stream) {
+  ISX_REQUIRE(dy && w && dx && B > 0 && H > 0 && W > 0, "isx_conv1_1_dgrad: bad arguments");
+  ISX_REQUIRE(xc == 1 || xc == 3, "isx_conv1_1_dgrad: xc must be 1 or 3");
+  return conv1_1_dgrad(P(dy), w, mask, mask_b, dx, xc, B, H, W, S(stream));
+}
+
+extern "C" int isx_conv3x3_bias_relu_fwd(const isx_bf16* in, const isx_bf16* w_fwd, const float* bias, isx_bf16* out,
+                                         int B, int H, int W, int Cin, int Cout, int relu, int tile_cfg,
+                                         isx_stream stream) {
+  ISX_REQUIRE(in && w_fwd && out, "isx_conv3x3_bias_relu_fwd: null pointer");
+  ConvArgs a;
+  a.in = P(in); a.weight = P(w_fwd); a.out = P(out);
+  a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ntaps = 9;
+  a.bias = bias; a.relu = relu;
+  decode_tile_cfg(tile_cfg, &a);
+  return conv_tc(a, S(stream));
+}
+
+extern "C" int isx_conv3x3_dgrad(const isx_bf16* dy, const isx_bf16* w_dgrad, isx_bf16* dx, int B, int H, int W,
+                                 int Cin, int Cout, const isx_bf16* relu_act, const isx_bf16* add_grad,
+                                 const float* aff_a, const float* aff_b, int tile_cfg, isx_stream stream) {
+  ISX_REQUIRE(dy && w_dgrad && dx, "isx_conv3x3_dgrad: null pointer");
+  ConvArgs a;
+  a.in = P(dy); a.weight = P(w_dgrad); a.out = P(dx);
+  a.B = B; a.H = H; a.W = W; a.Cin = Cout; a.Cout = Cin; a.ntaps = 9;  // GEMM K = fwd Cout, N = fwd Cin
+  a.mask_act = P(relu_act); a.add_buf = P(add_grad); a.aff_a = aff_a; a.aff_b = aff_b;
+  decode_tile_cfg(tile_cfg, &a);
+  return conv_tc(a, S(stream));
+}
+
+extern "C" int isx_maxpool2x2_fwd(const isx_bf16* in, isx_bf16* out, int B, int H, int W, int C, isx_stream stream) {
+  ISX_REQUIRE(in && out, "isx_maxpool2x2_fwd: null pointer");
+  return maxpool_fwd(P(in), P(out), B, H, W, C, S(stream));
+}
+
+extern "C" int isx_maxpool2x2_bwd(const isx_bf16* dy, const isx_bf16* act, isx_bf16* dx, int B, int H, int W, int C,
+                                  isx_stream stream) {
+  ISX_REQUIRE(dy && act && dx, "isx_maxpool2x2_bwd: null pointer");
+  return maxpool_bwd(P(dy), P(act), P(dx), B, H, W, C, S(stream));
+}
+
+extern "C" int64_t isx_gram_workspace_bytes(int B, int HW, int C) {
+  if (B <= 0 || HW <= 0 || C <= 0) return 0;
+  return static_cast<int64_t>(gram_pick_splits(B, HW, C)) * B * C * C * 4;
+}
+
+extern "C" int isx_gram_fwd(const isx_bf16* feat, int B, int HW, int C, float inv_n, void* workspace, float* G_out,
+                            const float* target, int target_b, double loss_scale, double* loss, float grad_scale,
+                            isx_bf16* D_out, isx_stream stream) {
+  ISX_REQUIRE(feat && workspace, "isx_gram_fwd: null pointer");
+  ISX_REQUIRE(!target || target_b == 1 || target_b == B, "isx_gram_fwd: target batch %d must be 1 or %d", target_b, B);
+  const int splits = gram_pick_splits(B, HW, C);
+  int rc = gram_tc_partial(P(feat), B, HW, C, splits, static_cast<float*>(workspace), S(stream));
+  if (rc) return rc;
+  return gram_finalize(static_cast<const float*>(workspace), B, splits, C, inv_n, G_out, target, target_b, loss_scale,
+                       loss, grad_scale, P(D_out), S(stream));
+}
+
+extern "C" int isx_gram_bwd(const isx_bf16* feat, const isx_bf16* D, isx_bf16* dF, int B, int H, int W, int C,
+                            const isx_bf16* relu_act, isx_stream stream) {
+  ISX_REQUIRE(feat && D && dF, "isx_gram_bwd: null pointer");
+  ConvArgs a;
+  a.in = P(feat); a.weight = P(D); a.out = P(dF);
+  a.B = B; a.H = H; a.W = W; a.Cin = C; a.Cout = C; a.ntaps = 1;
+  a.per_image_weights = true;
+  a.mask_act = P(relu_act);
+  return conv_tc(a, S(stream));
+}
+
+extern "C" int isx_content_mse_fwd_bwd(const isx_bf16* pred, const isx_bf16* target, int target_b, isx_bf16* grad,
+                                       int B, int64_t per_image, double loss_scale, float grad_scale, double* loss,
+                                       isx_stream stream) {
+  ISX_REQUIRE(pred && target && loss, "isx_content_mse_fwd_bwd: null pointer");
+  ISX_REQUIRE(target_b == 1 || target_b == B, "isx_content_mse_fwd_bwd: target batch %d must be 1 or %d", target_b, B);
+  return content_mse(P(pred), P(target), target_b, P(grad), B, per_image, loss_scale, grad_scale, loss, S(stream));
+}
+
+extern "C" int isx_bn_stats_fwd(const isx_bf16* feat, int B, int64_t HW, int C, double* sums, float* mean, float* std_,
+                                const float* t_mean, const float* t_std, int target_b, double loss_scale,
+                                double grad_scale, double* loss, float* aff_a, float* aff_b, isx_stream stream) {
+  ISX_REQUIRE(feat && sums, "isx_bn_stats_fwd: null pointer");
+  ISX_REQUIRE(HW >= 2, "isx_bn_stats_fwd: unbiased std needs at least 2 pixels");
+  ISX_CHECK_CUDA(cudaMemsetAsync(sums, 0, static_cast<size_t>(B) * C * 2 * sizeof(double), S(stream)));
+  int rc = chan_sums(P(feat), B, HW, C, sums, S(stream));
+  if (rc) return rc;
+  return bn_finalize(sums, B, C, HW, mean, std_, t_mean, t_std, target_b, loss_scale, grad_scale, loss, aff_a, aff_b,
+                     S(stream));
+}
+
+extern "C" int isx_tap_add_mask(const isx_bf16* g, const isx_bf16* add, const float* aff_a, const float* aff_b,
+                                const isx_bf16* act, isx_bf16* out, int B, int64_t HW, int C, isx_stream stream) {
+  ISX_REQUIRE(act && out, "isx_tap_add_mask: null pointer");
+  return tap_add_mask(P(g), P(add), aff_a, aff_b, P(act), P(out), B, HW, C, S(stream));
+}

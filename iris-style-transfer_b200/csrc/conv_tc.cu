@@ -1,0 +1,342 @@
+// K1 / K3 / K5: 3x3 (stride 1, pad 1) and 1x1 convolutions over NHWC bf16 activations as an
+// implicit GEMM on the 5th-gen tensor cores (tcgen05.mma, fp32 accumulators in TMEM), operands
+// staged by TMA.  One kernel covers
+//   * conv fwd + bias + ReLU                      (reference: torchvision vgg19.features Conv2d+ReLU,
+//                                                  called from models/vgg/vgg.py:87)
+//   * conv dgrad (+ tap gradient, x ReLU mask)     (autograd of the above, pipelines.py:90) -- a 3x3
+//                                                  conv of dY with the 180-degree-rotated, transposed filter
+//   * Gram backward dF = F . D_b (1x1, per-image D) (autograd of utils.py:253-256)
+//
+// GEMM view: M = pixels (a TW x TH x TB patch = 128 rows per M-tile, MT M-tiles per CTA),
+// N = Cout tile (BN), K = ntaps * Cin walked as (tap, 64-channel chunk).  For every K block the
+// producer issues one 4-D TMA box load per M-tile at the tap-shifted coordinate (out-of-bounds
+// rows/cols are zero-filled by TMA == the conv's zero padding) and one 2-D load of the weight slab.
+// The A/B tiles land in the SWIZZLE_128B K-major layout tcgen05 consumes directly.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> bias/ReLU/mask/tap-gradient -> bf16 -> swizzled smem ->
+// TMA store).
+#include "isx_common.cuh"
+#include "isx_internal.h"
+
+namespace isx {
+
+struct ConvParams {
+  int B, H, W, Cin, Cout;
+  int ntaps;                 // 9 or 1
+  int TW, TH, TB;            // patch shape, TW*TH*TB == 128
+  int tiles_x, tiles_y, tiles_b;
+  int n_tiles;               // Cout / BN
+  int w_rows_per_image;      // 0, or Cout when every image has its own [Cout x Cin] matrix (Gram bwd)
+  int stages;
+  int relu;
+  const float* bias;         // [Cout] or null
+  const __nv_bfloat16* mask_act;  // [B,H,W,Cout] or null: out = act > 0 ? out : 0
+  const __nv_bfloat16* add_buf;   // [B,H,W,Cout] or null: out += add
+  const float* aff_a;        // [B,Cout] or null: out += aff_a + aff_b * act   (BN-statistics tap gradient)
+  const float* aff_b;
+};
+
+static constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
+
+template <int BN, int MT>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
+  constexpr int kBTileBytes = BN * 128;
+  constexpr int kStageBytes = MT * kATileBytes + kBTileBytes;
+  constexpr int kTmemCols = (MT * BN) <= 32 ? 32 : (MT * BN) <= 64 ? 64 : (MT * BN) <= 128 ? 128 : (MT * BN) <= 256 ? 256 : 512;
+  static_assert(MT * BN <= 512, "accumulators exceed TMEM");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stages = p.stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * kStageBytes);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tmem_full_bar = empty_bar + stages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates --------------------------------------------------------------------
+  const int n_tile = blockIdx.x % p.n_tiles;
+  const int sp_super = blockIdx.x / p.n_tiles;
+  const int n0 = n_tile * BN;
+  int x0[MT], y0[MT], b0[MT];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    int t = sp_super * MT + mt;
+    int tx = t % p.tiles_x;
+    int r = t / p.tiles_x;
+    int ty = r % p.tiles_y;
+    int tb = r / p.tiles_y;  // may exceed tiles_b for the padded last super-tile: fully out of bounds
+    x0[mt] = tx * p.TW;
+    y0[mt] = ty * p.TH;
+    b0[mt] = tb * p.TB;
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int cin_blocks = p.Cin >> 6;
+  const int num_kb = p.ntaps * cin_blocks;
+
+  if (warp == 0) {
+    // ================================ TMA producer =========================================
+    if (lane == 0) {
+      const int wrow0 = (p.w_rows_per_image ? b0[0] * p.w_rows_per_image : 0) + n0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+        const int tap = kb / cin_blocks;
+        const int cb = kb - tap * cin_blocks;
+        const int ky = p.ntaps == 9 ? tap / 3 : 1;
+        const int kx = p.ntaps == 9 ? tap - ky * 3 : 1;
+        uint8_t* st = smem + s * kStageBytes;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+          tma_load_4d(st + mt * kATileBytes, &tmA, &full_bar[s], cb * 64, x0[mt] + kx - 1, y0[mt] + ky - 1, b0[mt]);
+        tma_load_2d(st + MT * kATileBytes, &tmB, &full_bar[s], cb * 64, tap * p.Cout + wrow0);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ===========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, false, false);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
+        const uint32_t b_addr = a_addr + MT * kATileBytes;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K(16) = 64 channels
+            const uint64_t da = umma_desc_sw128(a_addr + mt * kATileBytes + k * 32, 16, 1024);
+            const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16(tmem_base + mt * BN, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ================================ epilogue =============================================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int tw = row % p.TW;
+    const int th = (row / p.TW) % p.TH;
+    const int tb = row / (p.TW * p.TH);
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      const int x = x0[mt] + tw, y = y0[mt] + th, b = b0[mt] + tb;
+      const bool valid = (x < p.W) && (y < p.H) && (b < p.B);
+      const size_t pix = valid ? ((static_cast<size_t>(b) * p.H + y) * p.W + x) * p.Cout : 0;
+#pragma unroll 1
+      for (int g = 0; g < BN / 64; ++g) {
+        uint8_t* stg = smem + (mt * (BN / 64) + g) * kATileBytes;  // pipeline smem is drained by now
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const int nloc = g * 64 + h * 32;
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mt * BN + nloc, v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          const int n = n0 + nloc;
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+              f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+            }
+          }
+          if (p.add_buf != nullptr && valid) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.add_buf + pix + n + i));
+              float2 t;
+              t = unpack_bf16x2(u.x); f[i] += t.x; f[i + 1] += t.y;
+              t = unpack_bf16x2(u.y); f[i + 2] += t.x; f[i + 3] += t.y;
+              t = unpack_bf16x2(u.z); f[i + 4] += t.x; f[i + 5] += t.y;
+              t = unpack_bf16x2(u.w); f[i + 6] += t.x; f[i + 7] += t.y;
+            }
+          }
+          if (p.mask_act != nullptr) {
+            if (valid) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.mask_act + pix + n + i));
+                float a[8];
+                float2 t;
+                t = unpack_bf16x2(u.x); a[0] = t.x; a[1] = t.y;
+                t = unpack_bf16x2(u.y); a[2] = t.x; a[3] = t.y;
+                t = unpack_bf16x2(u.z); a[4] = t.x; a[5] = t.y;
+                t = unpack_bf16x2(u.w); a[6] = t.x; a[7] = t.y;
+                if (p.aff_a != nullptr) {
+                  const float* pa = p.aff_a + static_cast<size_t>(b) * p.Cout + n + i;
+                  const float* pb = p.aff_b + static_cast<size_t>(b) * p.Cout + n + i;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[i + j] += __ldg(pa + j) + __ldg(pb + j) * a[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[i + j] = a[j] > 0.f ? f[i + j] : 0.f;
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          // 32 channels -> 4 x 16 B chunks of this row, 128B-swizzled like the TMA box layout
+          uint8_t* rowp = stg + row * 128;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 o;
+            o.x = pack_bf16x2(f[c * 8 + 0], f[c * 8 + 1]);
+            o.y = pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]);
+            o.z = pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]);
+            o.w = pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]);
+            const int chunk = (h * 4 + c) ^ (row & 7);
+            *reinterpret_cast<uint4*>(rowp + chunk * 16) = o;
+          }
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+        if (threadIdx.x == 64) {
+          tma_store_4d(&tmO, stg, n0 + g * 64, x0[mt], y0[mt], b0[mt]);
+          tma_store_commit();
+        }
+      }
+    }
+    if (threadIdx.x == 64) tma_store_wait_all<0>();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// Pick the 128-pixel patch shape (TW x TH x TB) with the least padding; ties -> wider rows.
+static void choose_patch(int B, int H, int W, bool one_image_per_tile, int* TW, int* TH, int* TB) {
+  long best = -1;
+  for (int tw = 128; tw >= 1; tw >>= 1) {
+    for (int th = 128 / tw; th >= 1; th >>= 1) {
+      int tb = 128 / (tw * th);
+      if (one_image_per_tile && tb != 1) continue;
+      if (tw > 256 || th > 256 || tb > 256) continue;
+      long padded = static_cast<long>((W + tw - 1) / tw * tw) * ((H + th - 1) / th * th) * ((B + tb - 1) / tb * tb);
+      if (best < 0 || padded < best) {
+        best = padded;
+        *TW = tw; *TH = th; *TB = tb;
+      }
+    }
+  }
+}
+
+template <int BN, int MT>
+static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stream) {
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = a.B; p.H = a.H; p.W = a.W; p.Cin = a.Cin; p.Cout = a.Cout; p.ntaps = a.ntaps;
+  choose_patch(a.B, a.H, a.W, a.per_image_weights, &p.TW, &p.TH, &p.TB);
+  p.tiles_x = (a.W + p.TW - 1) / p.TW;
+  p.tiles_y = (a.H + p.TH - 1) / p.TH;
+  p.tiles_b = (a.B + p.TB - 1) / p.TB;
+  p.n_tiles = a.Cout / BN;
+  p.w_rows_per_image = a.per_image_weights ? a.Cout : 0;
+  p.relu = a.relu; p.bias = a.bias; p.mask_act = a.mask_act; p.add_buf = a.add_buf;
+  p.aff_a = a.aff_a; p.aff_b = a.aff_b;
+  if (a.per_image_weights && MT != 1)
+    ISX_REQUIRE(p.tiles_b == a.B, "per-image weights need one image per tile");
+
+  constexpr int kStageBytes = MT * kATileBytes + BN * 128;
+  int stages = stages_override > 0 ? stages_override : (200 * 1024) / kStageBytes;
+  if (stages > 8) stages = 8;
+  while (stages * kStageBytes < MT * (BN / 64) * kATileBytes) ++stages;  // epilogue staging aliases the pipeline
+  const int num_kb = a.ntaps * (a.Cin / 64);
+  if (stages > num_kb && num_kb * kStageBytes >= MT * (BN / 64) * kATileBytes) stages = num_kb;
+  p.stages = stages;
+  const size_t smem_bytes = 1024 + static_cast<size_t>(stages) * kStageBytes + 256;
+  ISX_REQUIRE(smem_bytes <= 227 * 1024, "conv_tc: %zu B of shared memory exceed 227 KB", smem_bytes);
+
+  CUtensorMap tmA, tmB, tmO;
+  {
+    uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
+    uint64_t str[3] = {(uint64_t)a.Cin * 2, (uint64_t)a.W * a.Cin * 2, (uint64_t)a.H * a.W * a.Cin * 2};
+    uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
+    if (isx_make_tmap_bf16(&tmA, a.in, 4, dims, str, box, true)) return 3;
+  }
+  {
+    uint64_t rows = (uint64_t)a.ntaps * a.Cout * (a.per_image_weights ? a.B : 1);
+    uint64_t dims[2] = {(uint64_t)a.Cin, rows};
+    uint64_t str[1] = {(uint64_t)a.Cin * 2};
+    uint32_t box[2] = {64, (uint32_t)BN};
+    if (isx_make_tmap_bf16(&tmB, a.weight, 2, dims, str, box, true)) return 3;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)a.Cout, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
+    uint64_t str[3] = {(uint64_t)a.Cout * 2, (uint64_t)a.W * a.Cout * 2, (uint64_t)a.H * a.W * a.Cout * 2};
+    uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
+    if (isx_make_tmap_bf16(&tmO, a.out, 4, dims, str, box, true)) return 3;
+  }
+  const long sp_tiles = static_cast<long>(p.tiles_x) * p.tiles_y * p.tiles_b;
+  const long grid = ((sp_tiles + MT - 1) / MT) * p.n_tiles;
+  auto kern = conv_tc_kernel<BN, MT>;
+  ISX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  kern<<<(unsigned)grid, 192, smem_bytes, stream>>>(tmA, tmB, tmO, p);
+  ISX_LAUNCH_CHECK();
+  return 0;
+}
+
+int conv_tc(const ConvArgs& a, cudaStream_t stream) {
+  ISX_REQUIRE(a.Cin % 64 == 0 && a.Cout % 64 == 0, "conv_tc: Cin=%d / Cout=%d must be multiples of 64", a.Cin, a.Cout);
+  ISX_REQUIRE(a.ntaps == 9 || a.ntaps == 1, "conv_tc: ntaps must be 9 or 1");
+  ISX_REQUIRE(a.B > 0 && a.H > 0 && a.W > 0, "conv_tc: empty input");
+  ISX_REQUIRE((a.aff_a == nullptr) || (a.mask_act != nullptr), "conv_tc: affine tap gradient needs the activation");
+  int bn = a.force_bn, mt = a.force_mt;
+  if (bn == 0) {
+    bn = a.Cout % 256 == 0 ? 256 : (a.Cout % 128 == 0 ? 128 : 64);
+    mt = a.per_image_weights ? 1 : 2;
+    // small problems: prefer more CTAs over bigger tiles
+    const long pix_tiles = (static_cast<long>(a.B) * a.H * a.W + 127) / 128;
+    auto ctas = [&](int BN_, int MT_) { return ((pix_tiles + MT_ - 1) / MT_) * (a.Cout / BN_); };
+    if (ctas(bn, mt) < 2 * kNumSMs && mt == 2) mt = 1;
+    if (ctas(bn, mt) < kNumSMs && bn == 256) bn = 128;
+  }
+  if (mt == 0) mt = 1;
+  const int st = a.force_stages;
+#define ISX_CONV_CASE(BN_, MT_) \
+  if (bn == BN_ && mt == MT_) return launch_conv<BN_, MT_>(a, st, stream);
+  ISX_CONV_CASE(64, 1) ISX_CONV_CASE(64, 2) ISX_CONV_CASE(128, 1) ISX_CONV_CASE(128, 2)
+  ISX_CONV_CASE(256, 1) ISX_CONV_CASE(256, 2)
+#undef ISX_CONV_CASE
+  ISX_REQUIRE(false, "conv_tc: unsupported tile BN=%d MT=%d", bn, mt);
+}
+
+}  // namespace isx

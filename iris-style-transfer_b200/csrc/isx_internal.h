@@ -1,0 +1,31 @@
+// Internal (C++) interfaces between the translation units of libisx.  The public C-ABI is
+// include/isx.h; everything here is implementation detail.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace isx {
+
+struct ConvArgs {
+  const __nv_bfloat16* in = nullptr;      // [B,H,W,Cin]
+  const __nv_bfloat16* weight = nullptr;  // [ntaps][Cout][Cin] (x B when per_image_weights)
+  __nv_bfloat16* out = nullptr;           // [B,H,W,Cout]
+  int B = 0, H = 0, W = 0, Cin = 0, Cout = 0, ntaps = 9;
+  bool per_image_weights = false;
+  const float* bias = nullptr;
+  int relu = 0;
+  const __nv_bfloat16* mask_act = nullptr;
+  const __nv_bfloat16* add_buf = nullptr;
+  const float* aff_a = nullptr;
+  const float* aff_b = nullptr;
+  int force_bn = 0, force_mt = 0, force_stages = 0;  // tuning / test hooks (0 = heuristic)
+};
+int conv_tc(const ConvArgs& a, cudaStream_t stream);
+
+// Gram partial products: partial[b][split][C][C] (fp32) = sum over the split's pixels of F^T F.
+int gram_tc_partial(const __nv_bfloat16* feat, int B, int HW, int C, int splits, float* partial,
+                    cudaStream_t stream);
+int gram_pick_splits(int B, int HW, int C);
+
+}  // namespace isx

@@ -1,0 +1,29 @@
+// Internal launchers of the HBM-bound kernels (elementwise.cu, lbfgs.cu, imageops.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace isx {
+
+int pack_conv_weights(const float* w, int Cout, int Cin, __nv_bfloat16* wf, __nv_bfloat16* wd, cudaStream_t s);
+int conv1_1_fwd(const float* x, int xc, const float* mask, int mask_b, const float* w, const float* bias,
+                __nv_bfloat16* out, int B, int H, int W, cudaStream_t s);
+int conv1_1_dgrad(const __nv_bfloat16* dy, const float* w, const float* mask, int mask_b, float* dx, int xc, int B,
+                  int H, int W, cudaStream_t s);
+int maxpool_fwd(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t s);
+int maxpool_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* act, __nv_bfloat16* dx, int B, int H, int W, int C,
+                cudaStream_t s);
+int tap_add_mask(const __nv_bfloat16* g, const __nv_bfloat16* add, const float* aff_a, const float* aff_b,
+                 const __nv_bfloat16* act, __nv_bfloat16* out, int B, long HW, int C, cudaStream_t s);
+int gram_finalize(const float* partial, int B, int splits, int C, float inv_n, float* G_out, const float* target,
+                  int target_b, double loss_scale, double* loss, float grad_scale, __nv_bfloat16* D_out,
+                  cudaStream_t s);
+int content_mse(const __nv_bfloat16* pred, const __nv_bfloat16* target, int target_b, __nv_bfloat16* grad, int B,
+                long per_image, double loss_scale, float grad_scale, double* loss, cudaStream_t s);
+int chan_sums(const __nv_bfloat16* f, int B, long HW, int C, double* sums, cudaStream_t s);
+int bn_finalize(const double* sums, int B, int C, long HW, float* mean, float* stdv, const float* t_mean,
+                const float* t_std, int target_b, double loss_scale, double grad_scale, double* loss, float* aff_a,
+                float* aff_b, cudaStream_t s);
+
+}  // namespace isx

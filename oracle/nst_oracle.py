@@ -367,17 +367,18 @@ def nst_eval(x, c_feats, targets, weights, BN_loss, c_loss_weight, s_loss_weight
     """One closure evaluation (pipelines.py:80-91) at a given x: returns (c_loss, s_loss, grad).
     `layer_mask`: optional frame-resolution mask for the G' extension (masked Gram)."""
     xv = x.detach().clone().requires_grad_(True)
-    _, x_c, x_s = vgg19_forward(xv, weights, content_layers, style_layers, full=False)
-    c_loss = content_loss_l2(x_c, c_feats)
-    if layer_mask is not None:
-        ms = layer_masks(layer_mask, [tuple(f.shape[-2:]) for f in x_s])
-        x_s = [f * m for f, m in zip(x_s, ms)]
-    if BN_loss:
-        s_loss = style_loss_bn(x_s, targets[0], targets[1])
-    else:
-        s_loss = style_loss_gram(x_s, targets)
-    loss = c_loss * c_loss_weight + s_loss * s_loss_weight
-    (g,) = torch.autograd.grad(loss, xv)
+    with torch.enable_grad():
+        _, x_c, x_s = vgg19_forward(xv, weights, content_layers, style_layers, full=False)
+        c_loss = content_loss_l2(x_c, c_feats)
+        if layer_mask is not None:
+            ms = layer_masks(layer_mask, [tuple(f.shape[-2:]) for f in x_s])
+            x_s = [f * m for f, m in zip(x_s, ms)]
+        if BN_loss:
+            s_loss = style_loss_bn(x_s, targets[0], targets[1])
+        else:
+            s_loss = style_loss_gram(x_s, targets)
+        loss = c_loss * c_loss_weight + s_loss * s_loss_weight
+        (g,) = torch.autograd.grad(loss, xv)
     return float(c_loss.detach()), float(s_loss.detach()), g
 
 

@@ -1,0 +1,238 @@
+"""Kernel-level parity on the B200: every C-ABI kernel against a plain PyTorch fp32 evaluation of
+the same op on the same (bf16-rounded) inputs.  Tolerances: one bf16 rounding of the output
+(2^-8 relative) for bf16 results, 1e-4 relative for fp32 results (fp32 accumulation order)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def isx():
+    import iris_b200
+    from iris_b200 import _lib
+
+    _lib.load()
+    _lib.call("isx_device_check", 0)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return _lib
+
+
+def nhwc_bf16(B, H, W, C, seed, scale=1.0, relu=False):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    t = torch.randn(B, H, W, C, device="cuda", generator=g) * scale
+    if relu:
+        t = t.clamp_min(0)
+    return t.to(torch.bfloat16).contiguous()
+
+
+def pack(isx, w):
+    Cout, Cin = w.shape[:2]
+    wf = torch.empty(9, Cout, Cin, device="cuda", dtype=torch.bfloat16)
+    wd = torch.empty(9, Cin, Cout, device="cuda", dtype=torch.bfloat16)
+    isx.call("isx_pack_conv3x3_weights", w.contiguous(), Cout, Cin, wf, wd, isx.stream_ptr())
+    return wf, wd
+
+
+def assert_close_bf16(got, ref, what):
+    got = got.float()
+    err = (got - ref).abs()
+    tol = 2.0 ** -7 * ref.abs() + 2e-2 * ref.abs().mean() + 1e-6
+    bad = (err > tol).sum().item()
+    assert bad == 0, "%s: %d / %d elements off (max err %.4g, ref absmax %.4g)" % (
+        what, bad, ref.numel(), err.max().item(), ref.abs().max().item())
+
+
+CONV_SHAPES = [
+    # B, H, W, Cin, Cout
+    (2, 20, 24, 64, 64),
+    (1, 50, 80, 128, 256),
+    (3, 13, 9, 256, 128),    # ragged tiles in every dimension
+    (1, 25, 40, 512, 512),
+    (5, 6, 10, 64, 128),     # several images per tile
+]
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+@pytest.mark.parametrize("cfg", [0, 6410, 6420, 12810, 12820, 25610, 25620, 12813])
+def test_conv3x3_fwd(isx, shape, cfg):
+    B, H, W, Cin, Cout = shape
+    bn = cfg // 100
+    if bn and Cout % bn:
+        pytest.skip("BN does not divide Cout")
+    x = nhwc_bf16(B, H, W, Cin, 1, relu=True)
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") * (2.0 / (9 * Cin)) ** 0.5
+    bias = torch.randn(Cout, device="cuda") * 0.1
+    wf, _ = pack(isx, w)
+    out = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    isx.call("isx_conv3x3_bias_relu_fwd", x, wf, bias, out, B, H, W, Cin, Cout, 1, cfg, isx.stream_ptr())
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), bias, padding=1))
+    assert_close_bf16(out, ref.permute(0, 2, 3, 1), "conv fwd %s cfg %d" % (shape, cfg))
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+@pytest.mark.parametrize("mode", ["plain", "mask", "mask_add", "mask_affine"])
+def test_conv3x3_dgrad(isx, shape, mode):
+    B, H, W, Cin, Cout = shape
+    dy = nhwc_bf16(B, H, W, Cout, 2)
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") * (2.0 / (9 * Cout)) ** 0.5
+    _, wd = pack(isx, w)
+    act = nhwc_bf16(B, H, W, Cin, 3, relu=True)
+    add = nhwc_bf16(B, H, W, Cin, 4, scale=0.5)
+    aa = torch.randn(B, Cin, device="cuda") * 0.3
+    ab = torch.randn(B, Cin, device="cuda") * 0.3
+    dx = torch.full((B, H, W, Cin), float("nan"), device="cuda", dtype=torch.bfloat16)
+    isx.call("isx_conv3x3_dgrad", dy, wd, dx, B, H, W, Cin, Cout,
+             act if mode != "plain" else None, add if mode == "mask_add" else None,
+             aa if mode == "mask_affine" else None, ab if mode == "mask_affine" else None, 0, isx.stream_ptr())
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), padding=1).permute(0, 2, 3, 1)
+    if mode == "mask_add":
+        ref = ref + add.float()
+    if mode == "mask_affine":
+        ref = ref + aa[:, None, None, :] + ab[:, None, None, :] * act.float()
+    if mode != "plain":
+        ref = torch.where(act.float() > 0, ref, torch.zeros_like(ref))
+    assert_close_bf16(dx, ref, "dgrad %s %s" % (shape, mode))
+
+
+@pytest.mark.parametrize("C", [64, 128, 256, 512])
+@pytest.mark.parametrize("B,H,W", [(1, 50, 80), (3, 17, 23), (2, 100, 160)])
+def test_gram_fwd_and_loss(isx, C, B, H, W):
+    f = nhwc_bf16(B, H, W, C, 5, relu=True)
+    HW = H * W
+    inv_n = 1.0 / (C * HW)
+    ws = torch.empty(isx.call_i64("isx_gram_workspace_bytes", B, HW, C), device="cuda", dtype=torch.uint8)
+    G = torch.full((B, C, C), float("nan"), device="cuda")
+    tgt = torch.randn(B, C, C, device="cuda") * 0.01
+    loss = torch.zeros(B, device="cuda", dtype=torch.float64)
+    D = torch.empty(B, C, C, device="cuda", dtype=torch.bfloat16)
+    isx.call("isx_gram_fwd", f, B, HW, C, isx.f32(inv_n), ws, G, tgt, B, isx.f64(0.25), loss, isx.f32(3.0), D,
+             isx.stream_ptr())
+    torch.cuda.synchronize()
+    ff = f.float().reshape(B, HW, C)
+    ref = torch.bmm(ff.transpose(1, 2), ff) * inv_n
+    assert torch.allclose(G, ref, rtol=2e-4, atol=1e-6 * ref.abs().max().item()), (G - ref).abs().max().item()
+    ref_loss = 0.25 * ((ref - tgt).double() ** 2).sum(dim=(1, 2))
+    assert torch.allclose(loss, ref_loss, rtol=1e-4)
+    assert_close_bf16(D, 3.0 * (ref - tgt), "gram D")
+    # single shared target (style batch 1)
+    loss.zero_()
+    isx.call("isx_gram_fwd", f, B, HW, C, isx.f32(inv_n), ws, None, tgt[:1].contiguous(), 1, isx.f64(0.25), loss,
+             isx.f32(0.0), None, isx.stream_ptr())
+    ref_loss1 = 0.25 * ((ref - tgt[:1]).double() ** 2).sum(dim=(1, 2))
+    assert torch.allclose(loss, ref_loss1, rtol=1e-4)
+
+
+@pytest.mark.parametrize("C", [64, 128, 256, 512])
+def test_gram_bwd(isx, C):
+    B, H, W = 2, 26, 40
+    f = nhwc_bf16(B, H, W, C, 6, relu=True)
+    Dm = torch.randn(B, C, C, device="cuda") * 0.1
+    Dm = (Dm + Dm.transpose(1, 2)).to(torch.bfloat16).contiguous()
+    dF = torch.full((B, H, W, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    isx.call("isx_gram_bwd", f, Dm, dF, B, H, W, C, None, isx.stream_ptr())
+    torch.cuda.synchronize()
+    ref = torch.bmm(f.float().reshape(B, H * W, C), Dm.float()).reshape(B, H, W, C)
+    assert_close_bf16(dF, ref, "gram bwd C=%d" % C)
+    isx.call("isx_gram_bwd", f, Dm, dF, B, H, W, C, f, isx.stream_ptr())
+    torch.cuda.synchronize()
+    assert_close_bf16(dF, torch.where(f.float() > 0, ref, torch.zeros_like(ref)), "gram bwd masked C=%d" % C)
+
+
+@pytest.mark.parametrize("xc", [3, 1])
+@pytest.mark.parametrize("use_mask", [False, True])
+def test_conv1_1_fwd_dgrad(isx, xc, use_mask):
+    B, H, W = 2, 21, 30
+    x = torch.rand(B, xc, H, W, device="cuda")
+    w = torch.randn(64, 3, 3, 3, device="cuda") * (2.0 / (9 * 64)) ** 0.5
+    bias = torch.randn(64, device="cuda") * 0.1
+    mask = (torch.rand(B, 1, H, W, device="cuda") > 0.3).float() if use_mask else None
+    out = torch.empty(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
+    isx.call("isx_conv1_1_fwd", x, xc, mask, B, w, bias, out, B, H, W, isx.stream_ptr())
+    mean = torch.tensor([0.485, 0.456, 0.406], device="cuda").view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device="cuda").view(1, 3, 1, 1)
+    xr = x.clone().requires_grad_(True)
+    xn = (xr - mean) / std
+    if use_mask:
+        xn = xn * mask
+    y = F.relu(F.conv2d(xn, w, bias, padding=1))
+    assert_close_bf16(out, y.detach().permute(0, 2, 3, 1), "conv1_1 fwd")
+    dy = nhwc_bf16(B, H, W, 64, 7)
+    y.backward(dy.float().permute(0, 3, 1, 2) * (y > 0))  # dy is "already ReLU-masked" in the kernel contract
+    dyk = (dy.float() * (y.detach().permute(0, 2, 3, 1) > 0)).to(torch.bfloat16).contiguous()
+    dx = torch.empty(B, xc, H, W, device="cuda")
+    isx.call("isx_conv1_1_dgrad", dyk, w, mask, B, dx, xc, B, H, W, isx.stream_ptr())
+    torch.cuda.synchronize()
+    ref = torch.autograd.grad(F.conv2d(xn, w, bias, padding=1), xr, dyk.float().permute(0, 3, 1, 2))[0] if False else None
+    # recompute the reference gradient from the bf16-rounded masked dy
+    xr2 = x.clone().requires_grad_(True)
+    xn2 = (xr2 - mean) / std
+    if use_mask:
+        xn2 = xn2 * mask
+    F.conv2d(xn2, w, bias, padding=1).backward(dyk.float().permute(0, 3, 1, 2))
+    assert torch.allclose(dx, xr2.grad, rtol=1e-4, atol=1e-4 * xr2.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 20, 24, 64), (1, 25, 41, 128), (3, 8, 6, 512)])
+def test_maxpool_fwd_bwd(isx, B, H, W, C):
+    a = nhwc_bf16(B, H, W, C, 8, relu=True)
+    out = torch.empty(B, H // 2, W // 2, C, device="cuda", dtype=torch.bfloat16)
+    isx.call("isx_maxpool2x2_fwd", a, out, B, H, W, C, isx.stream_ptr())
+    ar = a.float().permute(0, 3, 1, 2).requires_grad_(True)
+    pr = F.max_pool2d(ar, 2, 2)
+    assert torch.equal(out.float(), pr.detach().permute(0, 2, 3, 1))
+    dy = nhwc_bf16(B, H // 2, W // 2, C, 9)
+    dx = torch.full((B, H, W, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    isx.call("isx_maxpool2x2_bwd", dy, a, dx, B, H, W, C, isx.stream_ptr())
+    torch.cuda.synchronize()
+    pr.backward(dy.float().permute(0, 3, 1, 2))
+    ref = (ar.grad * (ar.detach() > 0)).permute(0, 2, 3, 1)
+    assert torch.equal(dx.float(), ref)
+
+
+def test_content_mse(isx):
+    B, n = 3, 512 * 50 * 80
+    p = nhwc_bf16(B, 50, 80, 512, 10, relu=True)
+    t = nhwc_bf16(B, 50, 80, 512, 11, relu=True)
+    g = torch.empty_like(p)
+    loss = torch.zeros(B, device="cuda", dtype=torch.float64)
+    isx.call("isx_content_mse_fwd_bwd", p, t, B, g, B, isx.i64(n), isx.f64(0.5 / n), isx.f32(1.0 / n), loss,
+             isx.stream_ptr())
+    torch.cuda.synchronize()
+    d = p.float() - t.float()
+    ref_loss = 0.5 * (d.double() ** 2).reshape(B, -1).mean(dim=1)
+    assert torch.allclose(loss, ref_loss, rtol=1e-5)
+    assert_close_bf16(g, d / n * (p.float() > 0), "content grad")
+
+
+@pytest.mark.parametrize("C", [64, 128, 256, 512])
+def test_bn_stats(isx, C):
+    B, H, W = 3, 37, 52
+    f = nhwc_bf16(B, H, W, C, 12, relu=True)
+    HW = H * W
+    sums = torch.empty(B, C, 2, device="cuda", dtype=torch.float64)
+    mean = torch.empty(B, C, device="cuda")
+    std = torch.empty(B, C, device="cuda")
+    tm = torch.rand(B, C, device="cuda")
+    ts = torch.rand(B, C, device="cuda")
+    loss = torch.zeros(B, device="cuda", dtype=torch.float64)
+    aa = torch.empty(B, C, device="cuda")
+    ab = torch.empty(B, C, device="cuda")
+    w_l, beta = 1.0, 1e4
+    isx.call("isx_bn_stats_fwd", f, B, isx.i64(HW), C, sums, mean, std, tm, ts, B, isx.f64(w_l / C),
+             isx.f64(beta * w_l / C), loss, aa, ab, isx.stream_ptr())
+    torch.cuda.synchronize()
+    fr = f.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    m_ref, s_ref = fr.mean(dim=(-2, -1)), fr.std(dim=(-2, -1))
+    assert torch.allclose(mean, m_ref.detach(), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(std, s_ref.detach(), rtol=1e-4, atol=1e-6)
+    l_ref = (((m_ref - tm) ** 2 + (s_ref - ts) ** 2).sum(dim=1) * w_l / C)
+    assert torch.allclose(loss, l_ref.detach().double(), rtol=1e-4)
+    (l_ref.sum() * beta).backward()
+    g_ref = fr.grad.permute(0, 2, 3, 1)
+    g_got = aa[:, None, None, :] + ab[:, None, None, :] * f.float()
+    assert torch.allclose(g_got, g_ref, rtol=2e-3, atol=2e-3 * g_ref.abs().max().item())
