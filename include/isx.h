@@ -1,10 +1,10 @@
 /* libisx -- B200 (sm_100a) kernels for the iris-masked neural-style-transfer hot path of
  * AnonymWriter/Iris-Style-Transfer.  C ABI: plain device pointers, explicit shapes, a cudaStream_t;
  * every function returns 0 on success and != 0 on failure (text via isx_last_error()).  Nothing
- * here allocates device memory: the caller (e.g. PyTorch's caching allocator) owns every buffer,
+ * here allocates device memory: the caller (e.g. a framework's caching allocator) owns every buffer,
  * including workspaces whose size is queried first.  Thread-compatible; no global device state.
  *
- * The reference has no FFI/plugin layer (pure PyTorch): each entry point names the reference
+ * The reference has no FFI/plugin layer (it is pure Python): each entry point names the reference
  * call site (relative to the reference repo root) whose library kernels it replaces.
  *
  * Layouts: activations / gradients are NHWC bf16 ("isx_bf16" = 2-byte bfloat16), images and
@@ -93,6 +93,110 @@ int isx_bn_stats_fwd(const isx_bf16* feat, int B, int64_t HW, int C, double* sum
 /* out = (g + add + aff) * (act > 0) -- tap gradient at a layer that no dgrad epilogue feeds; g/add/aff may be NULL */
 int isx_tap_add_mask(const isx_bf16* g, const isx_bf16* add, const float* aff_a, const float* aff_b,
                      const isx_bf16* act, isx_bf16* out, int B, int64_t HW, int C, isx_stream stream);
+
+/* ---- K7/K8: torch.optim.LBFGS([x], lr) with defaults (pipelines.py:59,103; torch/optim/lbfgs.py:333-537)
+ * P independent problems of N floats each advance in lock step, one closure evaluation per tick.
+ * All optimiser scalars live in device memory (state: isx_lbfgs_state_bytes(P)); history S,Y:
+ * fp32 [P][history+1][N] each; mats: isx_lbfgs_mats_bytes(P, history); scratch: isx_lbfgs_scratch_bytes. */
+typedef struct {
+  int32_t epochs;            /* closure evaluations requested (pipelines.py:16,79) */
+  int32_t max_iter;          /* 20 */
+  int32_t max_eval;          /* 25 */
+  int32_t history;           /* 100 (<= 100) */
+  double lr;                 /* 1.0 */
+  double tolerance_grad;     /* 1e-7 */
+  double tolerance_change;   /* 1e-9 */
+  double c_weight, s_weight; /* alpha, beta of pipelines.py:89 */
+} isx_lbfgs_config;
+int64_t isx_lbfgs_state_bytes(int P);
+int64_t isx_lbfgs_mats_bytes(int P, int history);
+int64_t isx_lbfgs_scratch_bytes(int P, int64_t N, int history);
+int isx_lbfgs_init(void* state, int P, isx_stream stream);
+/* One tick AFTER a closure evaluation produced grad and the per-image losses:
+ * memory update + direction + x = clamp(x + t d, 0, 1) (lbfgs.py:396-526 + pipelines.py:82), or the
+ * early-exit bookkeeping.  loss_c/loss_s: double [P*images_per_problem]; hist_c/hist_s: double
+ * [ticks][P] loss logs (pipelines.py:94-95). */
+int isx_lbfgs_tick(float* x, const float* grad, float* grad_prev, float* S, float* Y, void* state, void* mats,
+                   void* scratch, const double* loss_c, const double* loss_s, int images_per_problem, int P,
+                   int64_t N, const isx_lbfgs_config* cfg, double* hist_c, double* hist_s, int tick,
+                   isx_stream stream);
+/* done_out[p] (device int32) <- number of closure evaluations problem p performed once it has finished its
+ * pipelines.py:79 loop, 0 while it is still running */
+int isx_lbfgs_done_flags(const void* state, int P, int32_t* done_out, isx_stream stream);
+int isx_clamp01(float* x, int64_t n, isx_stream stream);
+
+/* ---- fused driver: one closure evaluation of pipelines.py:80-91 ------------------------------- */
+#define ISX_MAX_TAPS 8
+#define ISX_VGG19_CONVS 16
+typedef struct {
+  int32_t B, H, W, xc;                  /* image batch fp32 [B,xc,H,W] */
+  int32_t n_conv;                       /* number of convs to run (deepest tapped conv index + 1) */
+  int32_t style_mode;                   /* 0: Gram (utils.StyleLoss_Gram), 1: mean/std (utils.StyleLoss_BN) */
+  int32_t n_style;
+  int32_t style_conv[ISX_MAX_TAPS];     /* conv index (0..15) whose ReLU output is tapped */
+  float style_w[ISX_MAX_TAPS];
+  int32_t n_content;
+  int32_t content_conv[ISX_MAX_TAPS];
+  float content_w[ISX_MAX_TAPS];
+  int32_t style_target_b;               /* 1 or B */
+  int32_t content_target_b;             /* 1 or B */
+  int32_t coupled;                      /* 1: batch is ONE problem -> content loss is a mean over the batch too */
+  int32_t mask_b;                       /* 0: no input mask, else 1 or B */
+  double c_weight, s_weight;            /* alpha, beta */
+} isx_nst_config;
+
+typedef struct {
+  const float* w0;                      /* conv1_1 fp32 OIHW [64,3,3,3] */
+  const float* bias[ISX_VGG19_CONVS];   /* fp32 [Cout] per conv */
+  const isx_bf16* w_fwd[ISX_VGG19_CONVS];    /* packed (isx_pack_conv3x3_weights); [0] unused */
+  const isx_bf16* w_dgrad[ISX_VGG19_CONVS];
+  void* workspace;                      /* isx_nst_workspace_bytes(cfg) */
+  const isx_bf16* content_target[ISX_MAX_TAPS];  /* bf16 NHWC [content_target_b,h,w,C] */
+  const float* gram_target[ISX_MAX_TAPS];        /* fp32 [style_target_b,C,C] */
+  const float* bn_target_mean[ISX_MAX_TAPS];     /* fp32 [style_target_b,C] */
+  const float* bn_target_std[ISX_MAX_TAPS];
+  const float* input_mask;              /* fp32 [mask_b,1,H,W] or NULL (VGG19.forward(x, mask), vgg.py:84-85) */
+} isx_nst_buffers;
+
+int64_t isx_nst_workspace_bytes(const isx_nst_config* cfg);
+/* forward only (VGG19.forward, models/vgg/vgg.py:69-92) up to conv index n_conv-1 (+ trailing pool when
+ * with_last_pool); activations stay in the workspace, see isx_nst_feature. */
+int isx_nst_forward(const isx_nst_config* cfg, const isx_nst_buffers* bufs, const float* x, int with_last_pool,
+                    isx_stream stream);
+/* device pointer / shape of a stored activation: kind 0 = ReLU output of conv `idx`, 1 = output of pool `idx` (0..4) */
+int isx_nst_feature(const isx_nst_config* cfg, const isx_nst_buffers* bufs, int kind, int idx, isx_bf16** ptr,
+                    int32_t* h, int32_t* w, int32_t* c);
+/* closure evaluation: loss_c/loss_s double [B] (unweighted, per image), grad fp32 [B,xc,H,W] = d(alpha c + beta s)/dx */
+int isx_nst_eval(const isx_nst_config* cfg, const isx_nst_buffers* bufs, const float* x, double* loss_c,
+                 double* loss_s, float* grad, isx_stream stream);
+
+/* ---- K10: iris mask + bounding box (pipelines.py:139-165 mask_and_crop_iris; utils.py:44-72 crop_image) --
+ * x fp32 [B,1,H,W]; seg int64 [B,1,H,W] label map or NULL; m = (seg == label) & (x <= threshold) (either
+ * test can be off: seg NULL / use_threshold 0); mask uint8 [B,1,H,W] (0/1) and xm = x*m are optional
+ * outputs; bbox int32 [B,4] = (x_min, y_min, x_max, y_max) = (row_min, col_min, row_max, col_max) of the
+ * NONZERO PIXELS of x*m, inclusive (utils.py:57-64).  No nonzero pixel -> row_max = -1 (the reference
+ * raises on the empty min()).  Bit-exact integer work. */
+int isx_mask_bbox(const float* x, const int64_t* seg, int label, int use_threshold, float threshold, uint8_t* mask,
+                  float* xm, int32_t* bbox, int B, int H, int W, isx_stream stream);
+/* torchvision v2 Resize (bilinear, antialias=True) of the window src_bbox (or the whole image when NULL) of
+ * src fp32 [B,src_c,SH,SW] to dst fp32 [B,dst_c,DH,DW]; src_c == 3 is converted to gray first
+ * (rgb_to_grayscale, …2019.py:112); the single result channel is replicated dst_c times (…2019.py:79). */
+int isx_resize_bilinear_aa(const float* src, int src_c, int SH, int SW, const int32_t* src_bbox, float* dst, int dst_c,
+                           int DH, int DW, int B, isx_stream stream);
+/* ---- K9: composite (…2019.py:111-130, …2020.py:121-139): gray(new_iris) -> Resize(bbox shape) -> * mask ->
+ * frames[bbox] = frames[bbox] * ~mask + new, in place.  new_iris fp32 [B,src_c,SH,SW], frames fp32 [B,1,H,W],
+ * mask uint8 [B,1,H,W], bbox int32 [B,4]. */
+int isx_composite(const float* new_iris, int src_c, int SH, int SW, float* frames, const uint8_t* mask,
+                  const int32_t* bbox, int B, int H, int W, isx_stream stream);
+
+/* ---- measurement hooks (bench.py) -------------------------------------------------------------
+ * isx_launch_count: kernels launched by this library since load.  isx_prof_enable(1) brackets every launch
+ * of the tensor-core conv (family 0), Gram (1) and L-BFGS pass (2) kernels with CUDA events on the launching
+ * stream; after a device sync isx_prof_collect fills out[3*family + {0,1,2}] = {launches, total ms,
+ * total algorithmic work (FLOPs for 0/1, bytes for 2)}. */
+unsigned long long isx_launch_count(void);
+int isx_prof_enable(int on);
+int isx_prof_collect(double* out, int n_out);
 
 #ifdef __cplusplus
 }

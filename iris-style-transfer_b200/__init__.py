@@ -4,3 +4,13 @@ The arithmetic lives in libisx.so (hand-written CUDA, C ABI in include/isx.h); t
 host-side mirror of the reference's Python surface (pipelines.py, utils.py, models/vgg/vgg.py)."""
 from . import _lib  # noqa: F401
 from . import synthetic  # noqa: F401
+
+try:  # torch-dependent surface (the ctypes layer and the synthetic generators import without torch)
+    from .pipelines import (composite_irises, crop_resize_irises, iris_masks_and_bboxes, mask_and_crop_iris,  # noqa: F401
+                            nst)
+    from .utils import (ContentLoss_L2, GramMatrix, StyleLoss_BN, StyleLoss_Gram, crop_image,  # noqa: F401
+                        style_features)
+    from .vgg import VGG19, random_vgg19_weights  # noqa: F401
+    from . import features, sharding  # noqa: F401
+except ImportError:  # pragma: no cover
+    pass

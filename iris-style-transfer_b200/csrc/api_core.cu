@@ -78,3 +78,76 @@ int isx_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint6
   }
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// launch counter and per-family CUDA-event timing (used by bench.py; off by default)
+// ---------------------------------------------------------------------------------------------
+#include <vector>
+unsigned long long g_isx_launches = 0;
+
+namespace {
+struct ProfRec { cudaEvent_t e0, e1; int family; double work; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_pool;
+size_t g_pool_next = 0;
+cudaEvent_t g_open[ISX_PROF_FAMILIES];
+double g_open_work[ISX_PROF_FAMILIES];
+bool g_is_open[ISX_PROF_FAMILIES] = {false, false, false};
+const size_t kMaxRecs = 32768;
+
+cudaEvent_t pool_event() {
+  if (g_pool_next == g_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    g_pool.push_back(e);
+  }
+  return g_pool[g_pool_next++];
+}
+}  // namespace
+
+void isx_prof_begin(int family, double work, cudaStream_t s) {
+  if (!g_prof_on || g_prof.size() >= kMaxRecs) return;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &cs);
+  if (cs != cudaStreamCaptureStatusNone) return;
+  g_open[family] = pool_event();
+  g_open_work[family] = work;
+  g_is_open[family] = true;
+  cudaEventRecord(g_open[family], s);
+}
+void isx_prof_end(int family, cudaStream_t s) {
+  if (!g_prof_on || !g_is_open[family]) return;
+  ProfRec r;
+  r.e0 = g_open[family];
+  r.e1 = pool_event();
+  r.family = family;
+  r.work = g_open_work[family];
+  cudaEventRecord(r.e1, s);
+  g_prof.push_back(r);
+  g_is_open[family] = false;
+}
+
+extern "C" unsigned long long isx_launch_count(void) { return g_isx_launches; }
+extern "C" int isx_prof_enable(int on) {
+  g_prof_on = on != 0;
+  g_prof.clear();
+  g_pool_next = 0;
+  for (int f = 0; f < ISX_PROF_FAMILIES; ++f) g_is_open[f] = false;
+  return 0;
+}
+// After a device synchronisation: per family {launches, total ms, total work (FLOPs or bytes)}; out[3*family + k].
+extern "C" int isx_prof_collect(double* out, int n_out) {
+  ISX_REQUIRE(out && n_out >= 3 * ISX_PROF_FAMILIES, "isx_prof_collect: need %d doubles", 3 * ISX_PROF_FAMILIES);
+  for (int i = 0; i < 3 * ISX_PROF_FAMILIES; ++i) out[i] = 0.0;
+  for (const ProfRec& r : g_prof) {
+    float ms = 0.f;
+    ISX_CHECK_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    out[3 * r.family + 0] += 1.0;
+    out[3 * r.family + 1] += ms;
+    out[3 * r.family + 2] += r.work;
+  }
+  g_prof.clear();
+  g_pool_next = 0;
+  return 0;
+}

@@ -309,7 +309,9 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
   const long grid = ((sp_tiles + MT - 1) / MT) * p.n_tiles;
   auto kern = conv_tc_kernel<BN, MT>;
   ISX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  isx_prof_begin(ISX_PROF_CONV, 2.0 * a.ntaps * a.Cin * a.Cout * static_cast<double>(a.B) * a.H * a.W, stream);
   kern<<<(unsigned)grid, 192, smem_bytes, stream>>>(tmA, tmB, tmO, p);
+  isx_prof_end(ISX_PROF_CONV, stream);
   ISX_LAUNCH_CHECK();
   return 0;
 }
@@ -320,17 +322,23 @@ int conv_tc(const ConvArgs& a, cudaStream_t stream) {
   ISX_REQUIRE(a.B > 0 && a.H > 0 && a.W > 0, "conv_tc: empty input");
   ISX_REQUIRE((a.aff_a == nullptr) || (a.mask_act != nullptr), "conv_tc: affine tap gradient needs the activation");
   int bn = a.force_bn, mt = a.force_mt;
+  int st = a.force_stages;
   if (bn == 0) {
+    // Measured on B200 (profiles/r01_conv_tile_sweep.txt): two pipeline stages and >= 2 co-resident CTAs per SM
+    // (one CTA's epilogue overlaps the other's main loop) beat deeper pipelines with one CTA per SM.
+    //   Cout  64: BN  64, two M-tiles per CTA (the weight slab is shared by 256 pixels)
+    //   Cout 128: BN 128, two M-tiles
+    //   Cout 256+: BN 256, one M-tile
     bn = a.Cout % 256 == 0 ? 256 : (a.Cout % 128 == 0 ? 128 : 64);
-    mt = a.per_image_weights ? 1 : 2;
+    mt = (bn == 256 || a.per_image_weights) ? 1 : 2;
+    if (st == 0) st = 2;
     // small problems: prefer more CTAs over bigger tiles
     const long pix_tiles = (static_cast<long>(a.B) * a.H * a.W + 127) / 128;
     auto ctas = [&](int BN_, int MT_) { return ((pix_tiles + MT_ - 1) / MT_) * (a.Cout / BN_); };
     if (ctas(bn, mt) < 2 * kNumSMs && mt == 2) mt = 1;
-    if (ctas(bn, mt) < kNumSMs && bn == 256) bn = 128;
+    if (ctas(bn, mt) < 2 * kNumSMs && bn == 256) bn = 128;
   }
   if (mt == 0) mt = 1;
-  const int st = a.force_stages;
 #define ISX_CONV_CASE(BN_, MT_) \
   if (bn == BN_ && mt == MT_) return launch_conv<BN_, MT_>(a, st, stream);
   ISX_CONV_CASE(64, 1) ISX_CONV_CASE(64, 2) ISX_CONV_CASE(128, 1) ISX_CONV_CASE(128, 2)

@@ -170,7 +170,9 @@ static int launch_gram(const __nv_bfloat16* feat, int B, int HW, int C, int spli
   auto kern = gram_tc_kernel<NB, KP>;
   ISX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   const long grid = static_cast<long>(B) * p.mblks * splits;
+  isx_prof_begin(ISX_PROF_GRAM, 2.0 * C * C * static_cast<double>(B) * HW, stream);
   kern<<<(unsigned)grid, 192, smem_bytes, stream>>>(tmF, p);
+  isx_prof_end(ISX_PROF_GRAM, stream);
   ISX_LAUNCH_CHECK();
   return 0;
 }

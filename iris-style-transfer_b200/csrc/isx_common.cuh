@@ -30,7 +30,18 @@ void isx_set_error(const char* fmt, ...);
     }                            \
   } while (0)
 
-#define ISX_LAUNCH_CHECK() ISX_CHECK_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this: error check + launch counter (bench.py's gpu_launches)
+extern unsigned long long g_isx_launches;
+#define ISX_LAUNCH_CHECK()               \
+  do {                                   \
+    ++g_isx_launches;                    \
+    ISX_CHECK_CUDA(cudaGetLastError());  \
+  } while (0)
+
+// optional CUDA-event timing of one kernel family on the launching stream (bench.py roofline leg)
+void isx_prof_begin(int family, double work, cudaStream_t s);
+void isx_prof_end(int family, cudaStream_t s);
+enum { ISX_PROF_CONV = 0, ISX_PROF_GRAM = 1, ISX_PROF_LBFGS = 2, ISX_PROF_FAMILIES = 3 };
 
 // Encode a tiled bf16 tensor map (rank <= 5).  dims/strides innermost first; strides in BYTES
 // for dims 1..rank-1 (dim 0 is contiguous).  swizzle128: CU_TENSOR_MAP_SWIZZLE_128B else NONE.

@@ -424,12 +424,14 @@ int lbfgs_tick(float* x, const float* g, float* g_prev, float* S, float* Y, Lbfg
   const int nblk = lbfgs_nblk(N);
   dim3 grid(nblk, P);
   const size_t sm1 = static_cast<size_t>(M1) * 8 * 4 * sizeof(float);
+  isx_prof_begin(ISX_PROF_LBFGS, 0.0, s);  // both history passes + control; bytes are derived by the caller
   lbfgs_dots_kernel<<<grid, kDotThreads, sm1, s>>>(g, g_prev, S, Y, states, N, M1, nblk, part, ext);
   ISX_LAUNCH_CHECK();
   lbfgs_control_kernel<<<P, 128, 0, s>>>(states, mats, part, ext, loss_c, loss_s, images_per_problem, M1, nblk, cfg,
                                          hist_c, hist_s, tick, P);
   ISX_LAUNCH_CHECK();
   lbfgs_update_kernel<<<grid, kDotThreads, 0, s>>>(x, g, g_prev, S, Y, states, N, M1);
+  isx_prof_end(ISX_PROF_LBFGS, s);
   ISX_LAUNCH_CHECK();
   return 0;
 }

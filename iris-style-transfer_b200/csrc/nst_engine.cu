@@ -1,0 +1,352 @@
+// Host-side driver of one NST closure evaluation (pipelines.py:80-91): VGG-19 forward to the deepest
+// tap, style/content losses, backward to the image -- a fixed sequence of libisx kernels on one
+// stream (graph-capturable: no allocation, no host synchronisation).  Also the L-BFGS C-ABI glue.
+#include <vector>
+
+#include "../../include/isx.h"
+#include "isx_common.cuh"
+#include "isx_internal.h"
+#include "isx_kernels.h"
+#include "lbfgs_state.h"
+
+using namespace isx;
+typedef __nv_bfloat16 bf16;
+
+static inline cudaStream_t S(isx_stream s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// torchvision vgg19 cfg "E" (torchvision/models/vgg.py:94): channels per conv, pool after convs 1,3,7,11,15
+static const int kCout[16] = {64, 64, 128, 128, 256, 256, 256, 256, 512, 512, 512, 512, 512, 512, 512, 512};
+static const int kCin[16] = {3, 64, 64, 128, 128, 256, 256, 256, 256, 512, 512, 512, 512, 512, 512, 512};
+static const int kLevel[16] = {0, 0, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4};  // resolution level = #pools before
+static inline bool pool_after(int i) { return i == 1 || i == 3 || i == 7 || i == 11 || i == 15; }
+
+namespace {
+struct Layout {
+  int B, H[6], W[6];
+  size_t act[16];     // byte offsets of ReLU outputs
+  size_t pool[5];     // byte offsets of pool outputs
+  size_t gradA, gradB, tapbuf;
+  size_t cgrad[ISX_MAX_TAPS];
+  size_t gram_ws, D[ISX_MAX_TAPS], sums, aff_a[ISX_MAX_TAPS], aff_b[ISX_MAX_TAPS];
+  size_t total;
+};
+
+size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+
+int make_layout(const isx_nst_config* c, Layout* L) {
+  ISX_REQUIRE(c->B > 0 && c->H > 0 && c->W > 0, "nst: empty batch");
+  ISX_REQUIRE(c->n_conv >= 1 && c->n_conv <= 16, "nst: n_conv %d out of range", c->n_conv);
+  ISX_REQUIRE(c->n_style >= 0 && c->n_style <= ISX_MAX_TAPS && c->n_content >= 0 && c->n_content <= ISX_MAX_TAPS,
+              "nst: too many taps");
+  L->B = c->B;
+  L->H[0] = c->H; L->W[0] = c->W;
+  for (int l = 1; l < 6; ++l) { L->H[l] = L->H[l - 1] / 2; L->W[l] = L->W[l - 1] / 2; }
+  const int deepest_level = kLevel[c->n_conv - 1];
+  ISX_REQUIRE(L->H[deepest_level] >= 1 && L->W[deepest_level] >= 1, "nst: image %dx%d too small for %d convs", c->H,
+              c->W, c->n_conv);
+  size_t off = 0;
+  size_t max_act = 0, max_tap = 0;
+  for (int i = 0; i < 16; ++i) {
+    L->act[i] = off;
+    if (i < c->n_conv || true) {
+      size_t bytes = static_cast<size_t>(c->B) * L->H[kLevel[i]] * L->W[kLevel[i]] * kCout[i] * 2;
+      if (i < c->n_conv) { off += align_up(bytes); max_act = std::max(max_act, bytes); }
+    }
+  }
+  for (int k = 0; k < 5; ++k) {
+    L->pool[k] = off;
+    const int conv_before[5] = {1, 3, 7, 11, 15};
+    if (conv_before[k] < c->n_conv)
+      off += align_up(static_cast<size_t>(c->B) * L->H[k + 1] * L->W[k + 1] * kCout[conv_before[k]] * 2);
+  }
+  for (int t = 0; t < c->n_style; ++t) {
+    const int i = c->style_conv[t];
+    ISX_REQUIRE(i >= 0 && i < c->n_conv, "nst: style tap conv %d beyond n_conv %d", i, c->n_conv);
+    max_tap = std::max(max_tap, static_cast<size_t>(c->B) * L->H[kLevel[i]] * L->W[kLevel[i]] * kCout[i] * 2);
+  }
+  L->gradA = off; off += align_up(max_act);
+  L->gradB = off; off += align_up(max_act);
+  L->tapbuf = off; off += align_up(std::max<size_t>(max_tap, 256));
+  for (int t = 0; t < c->n_content; ++t) {
+    const int i = c->content_conv[t];
+    ISX_REQUIRE(i >= 0 && i < c->n_conv, "nst: content tap conv %d beyond n_conv %d", i, c->n_conv);
+    L->cgrad[t] = off;
+    off += align_up(static_cast<size_t>(c->B) * L->H[kLevel[i]] * L->W[kLevel[i]] * kCout[i] * 2);
+  }
+  size_t gram_ws = 256;
+  for (int t = 0; t < c->n_style; ++t) {
+    const int i = c->style_conv[t];
+    const int C = kCout[i];
+    const int HW = L->H[kLevel[i]] * L->W[kLevel[i]];
+    gram_ws = std::max<size_t>(gram_ws, static_cast<size_t>(gram_pick_splits(c->B, HW, C)) * c->B * C * C * 4);
+    L->D[t] = off; off += align_up(static_cast<size_t>(c->B) * C * C * 2);
+    L->aff_a[t] = off; off += align_up(static_cast<size_t>(c->B) * C * 4);
+    L->aff_b[t] = off; off += align_up(static_cast<size_t>(c->B) * C * 4);
+  }
+  L->gram_ws = off; off += align_up(gram_ws);
+  L->sums = off; off += align_up(static_cast<size_t>(c->B) * 512 * 2 * 8);
+  L->total = off;
+  return 0;
+}
+
+inline bf16* at(const isx_nst_buffers* b, size_t off) { return reinterpret_cast<bf16*>(static_cast<char*>(b->workspace) + off); }
+inline float* atf(const isx_nst_buffers* b, size_t off) { return reinterpret_cast<float*>(static_cast<char*>(b->workspace) + off); }
+
+int style_tap_of(const isx_nst_config* c, int conv) {
+  for (int t = 0; t < c->n_style; ++t) if (c->style_conv[t] == conv) return t;
+  return -1;
+}
+int content_tap_of(const isx_nst_config* c, int conv) {
+  for (int t = 0; t < c->n_content; ++t) if (c->content_conv[t] == conv) return t;
+  return -1;
+}
+
+// forward through conv `i` (input selection included)
+int run_conv_fwd(const isx_nst_config* c, const isx_nst_buffers* b, const Layout& L, int i, const float* x,
+                 cudaStream_t s) {
+  const int lv = kLevel[i];
+  if (i == 0)
+    return conv1_1_fwd(x, c->xc, c->mask_b ? b->input_mask : nullptr, c->mask_b, b->w0, b->bias[0], at(b, L.act[0]), c->B,
+                       L.H[0], L.W[0], s);
+  const bool first_of_block = (i == 2 || i == 4 || i == 8 || i == 12);
+  const bf16* in = first_of_block ? at(b, L.pool[lv - 1]) : at(b, L.act[i - 1]);
+  ISX_REQUIRE(b->w_fwd[i] != nullptr, "nst: packed forward weights of conv %d missing", i);
+  ConvArgs a;
+  a.in = in; a.weight = reinterpret_cast<const bf16*>(b->w_fwd[i]); a.out = at(b, L.act[i]);
+  a.B = c->B; a.H = L.H[lv]; a.W = L.W[lv]; a.Cin = kCin[i]; a.Cout = kCout[i]; a.ntaps = 9;
+  a.bias = b->bias[i]; a.relu = 1;
+  return conv_tc(a, s);
+}
+}  // namespace
+
+extern "C" int64_t isx_nst_workspace_bytes(const isx_nst_config* cfg) {
+  Layout L;
+  if (!cfg || make_layout(cfg, &L)) return -1;
+  return static_cast<int64_t>(L.total);
+}
+
+extern "C" int isx_nst_forward(const isx_nst_config* c, const isx_nst_buffers* b, const float* x, int with_last_pool,
+                               isx_stream stream) {
+  ISX_REQUIRE(c && b && x && b->workspace, "isx_nst_forward: null pointer");
+  Layout L;
+  if (int rc = make_layout(c, &L)) return rc;
+  cudaStream_t s = S(stream);
+  for (int i = 0; i < c->n_conv; ++i) {
+    if (int rc = run_conv_fwd(c, b, L, i, x, s)) return rc;
+    if (pool_after(i) && (i + 1 < c->n_conv || with_last_pool)) {
+      const int lv = kLevel[i];
+      ISX_REQUIRE(L.H[lv] >= 2 && L.W[lv] >= 2, "nst: cannot pool a %dx%d map", L.H[lv], L.W[lv]);
+      if (int rc = maxpool_fwd(at(b, L.act[i]), at(b, L.pool[lv]), c->B, L.H[lv], L.W[lv], kCout[i], s)) return rc;
+    }
+  }
+  return 0;
+}
+
+extern "C" int isx_nst_feature(const isx_nst_config* c, const isx_nst_buffers* b, int kind, int idx, isx_bf16** ptr,
+                               int32_t* h, int32_t* w, int32_t* ch) {
+  ISX_REQUIRE(c && b && ptr && h && w && ch, "isx_nst_feature: null pointer");
+  Layout L;
+  if (int rc = make_layout(c, &L)) return rc;
+  if (kind == 0) {
+    ISX_REQUIRE(idx >= 0 && idx < c->n_conv, "isx_nst_feature: conv %d not computed (n_conv=%d)", idx, c->n_conv);
+    *ptr = reinterpret_cast<isx_bf16*>(at(b, L.act[idx]));
+    *h = L.H[kLevel[idx]]; *w = L.W[kLevel[idx]]; *ch = kCout[idx];
+  } else {
+    const int conv_before[5] = {1, 3, 7, 11, 15};
+    ISX_REQUIRE(idx >= 0 && idx < 5 && conv_before[idx] < c->n_conv, "isx_nst_feature: pool %d not computed", idx);
+    *ptr = reinterpret_cast<isx_bf16*>(at(b, L.pool[idx]));
+    *h = L.H[idx + 1]; *w = L.W[idx + 1]; *ch = kCout[conv_before[idx]];
+  }
+  return 0;
+}
+
+extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, const float* x, double* loss_c,
+                            double* loss_s, float* grad, isx_stream stream) {
+  ISX_REQUIRE(c && b && x && loss_c && loss_s && grad && b->workspace, "isx_nst_eval: null pointer");
+  ISX_REQUIRE(c->n_style + c->n_content > 0, "isx_nst_eval: no loss taps");
+  Layout L;
+  if (int rc = make_layout(c, &L)) return rc;
+  cudaStream_t s = S(stream);
+  const int B = c->B;
+  const int deepest = c->n_conv - 1;
+  ISX_REQUIRE(style_tap_of(c, deepest) >= 0 || content_tap_of(c, deepest) >= 0, "isx_nst_eval: conv %d is not tapped",
+              deepest);
+  ISX_CHECK_CUDA(cudaMemsetAsync(loss_c, 0, sizeof(double) * B, s));
+  ISX_CHECK_CUDA(cudaMemsetAsync(loss_s, 0, sizeof(double) * B, s));
+
+  // ---------------- forward + losses ----------------
+  for (int i = 0; i < c->n_conv; ++i) {
+    if (int rc = run_conv_fwd(c, b, L, i, x, s)) return rc;
+    const int lv = kLevel[i];
+    const int C = kCout[i];
+    const long HW = static_cast<long>(L.H[lv]) * L.W[lv];
+    if (pool_after(i) && i + 1 < c->n_conv) {
+      ISX_REQUIRE(L.H[lv] >= 2 && L.W[lv] >= 2, "nst: cannot pool a %dx%d map", L.H[lv], L.W[lv]);
+      if (int rc = maxpool_fwd(at(b, L.act[i]), at(b, L.pool[lv]), B, L.H[lv], L.W[lv], C, s)) return rc;
+    }
+    const int st = style_tap_of(c, i);
+    if (st >= 0) {
+      const double w = c->style_w[st];
+      if (c->style_mode == 0) {  // StyleLoss_Gram (utils.py:317-322); GramMatrix n = C*H*W (utils.py:254)
+        ISX_REQUIRE(b->gram_target[st], "nst: Gram target %d missing", st);
+        const double inv_n = 1.0 / (static_cast<double>(C) * HW);
+        int rc = gram_tc_partial(at(b, L.act[i]), B, static_cast<int>(HW), C, gram_pick_splits(B, static_cast<int>(HW), C),
+                                 atf(b, L.gram_ws), s);
+        if (rc) return rc;
+        rc = gram_finalize(atf(b, L.gram_ws), B, gram_pick_splits(B, static_cast<int>(HW), C), C,
+                           static_cast<float>(inv_n), nullptr, b->gram_target[st], c->style_target_b, 0.25 * w, loss_s,
+                           static_cast<float>(c->s_weight * w * inv_n), at(b, L.D[st]), s);
+        if (rc) return rc;
+      } else {  // StyleLoss_BN (utils.py:350-355)
+        ISX_REQUIRE(b->bn_target_mean[st] && b->bn_target_std[st], "nst: BN target %d missing", st);
+        ISX_REQUIRE(HW >= 2, "nst: unbiased std needs >= 2 pixels at conv %d", i);
+        double* sums = reinterpret_cast<double*>(static_cast<char*>(b->workspace) + L.sums);
+        ISX_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * B * C * 2, s));
+        int rc = chan_sums(at(b, L.act[i]), B, HW, C, sums, s);
+        if (rc) return rc;
+        rc = bn_finalize(sums, B, C, HW, nullptr, nullptr, b->bn_target_mean[st], b->bn_target_std[st],
+                         c->style_target_b, w / C, c->s_weight * w / C, loss_s, atf(b, L.aff_a[st]), atf(b, L.aff_b[st]), s);
+        if (rc) return rc;
+      }
+    }
+    const int ct = content_tap_of(c, i);
+    if (ct >= 0) {  // ContentLoss_L2 (utils.py:285-290): 0.5 * w * mean((p-t)^2)
+      ISX_REQUIRE(b->content_target[ct], "nst: content target %d missing", ct);
+      const long per_image = HW * C;
+      const double denom = static_cast<double>(per_image) * (c->coupled ? B : 1);
+      int rc = content_mse(at(b, L.act[i]), reinterpret_cast<const bf16*>(b->content_target[ct]), c->content_target_b,
+                           at(b, L.cgrad[ct]), B, per_image, 0.5 * c->content_w[ct] / denom,
+                           static_cast<float>(c->c_weight * c->content_w[ct] / denom), loss_c, s);
+      if (rc) return rc;
+    }
+  }
+
+  // ---------------- backward ----------------
+  // gm = masked gradient w.r.t. the ReLU output of conv i (ready to be fed to conv i's dgrad)
+  bf16* ping = at(b, L.gradA);
+  bf16* pong = at(b, L.gradB);
+  bf16* tapbuf = at(b, L.tapbuf);
+  const bf16* gm = nullptr;
+  {
+    const int i = deepest, lv = kLevel[i], C = kCout[i];
+    const long HW = static_cast<long>(L.H[lv]) * L.W[lv];
+    const int st = style_tap_of(c, i), ct = content_tap_of(c, i);
+    if (ct >= 0 && st < 0) {
+      gm = at(b, L.cgrad[ct]);  // already masked by content_mse
+    } else {
+      const bf16* gsrc = ct >= 0 ? at(b, L.cgrad[ct]) : nullptr;
+      if (c->style_mode == 0) {
+        ConvArgs a;  // Gram backward dF = F . D  (+ mask when it is the only source)
+        a.in = at(b, L.act[i]); a.weight = at(b, L.D[st]); a.out = gsrc ? tapbuf : ping;
+        a.B = B; a.H = L.H[lv]; a.W = L.W[lv]; a.Cin = C; a.Cout = C; a.ntaps = 1; a.per_image_weights = true;
+        a.mask_act = gsrc ? nullptr : at(b, L.act[i]);
+        if (int rc = conv_tc(a, s)) return rc;
+        if (gsrc) {
+          if (int rc = tap_add_mask(gsrc, tapbuf, nullptr, nullptr, at(b, L.act[i]), ping, B, HW, C, s)) return rc;
+        }
+      } else {
+        if (int rc = tap_add_mask(gsrc, nullptr, atf(b, L.aff_a[st]), atf(b, L.aff_b[st]), at(b, L.act[i]), ping, B, HW, C, s))
+          return rc;
+      }
+      gm = ping;
+      std::swap(ping, pong);
+    }
+  }
+  for (int i = deepest; i >= 1; --i) {
+    const int lv = kLevel[i];
+    const int j = i - 1;  // layer below
+    const int lvj = kLevel[j];
+    const int Cj = kCout[j];
+    const long HWj = static_cast<long>(L.H[lvj]) * L.W[lvj];
+    const int st = style_tap_of(c, j), ct = content_tap_of(c, j);
+    const bool through_pool = pool_after(j);
+    // tap gradient of layer j (computed before the dgrad that consumes it)
+    const bf16* add = nullptr;
+    const float *aa = nullptr, *ab = nullptr;
+    if (st >= 0 && c->style_mode == 0) {
+      ConvArgs a;
+      a.in = at(b, L.act[j]); a.weight = at(b, L.D[st]); a.out = tapbuf;
+      a.B = B; a.H = L.H[lvj]; a.W = L.W[lvj]; a.Cin = Cj; a.Cout = Cj; a.ntaps = 1; a.per_image_weights = true;
+      if (int rc = conv_tc(a, s)) return rc;
+      add = tapbuf;
+      if (ct >= 0) {  // both taps on one layer: fold the content gradient into the tap buffer
+        if (int rc = tap_add_mask(at(b, L.cgrad[ct]), tapbuf, nullptr, nullptr, at(b, L.act[j]), tapbuf, B, HWj, Cj, s)) return rc;
+      }
+    } else if (st >= 0) {
+      aa = atf(b, L.aff_a[st]); ab = atf(b, L.aff_b[st]);
+      if (ct >= 0) add = at(b, L.cgrad[ct]);
+    } else if (ct >= 0) {
+      add = at(b, L.cgrad[ct]);
+    }
+    ConvArgs a;
+    a.in = gm; a.weight = reinterpret_cast<const bf16*>(b->w_dgrad[i]);
+    ISX_REQUIRE(b->w_dgrad[i] != nullptr, "nst: packed dgrad weights of conv %d missing", i);
+    a.B = B; a.H = L.H[lv]; a.W = L.W[lv]; a.Cin = kCout[i]; a.Cout = kCin[i]; a.ntaps = 9;
+    a.out = ping;
+    if (!through_pool) {
+      a.mask_act = at(b, L.act[j]); a.add_buf = add; a.aff_a = aa; a.aff_b = ab;
+      if (int rc = conv_tc(a, s)) return rc;
+      gm = ping;
+      std::swap(ping, pong);
+    } else {
+      if (int rc = conv_tc(a, s)) return rc;  // gradient w.r.t. the pooled map: no ReLU, no tap
+      if (int rc = maxpool_bwd(ping, at(b, L.act[j]), pong, B, L.H[lvj], L.W[lvj], Cj, s)) return rc;
+      if (add || aa) {
+        if (int rc = tap_add_mask(pong, add, aa, ab, at(b, L.act[j]), ping, B, HWj, Cj, s)) return rc;
+        gm = ping;
+        std::swap(ping, pong);
+      } else {
+        gm = pong;  // next dgrad writes into ping
+      }
+    }
+  }
+  return conv1_1_dgrad(gm, b->w0, c->mask_b ? b->input_mask : nullptr, c->mask_b, grad, c->xc, B, L.H[0], L.W[0], s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// L-BFGS C-ABI glue
+// ---------------------------------------------------------------------------------------------
+extern "C" int64_t isx_lbfgs_state_bytes(int P) { return static_cast<int64_t>(P) * sizeof(LbfgsState); }
+extern "C" int64_t isx_lbfgs_mats_bytes(int P, int history) {
+  return static_cast<int64_t>(P) * 3 * (history + 1) * (history + 1) * 8;
+}
+extern "C" int64_t isx_lbfgs_scratch_bytes(int P, int64_t N, int history) {
+  const int64_t nblk = lbfgs_nblk(N);
+  return P * nblk * (static_cast<int64_t>(history + 1) * 4 + 4) * 4 + 256;
+}
+extern "C" int isx_lbfgs_init(void* state, int P, isx_stream stream) {
+  ISX_REQUIRE(state && P > 0, "isx_lbfgs_init: bad arguments");
+  return lbfgs_init(static_cast<LbfgsState*>(state), P, S(stream));
+}
+extern "C" int isx_lbfgs_tick(float* x, const float* grad, float* grad_prev, float* Sh, float* Yh, void* state,
+                              void* mats, void* scratch, const double* loss_c, const double* loss_s,
+                              int images_per_problem, int P, int64_t N, const isx_lbfgs_config* cfg, double* hist_c,
+                              double* hist_s, int tick, isx_stream stream) {
+  ISX_REQUIRE(x && grad && grad_prev && Sh && Yh && state && mats && scratch && loss_c && loss_s && cfg && hist_c && hist_s,
+              "isx_lbfgs_tick: null pointer");
+  ISX_REQUIRE(cfg->history >= 1 && cfg->history <= 100, "isx_lbfgs_tick: history %d must be in 1..100", cfg->history);
+  LbfgsConfig lc;
+  lc.epochs = cfg->epochs; lc.max_iter = cfg->max_iter; lc.max_eval = cfg->max_eval; lc.history = cfg->history;
+  lc.lr = cfg->lr; lc.tolerance_grad = cfg->tolerance_grad; lc.tolerance_change = cfg->tolerance_change;
+  lc.c_weight = cfg->c_weight; lc.s_weight = cfg->s_weight;
+  const int nblk = lbfgs_nblk(N);
+  float* part = static_cast<float*>(scratch);
+  float* ext = part + static_cast<int64_t>(P) * nblk * (cfg->history + 1) * 4;
+  return lbfgs_tick(x, grad, grad_prev, Sh, Yh, static_cast<LbfgsState*>(state), static_cast<double*>(mats), part, ext,
+                    loss_c, loss_s, images_per_problem, P, N, lc, hist_c, hist_s, tick, S(stream));
+}
+
+__global__ void done_flags_kernel(const LbfgsState* st, int P, int32_t* out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P) out[p] = st[p].done ? st[p].func_evals : 0;
+}
+extern "C" int isx_lbfgs_done_flags(const void* state, int P, int32_t* done_out, isx_stream stream) {
+  ISX_REQUIRE(state && done_out, "isx_lbfgs_done_flags: null pointer");
+  done_flags_kernel<<<(P + 127) / 128, 128, 0, S(stream)>>>(static_cast<const LbfgsState*>(state), P, done_out);
+  ISX_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int isx_clamp01(float* x, int64_t n, isx_stream stream) {
+  ISX_REQUIRE(x && n >= 0, "isx_clamp01: bad arguments");
+  return clamp01(x, n, S(stream));
+}

@@ -1,0 +1,232 @@
+"""Host-side plumbing around libisx's fused NST driver (isx_nst_forward / isx_nst_eval /
+isx_lbfgs_tick): ctypes mirrors of the C structs, weight packing, workspace ownership.
+PyTorch supplies device memory and streams only -- no torch op touches the data path."""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+MAX_TAPS = 8
+N_CONVS = 16
+
+# models/vgg/vgg.py:6-10 (torchvision vgg19.features indices)
+VGG19_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512, "M"]
+VGG19_LAYERS: Dict[str, int] = {}
+CONV_OF_FEATURE_INDEX: Dict[int, int] = {}   # features index (conv or relu) -> conv ordinal 0..15
+POOL_OF_FEATURE_INDEX: Dict[int, int] = {}   # features index of a pool -> pool ordinal 0..4
+_i, _blk, _sub, _c, _p = 0, 1, 1, 0, 0
+for _v in VGG19_CFG:
+    if _v == "M":
+        VGG19_LAYERS["pool%d" % _blk] = _i
+        POOL_OF_FEATURE_INDEX[_i] = _p
+        _p += 1
+        _i += 1
+        _blk += 1
+        _sub = 1
+    else:
+        VGG19_LAYERS["conv%d_%d" % (_blk, _sub)] = _i
+        VGG19_LAYERS["relu%d_%d" % (_blk, _sub)] = _i + 1
+        CONV_OF_FEATURE_INDEX[_i] = _c       # in-place ReLU: a conv tap aliases the ReLU output
+        CONV_OF_FEATURE_INDEX[_i + 1] = _c
+        _c += 1
+        _i += 2
+        _sub += 1
+CONV_COUT = [v for v in VGG19_CFG if v != "M"]
+
+
+class NstConfig(ctypes.Structure):
+    _fields_ = [
+        ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32), ("xc", ctypes.c_int32),
+        ("n_conv", ctypes.c_int32), ("style_mode", ctypes.c_int32),
+        ("n_style", ctypes.c_int32), ("style_conv", ctypes.c_int32 * MAX_TAPS), ("style_w", ctypes.c_float * MAX_TAPS),
+        ("n_content", ctypes.c_int32), ("content_conv", ctypes.c_int32 * MAX_TAPS),
+        ("content_w", ctypes.c_float * MAX_TAPS),
+        ("style_target_b", ctypes.c_int32), ("content_target_b", ctypes.c_int32),
+        ("coupled", ctypes.c_int32), ("mask_b", ctypes.c_int32),
+        ("c_weight", ctypes.c_double), ("s_weight", ctypes.c_double),
+    ]
+
+
+class NstBuffers(ctypes.Structure):
+    _fields_ = [
+        ("w0", ctypes.c_void_p),
+        ("bias", ctypes.c_void_p * N_CONVS),
+        ("w_fwd", ctypes.c_void_p * N_CONVS),
+        ("w_dgrad", ctypes.c_void_p * N_CONVS),
+        ("workspace", ctypes.c_void_p),
+        ("content_target", ctypes.c_void_p * MAX_TAPS),
+        ("gram_target", ctypes.c_void_p * MAX_TAPS),
+        ("bn_target_mean", ctypes.c_void_p * MAX_TAPS),
+        ("bn_target_std", ctypes.c_void_p * MAX_TAPS),
+        ("input_mask", ctypes.c_void_p),
+    ]
+
+
+class LbfgsConfig(ctypes.Structure):
+    _fields_ = [
+        ("epochs", ctypes.c_int32), ("max_iter", ctypes.c_int32), ("max_eval", ctypes.c_int32),
+        ("history", ctypes.c_int32), ("lr", ctypes.c_double), ("tolerance_grad", ctypes.c_double),
+        ("tolerance_change", ctypes.c_double), ("c_weight", ctypes.c_double), ("s_weight", ctypes.c_double),
+    ]
+
+
+class PackedVGG:
+    """VGG-19 conv parameters packed once for the device kernels (isx_pack_conv3x3_weights)."""
+
+    def __init__(self, weights: Sequence[Tuple[torch.Tensor, torch.Tensor]], device: torch.device):
+        assert len(weights) == N_CONVS, "expected the 16 (weight, bias) pairs of vgg19.features"
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.IsxError("iris_b200 runs on a CUDA B200 only (device=%s); there is no CPU path" % device)
+        _lib.call("isx_device_check", self.device.index or 0)
+        self.w0 = weights[0][0].detach().to(self.device, torch.float32).contiguous()
+        self.bias = [b.detach().to(self.device, torch.float32).contiguous() for _, b in weights]
+        self.w_fwd: List[Optional[torch.Tensor]] = [None]
+        self.w_dgrad: List[Optional[torch.Tensor]] = [None]
+        with torch.cuda.device(self.device):
+            for i in range(1, N_CONVS):
+                w = weights[i][0].detach().to(self.device, torch.float32).contiguous()
+                cout, cin = w.shape[:2]
+                wf = torch.empty(9, cout, cin, device=self.device, dtype=torch.bfloat16)
+                wd = torch.empty(9, cin, cout, device=self.device, dtype=torch.bfloat16)
+                _lib.call("isx_pack_conv3x3_weights", w, cout, cin, wf, wd, _lib.stream_ptr())
+                self.w_fwd.append(wf)
+                self.w_dgrad.append(wd)
+            torch.cuda.current_stream().synchronize()
+
+
+class NstEngine:
+    """One (batch shape, tap set) instance of the fused driver.  Owns the workspace."""
+
+    def __init__(self, packed: PackedVGG, B: int, H: int, W: int, xc: int, content_convs: Sequence[int],
+                 style_convs: Sequence[int], style_mode: int = 0, content_w: Optional[Sequence[float]] = None,
+                 style_w: Optional[Sequence[float]] = None, c_weight: float = 1.0, s_weight: float = 1.0,
+                 coupled: bool = False, n_conv: Optional[int] = None):
+        self.packed = packed
+        self.device = packed.device
+        cfg = NstConfig()
+        cfg.B, cfg.H, cfg.W, cfg.xc = B, H, W, xc
+        taps = list(content_convs) + list(style_convs)
+        cfg.n_conv = n_conv if n_conv is not None else (max(taps) + 1 if taps else N_CONVS)
+        cfg.style_mode = style_mode
+        if len(style_convs) > MAX_TAPS or len(content_convs) > MAX_TAPS:
+            raise ValueError("at most %d style and %d content layers" % (MAX_TAPS, MAX_TAPS))
+        cfg.n_style = len(style_convs)
+        cfg.n_content = len(content_convs)
+        for t, c in enumerate(style_convs):
+            cfg.style_conv[t] = c
+            cfg.style_w[t] = 1.0 if style_w is None else float(style_w[t])
+        for t, c in enumerate(content_convs):
+            cfg.content_conv[t] = c
+            cfg.content_w[t] = 1.0 if content_w is None else float(content_w[t])
+        cfg.style_target_b = B
+        cfg.content_target_b = B
+        cfg.coupled = int(coupled)
+        cfg.mask_b = 0
+        cfg.c_weight, cfg.s_weight = float(c_weight), float(s_weight)
+        self.cfg = cfg
+        nbytes = _lib.call_i64("isx_nst_workspace_bytes", ctypes.byref(cfg))
+        if nbytes < 0:
+            raise _lib.IsxError("isx_nst_workspace_bytes: " + _lib.load().isx_last_error().decode())
+        self.workspace = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
+        bufs = NstBuffers()
+        bufs.w0 = packed.w0.data_ptr()
+        for i in range(N_CONVS):
+            bufs.bias[i] = packed.bias[i].data_ptr()
+            bufs.w_fwd[i] = packed.w_fwd[i].data_ptr() if packed.w_fwd[i] is not None else None
+            bufs.w_dgrad[i] = packed.w_dgrad[i].data_ptr() if packed.w_dgrad[i] is not None else None
+        bufs.workspace = self.workspace.data_ptr()
+        self.bufs = bufs
+        self._keep: List[torch.Tensor] = []  # targets referenced by raw pointer
+        self.loss_c = torch.zeros(B, device=self.device, dtype=torch.float64)
+        self.loss_s = torch.zeros(B, device=self.device, dtype=torch.float64)
+
+    # ---- targets -------------------------------------------------------------------------
+    def set_input_mask(self, mask: Optional[torch.Tensor]):
+        if mask is None:
+            self.cfg.mask_b = 0
+            self.bufs.input_mask = None
+            return
+        m = mask.detach().to(self.device, torch.float32).contiguous()
+        if m.dim() == 3:
+            m = m[None]
+        assert m.shape[-2:] == (self.cfg.H, self.cfg.W) and m.shape[0] in (1, self.cfg.B)
+        self._keep.append(m)
+        self.cfg.mask_b = m.shape[0]
+        self.bufs.input_mask = m.data_ptr()
+
+    def set_content_targets(self, feats: Sequence[torch.Tensor]):
+        for t, f in enumerate(feats):
+            f = f.contiguous()
+            self._keep.append(f)
+            self.bufs.content_target[t] = f.data_ptr()
+        if feats:
+            self.cfg.content_target_b = feats[0].shape[0]
+
+    def set_gram_targets(self, grams: Sequence[torch.Tensor]):
+        for t, g in enumerate(grams):
+            g = g.to(torch.float32).contiguous()
+            self._keep.append(g)
+            self.bufs.gram_target[t] = g.data_ptr()
+        if grams:
+            self.cfg.style_target_b = grams[0].shape[0] if grams[0].dim() == 3 else 1
+
+    def set_bn_targets(self, means: Sequence[torch.Tensor], stds: Sequence[torch.Tensor]):
+        for t, (m, s) in enumerate(zip(means, stds)):
+            m, s = m.to(torch.float32).contiguous(), s.to(torch.float32).contiguous()
+            self._keep += [m, s]
+            self.bufs.bn_target_mean[t] = m.data_ptr()
+            self.bufs.bn_target_std[t] = s.data_ptr()
+        if means:
+            self.cfg.style_target_b = means[0].shape[0] if means[0].dim() == 2 else 1
+
+    # ---- compute -------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, with_last_pool: bool = False):
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        assert tuple(x.shape) == (self.cfg.B, self.cfg.xc, self.cfg.H, self.cfg.W), (tuple(x.shape), self.cfg.B)
+        _lib.call("isx_nst_forward", ctypes.byref(self.cfg), ctypes.byref(self.bufs), x, int(with_last_pool),
+                  _lib.stream_ptr())
+
+    def feature(self, kind: int, idx: int) -> torch.Tensor:
+        """bf16 NHWC view (a COPY) of a stored activation: kind 0 = conv idx's ReLU output, 1 = pool idx."""
+        ptr = ctypes.c_void_p()
+        h, w, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        _lib.call("isx_nst_feature", ctypes.byref(self.cfg), ctypes.byref(self.bufs), kind, idx, ctypes.byref(ptr),
+                  ctypes.byref(h), ctypes.byref(w), ctypes.byref(c))
+        off = ptr.value - self.workspace.data_ptr()
+        n = self.cfg.B * h.value * w.value * c.value
+        view = self.workspace[off:off + 2 * n].view(torch.bfloat16).view(self.cfg.B, h.value, w.value, c.value)
+        return view.clone()
+
+    def eval(self, x: torch.Tensor, grad: torch.Tensor):
+        _lib.call("isx_nst_eval", ctypes.byref(self.cfg), ctypes.byref(self.bufs), x, self.loss_c, self.loss_s, grad,
+                  _lib.stream_ptr())
+
+
+def gram_of(feat_nhwc: torch.Tensor, inv_n: Optional[float] = None) -> torch.Tensor:
+    """utils.GramMatrix on a bf16 NHWC feature map via isx_gram_fwd -> fp32 [B,C,C]."""
+    B, H, W, C = feat_nhwc.shape
+    HW = H * W
+    if inv_n is None:
+        inv_n = 1.0 / (C * HW)
+    ws = torch.empty(max(256, _lib.call_i64("isx_gram_workspace_bytes", B, HW, C)), device=feat_nhwc.device,
+                     dtype=torch.uint8)
+    G = torch.empty(B, C, C, device=feat_nhwc.device, dtype=torch.float32)
+    _lib.call("isx_gram_fwd", feat_nhwc, B, HW, C, _lib.f32(inv_n), ws, G, None, 1, _lib.f64(0.0), None,
+              _lib.f32(0.0), None, _lib.stream_ptr())
+    return G
+
+
+def stats_of(feat_nhwc: torch.Tensor):
+    """Per-(image, channel) mean and unbiased std over (H,W) via isx_bn_stats_fwd -> fp32 [B,C] each."""
+    B, H, W, C = feat_nhwc.shape
+    sums = torch.empty(B, C, 2, device=feat_nhwc.device, dtype=torch.float64)
+    mean = torch.empty(B, C, device=feat_nhwc.device, dtype=torch.float32)
+    std = torch.empty(B, C, device=feat_nhwc.device, dtype=torch.float32)
+    _lib.call("isx_bn_stats_fwd", feat_nhwc, B, _lib.i64(H * W), C, sums, mean, std, None, None, 1, _lib.f64(0.0),
+              _lib.f64(0.0), None, None, None, _lib.stream_ptr())
+    return mean, std

@@ -1,0 +1,68 @@
+"""Style-feature extraction for iris classification (iris_classification.py:66-71,94-98;
+iris_style_transfer_openeds2019.py:82-84): VGG-19 forward to the deepest style tap, then per layer the
+mean/std statistics Classifier2 consumes (models/classifiers/classifiers.py:71 -> 1920 floats per eye) and,
+optionally, the Gram matrices (utils.py:242-257) as upper triangles (BASELINE config 3)."""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from .engine import gram_of, stats_of
+from .sharding import sharded_map
+from .vgg import VGG19
+
+
+def _triu_index(C: int, device):
+    return torch.triu_indices(C, C, device=device)
+
+
+@torch.no_grad()
+def style_features_batch(vgg: VGG19, x: torch.Tensor, gram: bool = True, stats: bool = True) -> torch.Tensor:
+    """x: [B,1|3,H,W] fp32 on a CUDA device -> [B, D]; D = 2*sum(C_l) (stats) + sum(C_l(C_l+1)/2) (gram)."""
+    if not (gram or stats):
+        raise ValueError("nothing to extract")
+    _, _, s, _ = vgg.features_nhwc(x, full=False)
+    cols = []
+    if stats:
+        for f in s:
+            m, sd = stats_of(f)
+            cols += [m, sd]
+    if gram:
+        for f in s:
+            G = gram_of(f)
+            iu = _triu_index(G.shape[-1], G.device)
+            cols.append(G[:, iu[0], iu[1]])
+    return torch.cat(cols, dim=1)
+
+
+def feature_dim(channels: Sequence[int], gram: bool = True, stats: bool = True) -> int:
+    d = 0
+    if stats:
+        d += 2 * sum(channels)
+    if gram:
+        d += sum(c * (c + 1) // 2 for c in channels)
+    return d
+
+
+@torch.no_grad()
+def extract_features_sharded(vgg: VGG19, images, batch: int = 32, gram: bool = True, stats: bool = True,
+                             device=None) -> torch.Tensor:
+    """`images`: indexable [n,1|3,H,W] (host or device).  Each rank extracts its contiguous shard in batches of
+    `batch`; one all-gather returns the full [n, D] matrix on every rank."""
+    n = len(images)
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+
+    def work(lo: int, hi: int) -> torch.Tensor:
+        rows = []
+        for i in range(lo, hi, batch):
+            xb = images[i:min(hi, i + batch)]
+            xb = torch.as_tensor(xb).to(dev, torch.float32, non_blocking=True)
+            rows.append(style_features_batch(vgg, xb, gram=gram, stats=stats))
+        if not rows:
+            chans = [vgg.packed(dev).bias[c].numel() for c in vgg.style_convs]
+            return torch.empty(0, feature_dim(chans, gram, stats), device=dev)
+        return torch.cat(rows, dim=0)
+
+    return sharded_map(n, work)

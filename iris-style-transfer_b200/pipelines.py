@@ -1,0 +1,257 @@
+"""Drop-in for the reference's pipelines.py: nst() (8-110) and mask_and_crop_iris() (112-166).
+
+nst() keeps the reference signature and return structure.  The closure evaluation (VGG-19 forward,
+losses, backward to the image) is ONE call of libisx's fused driver and the L-BFGS iteration is one
+call of isx_lbfgs_tick; all optimiser scalars stay on the device, so the loop runs without host
+synchronisation except one flag read-back every `max_iter` evaluations."""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .engine import LbfgsConfig, NstEngine, gram_of, stats_of
+from .vgg import VGG19
+
+last_info: dict = {}
+
+
+def _prep_images(img: torch.Tensor, device) -> Tuple[torch.Tensor, bool]:
+    unbatched = img.dim() == 3
+    if unbatched:
+        img = img[None]
+    return img.detach().to(device, torch.float32).contiguous(), unbatched
+
+
+class NstJob:
+    """Device-resident state of one nst() call: targets, L-BFGS buffers, the evaluation engine.
+    `tick()` = one closure evaluation (pipelines.py:80-101) + one L-BFGS iteration for the whole batch."""
+
+    def __init__(self, c_img, s_img, vgg, dev, clone_content=True, BN_loss=True, c_loss_weight=1.0,
+                 s_loss_weight=1.0, lr=1.0, epochs=200, independent=False, history_size=100, x_init=None):
+        c_img, _ = _prep_images(c_img, dev)
+        s_img, s_unbatched = _prep_images(s_img, dev)
+        if clone_content:
+            x = c_img.clone()
+        elif x_init is not None:
+            x = x_init.detach().to(dev, torch.float32).clone()
+        else:
+            x = torch.rand(c_img.shape).to(dev)  # pipelines.py:54
+        self.x = x.contiguous()
+        B, xc, H, W = self.x.shape
+        packed = vgg.packed(dev)
+        cc, sc = vgg.content_convs, vgg.style_convs
+        self.independent = independent
+        self.epochs = int(epochs)
+
+        # ---- targets (pipelines.py:62-68) ----
+        eng = NstEngine(packed, B, H, W, xc, cc, sc, style_mode=1 if BN_loss else 0, c_weight=c_loss_weight,
+                        s_weight=s_loss_weight, coupled=not independent)
+        eng.forward(c_img)
+        eng.set_content_targets([eng.feature(0, i) for i in cc])
+        Bs, xs, Hs, Ws = s_img.shape
+        if (Bs, xs, Hs, Ws) == (B, xc, H, W):
+            eng.forward(s_img)
+            s_feats = [eng.feature(0, i) for i in sc]
+        else:
+            if Bs not in (1, B):
+                raise ValueError("style batch %d must be 1 or %d" % (Bs, B))
+            seng = NstEngine(packed, Bs, Hs, Ws, xs, cc, sc)
+            seng.forward(s_img)
+            s_feats = [seng.feature(0, i) for i in sc]
+            del seng
+        if BN_loss:
+            st = [stats_of(f) for f in s_feats]
+            eng.set_bn_targets([m for m, _ in st], [s for _, s in st])
+        else:
+            # unbatched style image (…2020.py:103-104): GramMatrix divides by H*W only (SURVEY note N3)
+            eng.set_gram_targets([gram_of(f, 1.0 / (f.shape[1] * f.shape[2]) if s_unbatched else None) for f in s_feats])
+        del s_feats
+        self.eng = eng
+
+        # ---- optimiser (pipelines.py:59): torch.optim.LBFGS([x], lr) defaults ----
+        P = B if independent else 1
+        self.P, self.ipp, self.N = P, B // P, self.x.numel() // P
+        # one (y, s) pair per iteration, so a short job never needs all 100 slots
+        hist = max(1, min(int(history_size), self.epochs + 20))
+        self.cfg = LbfgsConfig(epochs=self.epochs, max_iter=20, max_eval=25, history=hist, lr=float(lr),
+                               tolerance_grad=1e-7, tolerance_change=1e-9, c_weight=float(c_loss_weight),
+                               s_weight=float(s_loss_weight))
+        self.max_ticks = self.epochs + 20
+        M1 = hist + 1
+        N = self.N
+        self.state = torch.empty(_lib.call_i64("isx_lbfgs_state_bytes", P), device=dev, dtype=torch.uint8)
+        self.mats = torch.zeros(_lib.call_i64("isx_lbfgs_mats_bytes", P, hist), device=dev, dtype=torch.uint8)
+        self.scratch = torch.empty(_lib.call_i64("isx_lbfgs_scratch_bytes", P, _lib.i64(N), hist), device=dev,
+                                   dtype=torch.uint8)
+        self.Sh = torch.empty(P, M1, N, device=dev, dtype=torch.float32)
+        self.Yh = torch.empty(P, M1, N, device=dev, dtype=torch.float32)
+        self.grad = torch.empty_like(self.x)
+        self.grad_prev = torch.empty_like(self.x)
+        self.hist_c = torch.zeros(self.max_ticks, P, device=dev, dtype=torch.float64)
+        self.hist_s = torch.zeros(self.max_ticks, P, device=dev, dtype=torch.float64)
+        self.done = torch.zeros(P, device=dev, dtype=torch.int32)
+        self.ticks = 0
+        _lib.call("isx_lbfgs_init", self.state, P, _lib.stream_ptr())
+        _lib.call("isx_clamp01", self.x, _lib.i64(self.x.numel()), _lib.stream_ptr())  # pipelines.py:82 (first closure)
+
+    def tick(self):
+        self.eng.eval(self.x, self.grad)
+        _lib.call("isx_lbfgs_tick", self.x, self.grad, self.grad_prev, self.Sh, self.Yh, self.state, self.mats,
+                  self.scratch, self.eng.loss_c, self.eng.loss_s, self.ipp, self.P, _lib.i64(self.N),
+                  ctypes.byref(self.cfg), self.hist_c, self.hist_s, self.ticks, _lib.stream_ptr())
+        self.ticks += 1
+
+    def evals_done(self):
+        """Per-problem evaluation counts (0 while a problem is still running); one small D2H read."""
+        _lib.call("isx_lbfgs_done_flags", self.state, self.P, self.done, _lib.stream_ptr())
+        return self.done.cpu()
+
+    def finish(self):
+        evals = self.evals_done()
+        n_evals = int(evals.max().item()) if bool((evals > 0).all().item()) else self.ticks
+        hc = self.hist_c[:n_evals].cpu()
+        hs = self.hist_s[:n_evals].cpu()
+        x = self.x.detach()
+        _lib.call("isx_clamp01", x, _lib.i64(x.numel()), _lib.stream_ptr())  # pipelines.py:108-109
+        return x, n_evals, evals, hc, hs
+
+
+def nst(c_img: torch.Tensor,
+        s_img: torch.Tensor,
+        clone_content: bool = True,
+        BN_loss: bool = True,
+        c_loss_weight: float = 1,
+        s_loss_weight: float = 1,
+        lr: float = 1,
+        epochs: int = 200,
+        vgg: torch.nn.Module = None,
+        use_tqdm: bool = True,
+        device: str = 'cuda:0',
+        *,
+        independent: bool = False,
+        x_hist_stride: int = 1,
+        history_size: int = 100,
+        x_init: Optional[torch.Tensor] = None,
+        ) -> tuple[torch.Tensor, list, list, list]:
+    """Neural style transfer pipeline (pipelines.py:8-110).
+
+    Reference arguments and returns are unchanged.  Extensions (keyword-only):
+      independent   False: the batch is ONE L-BFGS problem exactly like the reference (shared history,
+                    content loss averaged over the batch).  True: every image is its own
+                    problem (== calling the reference once per image with B=1); this is what shards.
+      x_hist_stride keep every k-th evaluated image in x_hist (1 = reference behaviour, 0 = none).
+      history_size  L-BFGS history (torch default 100).
+      x_init        replaces torch.rand (pipelines.py:54) when clone_content is False.
+    c_loss_hist / s_loss_hist hold one float per closure evaluation, aggregated over the batch the way
+    the reference's batched losses are (content: mean over images, style: sum over images); per-image
+    values are left in `pipelines.last_info`."""
+    dev = torch.device(device)
+    if dev.type != 'cuda':
+        raise _lib.IsxError("iris_b200.nst runs on a CUDA B200 only (device=%r); there is no CPU fallback" % (device,))
+    if dev.index is None:
+        dev = torch.device('cuda', torch.cuda.current_device())
+    if vgg is None:
+        vgg = VGG19()
+    vgg.to(dev)
+    with torch.cuda.device(dev), torch.no_grad():
+        job = NstJob(c_img, s_img, vgg, dev, clone_content=clone_content, BN_loss=BN_loss,
+                     c_loss_weight=c_loss_weight, s_loss_weight=s_loss_weight, lr=lr, epochs=epochs,
+                     independent=independent, history_size=history_size, x_init=x_init)
+        x_hist: List[torch.Tensor] = []
+        pbar = None
+        if use_tqdm:
+            import tqdm
+            pbar = tqdm.tqdm(total=epochs)
+        while job.ticks < job.max_ticks:
+            if x_hist_stride and job.ticks % x_hist_stride == 0:
+                x_hist.append(job.x.detach().to('cpu'))  # pipelines.py:93
+            job.tick()
+            if pbar is not None:
+                pbar.update(1)
+            if job.ticks % 20 == 0 or job.ticks >= job.max_ticks:
+                # a problem finishes at an optimizer.step boundary: every 20 evaluations unless an early exit of
+                # lbfgs.py:370-374,463,511-526 fired (then up to 19 no-op ticks are spent before this check)
+                if bool((job.evals_done() > 0).all().item()):
+                    break
+        if pbar is not None:
+            pbar.close()
+        x, n_evals, evals, hc, hs = job.finish()
+        if x_hist_stride:
+            x_hist = x_hist[:(n_evals + x_hist_stride - 1) // x_hist_stride]
+        c_loss_hist = (hc.mean(dim=1) if independent else hc[:, 0]).tolist()
+        s_loss_hist = (hs.sum(dim=1) if independent else hs[:, 0]).tolist()
+        last_info.clear()
+        last_info.update(ticks=job.ticks, evals=n_evals, evals_per_problem=evals, c_loss_per_image=hc,
+                         s_loss_per_image=hs, problems=job.P)
+    return x, x_hist, c_loss_hist, s_loss_hist
+
+
+def mask_and_crop_iris(x: torch.Tensor,
+                       ritnet: torch.nn.Module = None,
+                       glint_threshold: float = 0.8,
+                       area_threshold: int = 500,
+                       connectivity: int = 2,
+                       device: str = 'cuda:0',
+                       *,
+                       seg: Optional[torch.Tensor] = None,
+                       ) -> tuple[torch.Tensor, torch.Tensor, int, int, int, int]:
+    """pipelines.py:112-166: m = (ritnet(x) == 2) * (x <= glint_threshold); x*m; trim to the bbox of the nonzero
+    pixels; repeat to 3 channels.  The segmenter is the caller's (the mask PRODUCER is outside the accelerated
+    path): pass `ritnet` (any callable returning the (1,H,W) label map) or the label map itself as `seg`.
+    Returns (x (3,h,w) fp32, m (1,h,w) bool, x_min, y_min, x_max, y_max) like the reference."""
+    from .utils import _bbox_of
+
+    x = x.to(device)
+    if seg is None:
+        if ritnet is None:
+            raise ValueError("mask_and_crop_iris: pass `ritnet` (a callable segmenter) or `seg` (its label map); "
+                             "the RITnet model itself is not part of this package")
+        if hasattr(ritnet, "to"):
+            ritnet.to(device)
+        seg = ritnet(x)
+    bbox, mask, xm = _bbox_of(x[None], seg=seg.reshape(1, *x.shape), label=2, threshold=glint_threshold,
+                              want_mask=True, want_masked=True)
+    x_min, y_min, x_max, y_max = bbox[0].tolist()
+    if x_max < 0:
+        raise RuntimeError("mask_and_crop_iris: empty iris mask (the reference fails in min() of an empty tensor)")
+    xc = xm[0][:, x_min: x_max + 1, y_min: y_max + 1]
+    mc = mask[0][:, x_min: x_max + 1, y_min: y_max + 1].bool()
+    return xc.repeat(3, 1, 1), mc, x_min, y_min, x_max, y_max
+
+
+def iris_masks_and_bboxes(frames: torch.Tensor, segs: torch.Tensor, glint_threshold: float = 0.8, label: int = 2):
+    """Batched form of the mask recipe (data_preprocessing.py:164-185, …2020.py:79-100): frames [B,1,H,W],
+    label maps [B,1,H,W] -> (mask uint8 [B,1,H,W], bbox int32 [B,4]) in one kernel launch."""
+    from .utils import _bbox_of
+
+    bbox, mask, _ = _bbox_of(frames, seg=segs, label=label, threshold=glint_threshold, want_mask=True)
+    return mask, bbox
+
+
+def crop_resize_irises(frames: torch.Tensor, masks: torch.Tensor, bboxes: torch.Tensor, size=(224, 224)):
+    """…2019.py:66-79: (frame * mask)[bbox] -> Resize(size) (bilinear, antialias) -> repeat to 3 channels,
+    for the whole batch at once.  frames [B,1,H,W] fp32, masks uint8 [B,1,H,W], bboxes int32 [B,4]."""
+    B, _, H, W = frames.shape
+    xm = (frames * masks).contiguous()  # masking multiply: plumbing-level elementwise on the caller's tensors
+    out = torch.empty(B, 3, size[0], size[1], device=frames.device, dtype=torch.float32)
+    with torch.cuda.device(frames.device):
+        _lib.call("isx_resize_bilinear_aa", xm, 1, H, W, bboxes.contiguous(), out, 3, size[0], size[1], B,
+                  _lib.stream_ptr())
+    return out
+
+
+def composite_irises(frames: torch.Tensor, new_irises: torch.Tensor, masks: torch.Tensor, bboxes: torch.Tensor):
+    """…2019.py:111-130 / …2020.py:121-139 for the whole batch, in place on `frames` [B,1,H,W]:
+    rgb_to_grayscale(new) -> Resize(bbox shape) -> * mask[bbox] -> frame[bbox] = frame[bbox] * ~mask + new."""
+    if not frames.is_cuda:
+        raise _lib.IsxError("iris_b200 needs CUDA tensors (B200); there is no CPU path")
+    assert frames.is_contiguous() and frames.dtype == torch.float32
+    B, _, H, W = frames.shape
+    new = new_irises.detach().to(frames.device, torch.float32).contiguous()
+    with torch.cuda.device(frames.device):
+        _lib.call("isx_composite", new, new.shape[1], new.shape[2], new.shape[3], frames,
+                  masks.to(torch.uint8).contiguous(), bboxes.to(torch.int32).contiguous(), B, H, W, _lib.stream_ptr())
+    return frames

@@ -1,0 +1,133 @@
+"""Drop-ins for the hot-path symbols of the reference's utils.py: GramMatrix (242-257),
+ContentLoss_L2 (259-290), StyleLoss_Gram (292-322), StyleLoss_BN (324-355), crop_image (44-72).
+Inputs are fp32 NCHW CUDA tensors as in the reference; arithmetic runs in libisx."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .engine import gram_of, stats_of
+
+
+def _to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
+    if not x.is_cuda:
+        raise _lib.IsxError("iris_b200 needs CUDA tensors (B200); there is no CPU path")
+    if x.dim() == 3:
+        x = x[None]
+    return x.detach().permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
+
+
+def GramMatrix(x: torch.Tensor) -> torch.Tensor:
+    """utils.py:242-257: flatten (H,W), x @ x^T / n with n = x[0].numel() after the flatten, i.e.
+    C*H*W for a batched (B,C,H,W) input and H*W for an unbatched (C,H,W) one (SURVEY note N3)."""
+    unbatched = x.dim() == 3
+    f = _to_nhwc_bf16(x)
+    B, H, W, C = f.shape
+    inv_n = 1.0 / (H * W) if unbatched else 1.0 / (C * H * W)
+    G = gram_of(f, inv_n)
+    return G[0] if unbatched else G
+
+
+class ContentLoss_L2(torch.nn.Module):
+    """utils.py:259-290 (forward only; the differentiable path is nst()'s fused driver)."""
+
+    def __init__(self, targets: List[torch.Tensor] = None, weights: List[float] = None) -> None:
+        super().__init__()
+        self.targets = targets
+        self.weights = [1.0] * len(targets) if weights is None else weights
+
+    @torch.no_grad()
+    def forward(self, preds: List[torch.Tensor]) -> torch.Tensor:
+        total = torch.zeros((), device=preds[0].device, dtype=torch.float64)
+        for p, t, w in zip(preds, self.targets, self.weights):
+            pn, tn = _to_nhwc_bf16(p), _to_nhwc_bf16(t)
+            B = pn.shape[0]
+            per_image = pn[0].numel()
+            loss = torch.zeros(B, device=p.device, dtype=torch.float64)
+            _lib.call("isx_content_mse_fwd_bwd", pn, tn, tn.shape[0], None, B, _lib.i64(per_image),
+                      _lib.f64(1.0 / (per_image * B)), _lib.f32(0.0), loss, _lib.stream_ptr())
+            total = total + loss.sum() * w
+        return (total * 0.5).float()
+
+
+class StyleLoss_Gram(torch.nn.Module):
+    """utils.py:292-322."""
+
+    def __init__(self, targets: List[torch.Tensor] = None, weights: List[float] = None) -> None:
+        super().__init__()
+        self.targets = [GramMatrix(t) for t in targets]
+        self.weights = [1.0] * len(targets) if weights is None else weights
+
+    @torch.no_grad()
+    def forward(self, preds: List[torch.Tensor]) -> torch.Tensor:
+        total = torch.zeros((), device=preds[0].device, dtype=torch.float64)
+        for p, t, w in zip(preds, self.targets, self.weights):
+            total = total + ((GramMatrix(p) - t).double() ** 2).sum() * w
+        return (total * 0.25).float()
+
+
+class StyleLoss_BN(torch.nn.Module):
+    """utils.py:324-355 (the reference's default style loss, pipelines.py:11,65-66)."""
+
+    def __init__(self, targets: List[torch.Tensor] = None, weights: List[float] = None) -> None:
+        super().__init__()
+        stats = [stats_of(_to_nhwc_bf16(t)) for t in targets]
+        self.targets_mean = [m if t.dim() == 4 else m[0] for (m, _), t in zip(stats, targets)]
+        self.targets_std = [s if t.dim() == 4 else s[0] for (_, s), t in zip(stats, targets)]
+        self.weights = [1.0] * len(targets) if weights is None else weights
+
+    @torch.no_grad()
+    def forward(self, preds: List[torch.Tensor]) -> torch.Tensor:
+        total = torch.zeros((), device=preds[0].device, dtype=torch.float64)
+        for p, tm, ts, w in zip(preds, self.targets_mean, self.targets_std, self.weights):
+            pm, ps = stats_of(_to_nhwc_bf16(p))
+            total = total + ((pm - tm).double() ** 2 + (ps - ts).double() ** 2).sum() * w / pm.shape[-1]
+        return total.float()
+
+
+def style_features(style_feats: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Classifier2's reduction (models/classifiers/classifiers.py:71): per layer cat(mean, std_unbiased)
+    over (H,W), concatenated -> (B, 2*sum C_l).  Accepts fp32 NCHW or bf16 NHWC (from features_nhwc)."""
+    out = []
+    for f in style_feats:
+        fn = f if f.dtype == torch.bfloat16 else _to_nhwc_bf16(f)
+        m, s = stats_of(fn)
+        out += [m, s]
+    return torch.cat(out, dim=1)
+
+
+def _bbox_of(image: torch.Tensor, seg: Optional[torch.Tensor] = None, label: int = 2,
+             threshold: Optional[float] = None, want_mask: bool = False, want_masked: bool = False):
+    """isx_mask_bbox on a batch [B,1,H,W]: returns (bbox int32 [B,4] on device, mask or None, x*m or None)."""
+    if not image.is_cuda:
+        raise _lib.IsxError("iris_b200 needs CUDA tensors (B200); there is no CPU path")
+    x = image.detach().to(torch.float32).contiguous()
+    B, _, H, W = x.shape
+    bbox = torch.empty(B, 4, device=x.device, dtype=torch.int32)
+    mask = torch.empty(B, 1, H, W, device=x.device, dtype=torch.uint8) if want_mask else None
+    xm = torch.empty_like(x) if want_masked else None
+    segc = seg.detach().to(x.device, torch.int64).contiguous() if seg is not None else None
+    with torch.cuda.device(x.device):
+        _lib.call("isx_mask_bbox", x, segc, int(label), int(threshold is not None),
+                  _lib.f32(threshold if threshold is not None else 0.0), mask, xm, bbox, B, H, W, _lib.stream_ptr())
+    return bbox, mask, xm
+
+
+def crop_image(image: torch.Tensor, return_idx: bool = False):
+    """utils.py:44-72: trim the black border -- bbox of the NONZERO PIXELS, (x_min, y_min, x_max, y_max) =
+    (row_min, col_min, row_max, col_max) inclusive; `image` is (h,w) or (1,h,w)."""
+    if image.dim() == 2:
+        img3 = image[None]
+    elif image.dim() == 3 and image.shape[0] == 1:
+        img3 = image
+    else:
+        raise Exception('image shape wrong:', image.shape)  # utils.py:66
+    bbox, _, _ = _bbox_of(img3[None])
+    x_min, y_min, x_max, y_max = bbox[0].tolist()
+    if x_max < 0:
+        raise RuntimeError("crop_image: image has no nonzero pixel (the reference fails in min() of an empty tensor)")
+    if return_idx:
+        return x_min, y_min, x_max, y_max
+    return img3[:, x_min: x_max + 1, y_min: y_max + 1]

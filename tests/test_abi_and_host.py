@@ -1,0 +1,121 @@
+"""CPU tier: the C-ABI library loads and exports every symbol include/isx.h declares (no compute calls
+without a GPU), the host-side mirrors of the reference interface are consistent, and the product path
+refuses to run without CUDA instead of falling back."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import iris_b200
+from iris_b200 import _lib, engine, synthetic
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _lib.declared_symbols()
+    assert len(names) >= 25 and "isx_nst_eval" in names and "isx_lbfgs_tick" in names
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.isx_version() == 100
+    assert isinstance(lib.isx_last_error(), bytes)
+
+
+def test_header_has_no_torch_types():
+    txt = open(_lib.HEADER_PATH).read()
+    assert 'extern "C"' in txt
+    code = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)  # declarations only, comments stripped
+    assert "torch" not in code.lower() and "at::" not in code and "Tensor" not in code and "#include <stdint.h>" in code
+
+
+def test_struct_mirrors_match_header():
+    """ctypes mirrors vs the C structs: field order and a size the C side would compute."""
+    txt = re.sub(r"/\*.*?\*/", "", open(_lib.HEADER_PATH).read(), flags=re.S)
+
+    def c_struct_fields(name):
+        body = [b for b in txt.split("typedef struct {")[1:] if re.match(r"[^}]*\}\s*%s;" % name, b, flags=re.S)][0]
+        body = body[: body.index("}")]
+        out = []
+        for decl in re.findall(r"\b(?:int32_t|float|double)\s+([^;]+);", body):
+            out += [re.sub(r"\[.*?\]", "", n).strip() for n in decl.split(",")]
+        return out
+
+    assert [f[0] for f in engine.NstConfig._fields_] == c_struct_fields("isx_nst_config")
+    assert [f[0] for f in engine.LbfgsConfig._fields_] == c_struct_fields("isx_lbfgs_config")
+    assert ctypes.sizeof(engine.NstConfig) == 4 * 7 + 4 * 8 * 2 + 4 + 4 * 8 * 2 + 4 * 4 + 8 * 2
+    assert ctypes.sizeof(engine.LbfgsConfig) == 16 + 8 * 5
+    # pure-host size queries work without a device
+    assert _lib.call_i64("isx_lbfgs_mats_bytes", 2, 100) == 2 * 3 * 101 * 101 * 8
+    assert _lib.call_i64("isx_lbfgs_state_bytes", 1) > 0
+    assert _lib.call_i64("isx_gram_workspace_bytes", 1, 256000, 64) >= 64 * 64 * 4
+
+
+def test_workspace_query_and_argument_errors():
+    cfg = engine.NstConfig()
+    cfg.B, cfg.H, cfg.W, cfg.xc, cfg.n_conv = 2, 64, 48, 3, 10
+    cfg.n_style, cfg.n_content = 4, 1
+    for t, c in enumerate([0, 2, 4, 8]):
+        cfg.style_conv[t] = c
+    cfg.content_conv[0] = 9
+    n = _lib.call_i64("isx_nst_workspace_bytes", ctypes.byref(cfg))
+    acts = 2 * 64 * 48 * 2 * (64 + 64) + 2 * 32 * 24 * 2 * (128 + 128) + 2 * 16 * 12 * 2 * 256 * 4 + 2 * 8 * 6 * 2 * 512 * 2
+    assert n > acts
+    cfg.style_conv[3] = 12  # tap beyond n_conv -> error, not UB
+    assert _lib.call_i64("isx_nst_workspace_bytes", ctypes.byref(cfg)) == -1
+    assert b"style tap" in _lib.load().isx_last_error()
+    with pytest.raises(_lib.IsxError):
+        _lib.call("isx_gram_fwd", None, 1, 16, 64, _lib.f32(1.0), None, None, None, 1, _lib.f64(0), None, _lib.f32(0),
+                  None, None)
+
+
+def test_layer_map_matches_reference_table():
+    # models/vgg/vgg.py:6-10
+    L = engine.VGG19_LAYERS
+    assert (L["conv1_1"], L["relu1_1"], L["pool1"], L["relu2_1"], L["relu3_1"], L["relu4_1"], L["relu4_2"],
+            L["relu5_1"], L["pool5"]) == (0, 1, 4, 6, 11, 20, 22, 29, 36)
+    assert len(L) == 37
+    conv = engine.CONV_OF_FEATURE_INDEX
+    assert conv[L["relu4_2"]] == 9 and conv[L["conv4_2"]] == 9 and conv[L["relu5_1"]] == 12
+    assert engine.CONV_COUT == [64, 64, 128, 128, 256, 256, 256, 256, 512, 512, 512, 512, 512, 512, 512, 512]
+
+
+def test_vgg19_surface_and_no_cpu_fallback():
+    from oracle import nst_oracle as O
+
+    w = O.random_vgg19_weights(0)
+    net = iris_b200.VGG19(weights=w)
+    assert net.content_layers_idx == [22] and net.style_layers_idx == [1, 6, 11, 20]
+    assert net.content_convs == [9] and net.style_convs == [0, 2, 4, 8]
+    net5 = iris_b200.VGG19(style_layers=["conv1_1", "relu2_1", "relu3_1", "relu4_1", "relu5_1"], weights=w)
+    assert net5.style_convs == [0, 2, 4, 8, 12]
+    with pytest.raises(NotImplementedError):
+        iris_b200.VGG19(bn=True, weights=w)
+    with pytest.raises(NotImplementedError):
+        iris_b200.VGG19(style_layers=["pool1"], weights=w)
+    x = torch.rand(1, 3, 32, 32)
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            net(x)
+        with pytest.raises(_lib.IsxError):
+            iris_b200.nst(x, x, vgg=net, use_tqdm=False, device="cpu")
+        with pytest.raises(_lib.IsxError):
+            iris_b200.GramMatrix(torch.rand(1, 64, 8, 8))
+        with pytest.raises(_lib.IsxError):
+            iris_b200.crop_image(torch.rand(8, 8))
+
+
+def test_synthetic_eyes_are_deterministic_and_exercise_the_mask():
+    f1, s1 = synthetic.synthetic_eye(5, 640, 400)
+    f2, s2 = synthetic.synthetic_eye(5, 640, 400)
+    assert np.array_equal(f1, f2) and np.array_equal(s1, s2)
+    assert f1.shape == (1, 640, 400) and f1.dtype == np.float32 and s1.dtype == np.int64
+    assert 0.0 <= f1.min() and f1.max() <= 1.0
+    iris = s1 == 2
+    frac = iris.mean()
+    assert 0.04 < frac < 0.16, frac                      # 6-10 % of the frame like the shipped eye PNGs
+    assert ((f1 > 0.8) & iris).sum() > 0                 # glints inside the iris: the x <= 0.8 test matters
+    assert set(np.unique(s1)) == {0, 1, 2, 3}
+    crops = synthetic.synthetic_iris_crops([1, 2], 64)
+    assert crops.shape == (2, 3, 64, 64) and np.array_equal(crops[:, 0], crops[:, 2])
