@@ -41,10 +41,21 @@ int isx_pack_conv3x3_weights(const float* w_oihw, int Cout, int Cin, isx_bf16* w
  * mask: NULL or fp32 [mask_b,1,H,W] with mask_b in {1,B}; w: fp32 [64,3,3,3]; out: bf16 [B,H,W,64]. */
 int isx_conv1_1_fwd(const float* x, int xc, const float* mask, int mask_b, const float* w, const float* bias,
                     isx_bf16* out, int B, int H, int W, isx_stream stream);
+/* Same head on the tensor cores: per-pixel 27-tap gather, bf16 hi+lo split of the normalised input (K = 64),
+ * one tcgen05 128x64x64 MMA per 128 pixels.  w0_fwd: bf16 [64][64] from isx_pack_conv1_1_fwd. */
+int isx_pack_conv1_1_fwd(const float* w, isx_bf16* w0_fwd, isx_stream stream);
+int isx_conv1_1_fwd_tc(const float* x, int xc, const float* mask, int mask_b, const isx_bf16* w0_fwd, const float* bias,
+                       isx_bf16* out, int B, int H, int W, isx_stream stream);
 /* autograd tail of the same (pipelines.py:90): dY bf16 [B,H,W,64] (already ReLU-masked) ->
  * d(loss)/dx fp32 [B,xc,H,W], including Normalize's 1/std and the optional mask. */
 int isx_conv1_1_dgrad(const isx_bf16* dy, const float* w, const float* mask, int mask_b, float* dx, int xc, int B,
                       int H, int W, isx_stream stream);
+
+/* Same tail on the tensor cores: the 64->3 dgrad as a tcgen05 implicit GEMM with N padded to 16
+ * (w0_dgrad: bf16 [9][16][64] from isx_pack_conv1_1_dgrad) and an fp32-NCHW epilogue. */
+int isx_pack_conv1_1_dgrad(const float* w, isx_bf16* w0_dgrad, isx_stream stream);
+int isx_conv1_1_dgrad_tc(const isx_bf16* dy, const isx_bf16* w0_dgrad, const float* mask, int mask_b, float* dx, int xc,
+                         int B, int H, int W, isx_stream stream);
 
 /* ---- K1: Conv2d 3x3 s1 p1 + bias + ReLU on tcgen05 (models/vgg/vgg.py:87) ---------------------
  * in bf16 [B,H,W,Cin], w_fwd from isx_pack_conv3x3_weights, bias fp32 [Cout], out bf16 [B,H,W,Cout].
@@ -147,6 +158,8 @@ typedef struct {
 
 typedef struct {
   const float* w0;                      /* conv1_1 fp32 OIHW [64,3,3,3] */
+  const isx_bf16* w0_fwd;               /* isx_pack_conv1_1_fwd (tensor-core head); NULL -> CUDA-core head */
+  const isx_bf16* w0_dgrad;             /* isx_pack_conv1_1_dgrad (tensor-core image-gradient tail); NULL -> CUDA-core tail */
   const float* bias[ISX_VGG19_CONVS];   /* fp32 [Cout] per conv */
   const isx_bf16* w_fwd[ISX_VGG19_CONVS];    /* packed (isx_pack_conv3x3_weights); [0] unused */
   const isx_bf16* w_dgrad[ISX_VGG19_CONVS];

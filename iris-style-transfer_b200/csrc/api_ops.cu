@@ -33,6 +33,34 @@ extern "C" int isx_conv1_1_fwd(const float* x, int xc, const float* mask, int ma
   return conv1_1_fwd(x, xc, mask, mask_b, w, bias, P(out), B, H, W, S(stream));
 }
 
+extern "C" int isx_pack_conv1_1_fwd(const float* w, isx_bf16* w0_fwd, isx_stream stream) {
+  ISX_REQUIRE(w && w0_fwd, "isx_pack_conv1_1_fwd: null pointer");
+  return pack_w0_fwd(w, P(w0_fwd), S(stream));
+}
+
+extern "C" int isx_conv1_1_fwd_tc(const float* x, int xc, const float* mask, int mask_b, const isx_bf16* w0_fwd,
+                                  const float* bias, isx_bf16* out, int B, int H, int W, isx_stream stream) {
+  ISX_REQUIRE(x && w0_fwd && out && B > 0 && H > 0 && W > 0, "isx_conv1_1_fwd_tc: bad arguments");
+  ISX_REQUIRE(!mask || mask_b == 1 || mask_b == B, "isx_conv1_1_fwd_tc: mask batch %d must be 1 or %d", mask_b, B);
+  return conv1_1_fwd_tc(x, xc, mask, mask ? mask_b : 0, P(w0_fwd), bias, P(out), B, H, W, S(stream));
+}
+
+extern "C" int isx_pack_conv1_1_dgrad(const float* w, isx_bf16* w0_dgrad, isx_stream stream) {
+  ISX_REQUIRE(w && w0_dgrad, "isx_pack_conv1_1_dgrad: null pointer");
+  return pack_w0_dgrad(w, P(w0_dgrad), S(stream));
+}
+
+extern "C" int isx_conv1_1_dgrad_tc(const isx_bf16* dy, const isx_bf16* w0_dgrad, const float* mask, int mask_b,
+                                    float* dx, int xc, int B, int H, int W, isx_stream stream) {
+  ISX_REQUIRE(dy && w0_dgrad && dx && B > 0 && H > 0 && W > 0, "isx_conv1_1_dgrad_tc: bad arguments");
+  ISX_REQUIRE(!mask || mask_b == 1 || mask_b == B, "isx_conv1_1_dgrad_tc: mask batch %d must be 1 or %d", mask_b, B);
+  ConvArgs a;
+  a.in = P(dy); a.weight = P(w0_dgrad); a.out = nullptr;
+  a.B = B; a.H = H; a.W = W; a.Cin = 64; a.Cout = 16; a.ntaps = 9;
+  a.dx_nchw = dx; a.xc = xc; a.in_mask = mask; a.mask_b = mask ? mask_b : 0;
+  return conv_tc(a, S(stream));
+}
+
 extern "C" int isx_conv1_1_dgrad(const isx_bf16* dy, const float* w, const float* mask, int mask_b, float* dx, int xc,
                                  int B, int H, int W, isx_stream stream) {
   ISX_REQUIRE(dy && w && dx && B > 0 && H > 0 && W > 0, "isx_conv1_1_dgrad: bad arguments");

@@ -35,11 +35,16 @@ struct ConvParams {
   const __nv_bfloat16* add_buf;   // [B,H,W,Cout] or null: out += add
   const float* aff_a;        // [B,Cout] or null: out += aff_a + aff_b * act   (BN-statistics tap gradient)
   const float* aff_b;
+  // EPI == 1 (image-gradient tail, BN = 16): dx fp32 NCHW [B,xc,H,W] = acc[c] * mask / std[c]
+  float* dx_nchw;
+  int xc;
+  const float* in_mask;      // [mask_b,1,H,W] or null
+  int mask_b;
 };
 
 static constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
 
-template <int BN, int MT>
+template <int BN, int MT, int EPI>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
@@ -79,7 +84,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmO);
+    if (EPI == 0) tma_prefetch_desc(&tmO);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -149,6 +154,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int tw = row % p.TW;
     const int th = (row / p.TW) % p.TH;
     const int tb = row / (p.TW * p.TH);
+    if constexpr (EPI == 1) {
+      // image-gradient tail: 3 (of 16) accumulator columns -> fp32 NCHW planes, Normalize backward (1/std), mask
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        const int x = x0[mt] + tw, y = y0[mt] + th, b = b0[mt] + tb;
+        const bool valid = (x < p.W) && (y < p.H) && (b < p.B);
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mt * BN, v);
+        tmem_ld_wait();
+        if (valid) {
+          const size_t hw = static_cast<size_t>(p.H) * p.W;
+          const size_t off = static_cast<size_t>(y) * p.W + x;
+          float m = 1.f;
+          if (p.in_mask != nullptr) m = __ldg(p.in_mask + (p.mask_b > 1 ? b : 0) * hw + off);
+          const float a0 = __uint_as_float(v[0]) * m / 0.229f;
+          const float a1 = __uint_as_float(v[1]) * m / 0.224f;
+          const float a2 = __uint_as_float(v[2]) * m / 0.225f;
+          if (p.xc == 3) {
+            float* o = p.dx_nchw + static_cast<size_t>(b) * 3 * hw + off;
+            o[0] = a0; o[hw] = a1; o[2 * hw] = a2;
+          } else {
+            p.dx_nchw[static_cast<size_t>(b) * hw + off] = a0 + a1 + a2;
+          }
+        }
+      }
+    } else {
 #pragma unroll 1
     for (int mt = 0; mt < MT; ++mt) {
       const int x = x0[mt] + tw, y = y0[mt] + th, b = b0[mt] + tb;
@@ -232,7 +263,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-    if (threadIdx.x == 64) tma_store_wait_all<0>();
+    }
+    if (EPI == 0 && threadIdx.x == 64) tma_store_wait_all<0>();
     tc_fence_before();
   }
   __syncthreads();
@@ -259,7 +291,7 @@ static void choose_patch(int B, int H, int W, bool one_image_per_tile, int* TW, 
   }
 }
 
-template <int BN, int MT>
+template <int BN, int MT, int EPI = 0>
 static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stream) {
   ConvParams p;
   memset(&p, 0, sizeof(p));
@@ -272,6 +304,7 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
   p.w_rows_per_image = a.per_image_weights ? a.Cout : 0;
   p.relu = a.relu; p.bias = a.bias; p.mask_act = a.mask_act; p.add_buf = a.add_buf;
   p.aff_a = a.aff_a; p.aff_b = a.aff_b;
+  p.dx_nchw = a.dx_nchw; p.xc = a.xc; p.in_mask = a.in_mask; p.mask_b = a.mask_b;
   if (a.per_image_weights && MT != 1)
     ISX_REQUIRE(p.tiles_b == a.B, "per-image weights need one image per tile");
 
@@ -281,6 +314,7 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
   while (stages * kStageBytes < MT * (BN / 64) * kATileBytes) ++stages;  // epilogue staging aliases the pipeline
   const int num_kb = a.ntaps * (a.Cin / 64);
   if (stages > num_kb && num_kb * kStageBytes >= MT * (BN / 64) * kATileBytes) stages = num_kb;
+  if (stages < 2) stages = 2;
   p.stages = stages;
   const size_t smem_bytes = 1024 + static_cast<size_t>(stages) * kStageBytes + 256;
   ISX_REQUIRE(smem_bytes <= 227 * 1024, "conv_tc: %zu B of shared memory exceed 227 KB", smem_bytes);
@@ -299,15 +333,17 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
     uint32_t box[2] = {64, (uint32_t)BN};
     if (isx_make_tmap_bf16(&tmB, a.weight, 2, dims, str, box, true)) return 3;
   }
-  {
+  if (EPI == 0) {
     uint64_t dims[4] = {(uint64_t)a.Cout, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
     uint64_t str[3] = {(uint64_t)a.Cout * 2, (uint64_t)a.W * a.Cout * 2, (uint64_t)a.H * a.W * a.Cout * 2};
     uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
     if (isx_make_tmap_bf16(&tmO, a.out, 4, dims, str, box, true)) return 3;
+  } else {
+    tmO = tmA;  // unused by the image-gradient epilogue
   }
   const long sp_tiles = static_cast<long>(p.tiles_x) * p.tiles_y * p.tiles_b;
   const long grid = ((sp_tiles + MT - 1) / MT) * p.n_tiles;
-  auto kern = conv_tc_kernel<BN, MT>;
+  auto kern = conv_tc_kernel<BN, MT, EPI>;
   ISX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   isx_prof_begin(ISX_PROF_CONV, 2.0 * a.ntaps * a.Cin * a.Cout * static_cast<double>(a.B) * a.H * a.W, stream);
   kern<<<(unsigned)grid, 192, smem_bytes, stream>>>(tmA, tmB, tmO, p);
@@ -317,6 +353,13 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
 }
 
 int conv_tc(const ConvArgs& a, cudaStream_t stream) {
+  if (a.dx_nchw != nullptr) {  // conv1_1 dgrad tail: N = 16 (3 real output channels), fp32 NCHW epilogue
+    ISX_REQUIRE(a.Cin == 64 && a.Cout == 16 && a.ntaps == 9, "conv_tc: image-gradient mode needs Cin 64, Cout 16 (padded)");
+    ISX_REQUIRE(a.xc == 1 || a.xc == 3, "conv_tc: xc must be 1 or 3");
+    const long pix_tiles = (static_cast<long>(a.B) * a.H * a.W + 127) / 128;
+    if (a.force_mt == 1 || pix_tiles < 4 * kNumSMs) return launch_conv<16, 1, 1>(a, a.force_stages ? a.force_stages : 3, stream);
+    return launch_conv<16, 2, 1>(a, a.force_stages ? a.force_stages : 2, stream);
+  }
   ISX_REQUIRE(a.Cin % 64 == 0 && a.Cout % 64 == 0, "conv_tc: Cin=%d / Cout=%d must be multiples of 64", a.Cin, a.Cout);
   ISX_REQUIRE(a.ntaps == 9 || a.ntaps == 1, "conv_tc: ntaps must be 9 or 1");
   ISX_REQUIRE(a.B > 0 && a.H > 0 && a.W > 0, "conv_tc: empty input");

@@ -38,6 +38,21 @@ int pack_conv_weights(const float* w, int Cout, int Cin, __nv_bfloat16* wf, __nv
   return 0;
 }
 
+// conv1_1 dgrad weights for the tensor-core tail: fp32 [64,3,3,3] -> bf16 [8-tap][16][64], rows 3..15 zero
+__global__ void pack_w0_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 9*16*64
+  if (i >= 9 * 16 * 64) return;
+  const int o = i % 64, c = (i / 64) % 16, tapd = i / (64 * 16);
+  const int tap = 8 - tapd;
+  wd[i] = c < 3 ? __float2bfloat16_rn(w[(o * 3 + c) * 9 + tap]) : __float2bfloat16_rn(0.f);
+}
+
+int pack_w0_dgrad(const float* w, __nv_bfloat16* wd, cudaStream_t s) {
+  pack_w0_dgrad_kernel<<<(9 * 16 * 64 + 255) / 256, 256, 0, s>>>(w, wd);
+  ISX_LAUNCH_CHECK();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // conv1_1 forward: fp32 NCHW image -> Normalize (-> * mask) -> 3x3 conv (3->64) + bias + ReLU -> bf16 NHWC
 // (models/vgg/vgg.py:81-87; K0 fused into K1's first layer)

@@ -20,6 +20,11 @@ struct ConvArgs {
   const float* aff_a = nullptr;
   const float* aff_b = nullptr;
   int force_bn = 0, force_mt = 0, force_stages = 0;  // tuning / test hooks (0 = heuristic)
+  // image-gradient tail (conv1_1 dgrad): when dx_nchw != null the epilogue writes fp32 NCHW instead of `out`
+  float* dx_nchw = nullptr;
+  int xc = 3;
+  const float* in_mask = nullptr;
+  int mask_b = 0;
 };
 int conv_tc(const ConvArgs& a, cudaStream_t stream);
 

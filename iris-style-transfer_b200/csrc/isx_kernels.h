@@ -7,6 +7,10 @@
 namespace isx {
 
 int pack_conv_weights(const float* w, int Cout, int Cin, __nv_bfloat16* wf, __nv_bfloat16* wd, cudaStream_t s);
+int pack_w0_dgrad(const float* w, __nv_bfloat16* wd, cudaStream_t s);
+int pack_w0_fwd(const float* w, __nv_bfloat16* wp, cudaStream_t s);
+int conv1_1_fwd_tc(const float* x, int xc, const float* mask, int mask_b, const __nv_bfloat16* w0_packed,
+                   const float* bias, __nv_bfloat16* out, int B, int H, int W, cudaStream_t s);
 int conv1_1_fwd(const float* x, int xc, const float* mask, int mask_b, const float* w, const float* bias,
                 __nv_bfloat16* out, int B, int H, int W, cudaStream_t s);
 int conv1_1_dgrad(const __nv_bfloat16* dy, const float* w, const float* mask, int mask_b, float* dx, int xc, int B,

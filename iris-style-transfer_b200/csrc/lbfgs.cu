@@ -132,6 +132,51 @@ lbfgs_dots_kernel(const float* __restrict__ g, const float* __restrict__ g_prev,
 }
 
 // ---------------------------------------------------------------------------------------------
+// reduce the per-block partials: one block per (slot | extras, problem) -> dots[p][slot][4], dots[p][M1][0..2]
+// (kept out of the control kernel: with 375+ partial blocks per image the serial sum was its latency floor)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+lbfgs_reduce_kernel(const LbfgsState* __restrict__ states, const float* __restrict__ part,
+                    const float* __restrict__ ext, int M1, int nblk, double* __restrict__ dots) {
+  const int p = blockIdx.y;
+  const LbfgsState& st = states[p];
+  if (st.done) return;
+  const int slot = blockIdx.x;
+  __shared__ double red[4][4];
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  if (slot < M1) {
+    if (st.n_iter < 1) return;
+    // live ring slots and the candidate only
+    const int rel = (slot - st.hist_head + M1) % M1;
+    if (!(rel < st.hist_count || slot == st.cand_slot)) return;
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(part + ((static_cast<long>(p) * nblk + b) * M1 + slot) * 4));
+      a0 += q.x; a1 += q.y; a2 += q.z; a3 += q.w;
+    }
+  } else {
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(ext + (static_cast<long>(p) * nblk + b) * 4));
+      a0 += q.x; a1 += q.y; a2 = fmax(a2, static_cast<double>(q.z));
+    }
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a3 = warp_sum(a3);
+  if (slot < M1) a2 = warp_sum(a2);
+  else
+    for (int o = 16; o > 0; o >>= 1) a2 = fmax(a2, __shfl_xor_sync(0xffffffffu, a2, o));
+  if ((threadIdx.x & 31) == 0) {
+    red[threadIdx.x >> 5][0] = a0; red[threadIdx.x >> 5][1] = a1; red[threadIdx.x >> 5][2] = a2; red[threadIdx.x >> 5][3] = a3;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    const int c = threadIdx.x;
+    double v;
+    if (slot == M1 && c == 2) v = fmax(fmax(red[0][2], red[1][2]), fmax(red[2][2], red[3][2]));
+    else v = red[0][c] + red[1][c] + red[2][c] + red[3][c];
+    dots[(static_cast<long>(p) * (M1 + 1) + slot) * 4 + c] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // control: one block (4 warps) per problem
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double block_sum_128(double v, double* red) {
@@ -143,9 +188,9 @@ __device__ __forceinline__ double block_sum_128(double v, double* red) {
 }
 
 __global__ void __launch_bounds__(128)
-lbfgs_control_kernel(LbfgsState* __restrict__ states, double* __restrict__ mats, const float* __restrict__ part,
-                     const float* __restrict__ ext, const double* __restrict__ loss_c,
-                     const double* __restrict__ loss_s, int images_per_problem, int M1, int nblk, LbfgsConfig cfg,
+lbfgs_control_kernel(LbfgsState* __restrict__ states, double* __restrict__ mats, const double* __restrict__ dots,
+                     const double* __restrict__ loss_c,
+                     const double* __restrict__ loss_s, int images_per_problem, int M1, LbfgsConfig cfg,
                      double* __restrict__ hist_c, double* __restrict__ hist_s, int tick, int P) {
   const int p = blockIdx.x;
   LbfgsState& st = states[p];
@@ -176,29 +221,12 @@ lbfgs_control_kernel(LbfgsState* __restrict__ states, double* __restrict__ mats,
   const int M = cfg.history;
   const bool have_prev = st.n_iter >= 1;
   const int nlive = have_prev ? st.hist_count + 1 : 0;
+  const double* dp = dots + static_cast<long>(p) * (M1 + 1) * 4;
   for (int k = tid; k < nlive; k += blockDim.x) {
     const int slot = k < st.hist_count ? (st.hist_head + k) % M1 : st.cand_slot;
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    for (int b = 0; b < nblk; ++b) {
-      const float* q = part + ((static_cast<long>(p) * nblk + b) * M1 + slot) * 4;
-      a0 += q[0]; a1 += q[1]; a2 += q[2]; a3 += q[3];
-    }
-    sg[slot] = a0; yg[slot] = a1; syn[slot] = a2; yyn[slot] = a3;
+    sg[slot] = dp[slot * 4 + 0]; yg[slot] = dp[slot * 4 + 1]; syn[slot] = dp[slot * 4 + 2]; yyn[slot] = dp[slot * 4 + 3];
   }
-  double gg = 0, g1 = 0, gm = 0;
-  for (int b = tid; b < nblk; b += blockDim.x) {
-    const float* q = ext + (static_cast<long>(p) * nblk + b) * 4;
-    gg += q[0]; g1 += q[1]; gm = fmax(gm, static_cast<double>(q[2]));
-  }
-  gg = block_sum_128(gg, red);
-  g1 = block_sum_128(g1, red);
-  {  // block max
-    for (int o = 16; o > 0; o >>= 1) gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, o));
-    __syncthreads();
-    if ((tid & 31) == 0) red[tid >> 5] = gm;
-    __syncthreads();
-    gm = fmax(fmax(red[0], red[1]), fmax(red[2], red[3]));
-  }
+  const double gg = dp[M1 * 4 + 0], g1 = dp[M1 * 4 + 1], gm = dp[M1 * 4 + 2];
   __syncthreads();
 
   double* SY = mats + static_cast<long>(p) * 3 * M1 * M1;  // SY[i][j] = s_i . y_j
@@ -416,7 +444,7 @@ int clamp01(float* x, long n, cudaStream_t s) {
 }
 
 int lbfgs_tick(float* x, const float* g, float* g_prev, float* S, float* Y, LbfgsState* states, double* mats,
-               float* part, float* ext, const double* loss_c, const double* loss_s, int images_per_problem, int P,
+               float* part, float* ext, double* dots, const double* loss_c, const double* loss_s, int images_per_problem, int P,
                long N, const LbfgsConfig& cfg, double* hist_c, double* hist_s, int tick, cudaStream_t s) {
   const int M1 = cfg.history + 1;
   ISX_REQUIRE(M1 <= kMaxSlots, "lbfgs: history %d exceeds %d", cfg.history, kMaxSlots - 1);
@@ -427,8 +455,10 @@ int lbfgs_tick(float* x, const float* g, float* g_prev, float* S, float* Y, Lbfg
   isx_prof_begin(ISX_PROF_LBFGS, 0.0, s);  // both history passes + control; bytes are derived by the caller
   lbfgs_dots_kernel<<<grid, kDotThreads, sm1, s>>>(g, g_prev, S, Y, states, N, M1, nblk, part, ext);
   ISX_LAUNCH_CHECK();
-  lbfgs_control_kernel<<<P, 128, 0, s>>>(states, mats, part, ext, loss_c, loss_s, images_per_problem, M1, nblk, cfg,
-                                         hist_c, hist_s, tick, P);
+  lbfgs_reduce_kernel<<<dim3(M1 + 1, P), 128, 0, s>>>(states, part, ext, M1, nblk, dots);
+  ISX_LAUNCH_CHECK();
+  lbfgs_control_kernel<<<P, 128, 0, s>>>(states, mats, dots, loss_c, loss_s, images_per_problem, M1, cfg, hist_c, hist_s,
+                                         tick, P);
   ISX_LAUNCH_CHECK();
   lbfgs_update_kernel<<<grid, kDotThreads, 0, s>>>(x, g, g_prev, S, Y, states, N, M1);
   isx_prof_end(ISX_PROF_LBFGS, s);

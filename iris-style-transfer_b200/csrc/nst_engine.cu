@@ -105,6 +105,9 @@ int content_tap_of(const isx_nst_config* c, int conv) {
 int run_conv_fwd(const isx_nst_config* c, const isx_nst_buffers* b, const Layout& L, int i, const float* x,
                  cudaStream_t s) {
   const int lv = kLevel[i];
+  if (i == 0 && b->w0_fwd != nullptr)
+    return conv1_1_fwd_tc(x, c->xc, c->mask_b ? b->input_mask : nullptr, c->mask_b,
+                          reinterpret_cast<const bf16*>(b->w0_fwd), b->bias[0], at(b, L.act[0]), c->B, L.H[0], L.W[0], s);
   if (i == 0)
     return conv1_1_fwd(x, c->xc, c->mask_b ? b->input_mask : nullptr, c->mask_b, b->w0, b->bias[0], at(b, L.act[0]), c->B,
                        L.H[0], L.W[0], s);
@@ -300,6 +303,13 @@ extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, c
       }
     }
   }
+  if (b->w0_dgrad != nullptr) {
+    ConvArgs a;
+    a.in = gm; a.weight = reinterpret_cast<const bf16*>(b->w0_dgrad);
+    a.B = B; a.H = L.H[0]; a.W = L.W[0]; a.Cin = 64; a.Cout = 16; a.ntaps = 9;
+    a.dx_nchw = grad; a.xc = c->xc; a.in_mask = c->mask_b ? b->input_mask : nullptr; a.mask_b = c->mask_b;
+    return conv_tc(a, s);
+  }
   return conv1_1_dgrad(gm, b->w0, c->mask_b ? b->input_mask : nullptr, c->mask_b, grad, c->xc, B, L.H[0], L.W[0], s);
 }
 
@@ -312,7 +322,8 @@ extern "C" int64_t isx_lbfgs_mats_bytes(int P, int history) {
 }
 extern "C" int64_t isx_lbfgs_scratch_bytes(int P, int64_t N, int history) {
   const int64_t nblk = lbfgs_nblk(N);
-  return P * nblk * (static_cast<int64_t>(history + 1) * 4 + 4) * 4 + 256;
+  const int64_t floats = P * nblk * (static_cast<int64_t>(history + 1) * 4 + 4);
+  return ((floats * 4 + 255) / 256) * 256 + static_cast<int64_t>(P) * (history + 2) * 4 * 8 + 256;
 }
 extern "C" int isx_lbfgs_init(void* state, int P, isx_stream stream) {
   ISX_REQUIRE(state && P > 0, "isx_lbfgs_init: bad arguments");
@@ -332,8 +343,10 @@ extern "C" int isx_lbfgs_tick(float* x, const float* grad, float* grad_prev, flo
   const int nblk = lbfgs_nblk(N);
   float* part = static_cast<float*>(scratch);
   float* ext = part + static_cast<int64_t>(P) * nblk * (cfg->history + 1) * 4;
+  const int64_t floats = static_cast<int64_t>(P) * nblk * (static_cast<int64_t>(cfg->history + 1) * 4 + 4);
+  double* dots = reinterpret_cast<double*>(static_cast<char*>(scratch) + ((floats * 4 + 255) / 256) * 256);
   return lbfgs_tick(x, grad, grad_prev, Sh, Yh, static_cast<LbfgsState*>(state), static_cast<double*>(mats), part, ext,
-                    loss_c, loss_s, images_per_problem, P, N, lc, hist_c, hist_s, tick, S(stream));
+                    dots, loss_c, loss_s, images_per_problem, P, N, lc, hist_c, hist_s, tick, S(stream));
 }
 
 __global__ void done_flags_kernel(const LbfgsState* st, int P, int32_t* out) {

@@ -54,6 +54,8 @@ class NstConfig(ctypes.Structure):
 class NstBuffers(ctypes.Structure):
     _fields_ = [
         ("w0", ctypes.c_void_p),
+        ("w0_fwd", ctypes.c_void_p),
+        ("w0_dgrad", ctypes.c_void_p),
         ("bias", ctypes.c_void_p * N_CONVS),
         ("w_fwd", ctypes.c_void_p * N_CONVS),
         ("w_dgrad", ctypes.c_void_p * N_CONVS),
@@ -88,6 +90,10 @@ class PackedVGG:
         self.w_fwd: List[Optional[torch.Tensor]] = [None]
         self.w_dgrad: List[Optional[torch.Tensor]] = [None]
         with torch.cuda.device(self.device):
+            self.w0_dgrad = torch.empty(9, 16, 64, device=self.device, dtype=torch.bfloat16)
+            _lib.call("isx_pack_conv1_1_dgrad", self.w0, self.w0_dgrad, _lib.stream_ptr())
+            self.w0_fwd = torch.empty(64, 64, device=self.device, dtype=torch.bfloat16)
+            _lib.call("isx_pack_conv1_1_fwd", self.w0, self.w0_fwd, _lib.stream_ptr())
             for i in range(1, N_CONVS):
                 w = weights[i][0].detach().to(self.device, torch.float32).contiguous()
                 cout, cin = w.shape[:2]
@@ -135,6 +141,8 @@ class NstEngine:
         self.workspace = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
         bufs = NstBuffers()
         bufs.w0 = packed.w0.data_ptr()
+        bufs.w0_dgrad = packed.w0_dgrad.data_ptr()
+        bufs.w0_fwd = packed.w0_fwd.data_ptr()
         for i in range(N_CONVS):
             bufs.bias[i] = packed.bias[i].data_ptr()
             bufs.w_fwd[i] = packed.w_fwd[i].data_ptr() if packed.w_fwd[i] is not None else None

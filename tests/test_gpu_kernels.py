@@ -161,6 +161,14 @@ def test_conv1_1_fwd_dgrad(isx, xc, use_mask):
         xn = xn * mask
     y = F.relu(F.conv2d(xn, w, bias, padding=1))
     assert_close_bf16(out, y.detach().permute(0, 2, 3, 1), "conv1_1 fwd")
+    # tensor-core head: bf16 weights, input split into bf16 hi + lo
+    w0p = torch.empty(64, 64, device="cuda", dtype=torch.bfloat16)
+    isx.call("isx_pack_conv1_1_fwd", w, w0p, isx.stream_ptr())
+    out2 = torch.full_like(out, float("nan"))
+    isx.call("isx_conv1_1_fwd_tc", x, xc, mask, B, w0p, bias, out2, B, H, W, isx.stream_ptr())
+    torch.cuda.synchronize()
+    y2 = F.relu(F.conv2d(xn.detach(), w.to(torch.bfloat16).float(), bias, padding=1))
+    assert_close_bf16(out2, y2.permute(0, 2, 3, 1), "conv1_1 fwd (tensor cores)")
     dy = nhwc_bf16(B, H, W, 64, 7)
     y.backward(dy.float().permute(0, 3, 1, 2) * (y > 0))  # dy is "already ReLU-masked" in the kernel contract
     dyk = (dy.float() * (y.detach().permute(0, 2, 3, 1) > 0)).to(torch.bfloat16).contiguous()
@@ -175,6 +183,18 @@ def test_conv1_1_fwd_dgrad(isx, xc, use_mask):
         xn2 = xn2 * mask
     F.conv2d(xn2, w, bias, padding=1).backward(dyk.float().permute(0, 3, 1, 2))
     assert torch.allclose(dx, xr2.grad, rtol=1e-4, atol=1e-4 * xr2.grad.abs().max().item())
+    # the same tail on the tensor cores (bf16-rounded weights, fp32 accumulation)
+    wd0 = torch.empty(9, 16, 64, device="cuda", dtype=torch.bfloat16)
+    isx.call("isx_pack_conv1_1_dgrad", w, wd0, isx.stream_ptr())
+    dx2 = torch.full_like(dx, float("nan"))
+    isx.call("isx_conv1_1_dgrad_tc", dyk, wd0, mask, B, dx2, xc, B, H, W, isx.stream_ptr())
+    torch.cuda.synchronize()
+    xr3 = x.clone().requires_grad_(True)
+    xn3 = (xr3 - mean) / std
+    if use_mask:
+        xn3 = xn3 * mask
+    F.conv2d(xn3, w.to(torch.bfloat16).float(), bias, padding=1).backward(dyk.float().permute(0, 3, 1, 2))
+    assert torch.allclose(dx2, xr3.grad, rtol=1e-4, atol=1e-4 * xr3.grad.abs().max().item())
 
 
 @pytest.mark.parametrize("B,H,W,C", [(2, 20, 24, 64), (1, 25, 41, 128), (3, 8, 6, 512)])
