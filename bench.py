@@ -161,6 +161,9 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-features", action="store_true")
+    ap.add_argument("--history-bf16", action="store_true", help="opt-in: store the L-BFGS (s, y) history in bf16")
+    ap.add_argument("--feature-images", type=int, default=512, help="images per GPU of the feature-extraction leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -206,7 +209,8 @@ def main():
     # ------------------------------------------------------------------ device-resident leg
     with torch.cuda.device(dev), torch.no_grad():
         job = pipelines.NstJob(c_host.to(dev), s_host.to(dev), vgg, dev, clone_content=True, BN_loss=False,
-                               c_loss_weight=1.0, s_loss_weight=1e6, lr=1.0, epochs=K + Wm + 40, independent=True)
+                               c_loss_weight=1.0, s_loss_weight=1e6, lr=1.0, epochs=K + Wm + 40, independent=True,
+                               history_dtype=torch.bfloat16 if args.history_bf16 else torch.float32)
         x0 = job.x.clone()
         for _ in range(Wm):
             job.tick()
@@ -247,7 +251,8 @@ def main():
         t0 = time.perf_counter()
         x, _, c_hist, s_hist = iris_b200.nst(c_host, s_host, BN_loss=False, c_loss_weight=1.0, s_loss_weight=1e6,
                                               epochs=K, vgg=vgg, use_tqdm=False, device=str(dev), independent=True,
-                                              x_hist_stride=0)
+                                              x_hist_stride=0,
+                                              history_dtype=torch.bfloat16 if args.history_bf16 else torch.float32)
         x_host = x.cpu()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -263,6 +268,46 @@ def main():
                "note": "iris_b200.nst() from pinned host tensors to host results: targets, %d evaluations, final image "
                        "and per-evaluation losses copied back; wall clock" % evals}
         del x
+        torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ secondary metric: Gram-feature images/s
+    # BASELINE config[2]: style features (mean/std + Gram upper triangles of relu1_1..relu4_1) of synthetic eyes for
+    # the iris classifier, image list sharded contiguously over the ranks, ONE all-gather of the rows at the end.
+    feat = None
+    if not args.no_features:
+        from iris_b200 import features
+
+        n_per_gpu = args.feature_images
+        n_total = n_per_gpu * world
+        base, _ = __import__("iris_b200").synthetic.synthetic_batch(list(range(16)), H, W)   # 16 distinct eyes, tiled
+        base = torch.from_numpy(base).pin_memory()
+
+        class Tiled:
+            def __len__(self):
+                return n_total
+
+            def __getitem__(self, sl):
+                idx = torch.arange(sl.start, sl.stop) % base.shape[0]
+                return base[idx]
+
+        imgs = Tiled()
+        vgg_feat = iris_b200.VGG19(content_layers=[], weights=vgg.host_weights)  # forward stops at relu4_1
+        features.extract_features_sharded(vgg_feat, imgs, batch=32, device=dev)  # warm-up (workspaces, NCCL)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        rows = features.extract_features_sharded(vgg_feat, imgs, batch=32, device=dev)
+        f1.record()
+        barrier()
+        tf = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        feat = {"metric": "Gram-feature images/sec @640x400 (relu1_1..relu4_1: mean/std + Gram upper triangles)",
+                "value": n_total / (float(tf.item()) / 1e3), "unit": "images/s", "n_images": n_total,
+                "feature_dim": int(rows.shape[1]), "all_gather_bytes": int(rows.numel() * 4),
+                "flops_per_image": 131.96e9,
+                "note": "host (pinned) -> device copies of the frames inside the timed region; one NCCL all-gather"}
+        del rows
         torch.cuda.empty_cache()
 
     if rank != 0:
@@ -305,10 +350,10 @@ def main():
                                "3-channel, random-init VGG-19, Gram style loss (relu1_1..relu4_1) + content relu4_2, "
                                "alpha=1 beta=1e6, L-BFGS(lr=1, history 100), every image its own problem" % B,
                    "batch_per_gpu": B, "image": "3x%dx%d" % (H, W), "l2": "inputs larger than L2 (activations %.1f GB per step)"
-                   % (B * 139e6 / 1e9), "history_slots": hist_slots,
+                   % (B * 139e6 / 1e9), "history_slots": hist_slots, "history_dtype": "bf16" if args.history_bf16 else "f32",
                    "flops_per_image_step": FLOPS_PER_IMAGE_STEP,
                    "model_tflops": value * FLOPS_PER_IMAGE_STEP / 1e12 / world},
-        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": e2e, "secondary": feat, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "sanity": {"image_moved_mae": moved, "s_loss_first": loss_first, "s_loss_last": loss_last},
     }
     print(json.dumps(line), flush=True)

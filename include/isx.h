@@ -73,6 +73,11 @@ int isx_conv3x3_dgrad(const isx_bf16* dy, const isx_bf16* w_dgrad, isx_bf16* dx,
                       int Cout, const isx_bf16* relu_act, const isx_bf16* add_grad, const float* aff_a,
                       const float* aff_b, int tile_cfg, isx_stream stream);
 
+/* K3 + K5 fused: dx = relu'(act_below) * (dgrad(dy) + act_below . D[b]) -- the Gram tap gradient of the layer below
+ * (gram_D bf16 [B,Cin,Cin] from isx_gram_fwd) rides the same tcgen05 main loop as Cin/64 extra K blocks. */
+int isx_conv3x3_dgrad_gram(const isx_bf16* dy, const isx_bf16* w_dgrad, isx_bf16* dx, int B, int H, int W, int Cin,
+                           int Cout, const isx_bf16* act_below, const isx_bf16* gram_D, isx_stream stream);
+
 /* ---- K2: MaxPool2d(2,2) fwd / bwd (bwd fused with the ReLU mask of the pre-pool activation) ---- */
 int isx_maxpool2x2_fwd(const isx_bf16* in, isx_bf16* out, int B, int H, int W, int C, isx_stream stream);
 int isx_maxpool2x2_bwd(const isx_bf16* dy_pooled, const isx_bf16* act_prepool, isx_bf16* dx, int B, int H, int W,
@@ -108,12 +113,14 @@ int isx_tap_add_mask(const isx_bf16* g, const isx_bf16* add, const float* aff_a,
 /* ---- K7/K8: torch.optim.LBFGS([x], lr) with defaults (pipelines.py:59,103; torch/optim/lbfgs.py:333-537)
  * P independent problems of N floats each advance in lock step, one closure evaluation per tick.
  * All optimiser scalars live in device memory (state: isx_lbfgs_state_bytes(P)); history S,Y:
- * fp32 [P][history+1][N] each; mats: isx_lbfgs_mats_bytes(P, history); scratch: isx_lbfgs_scratch_bytes. */
+ * fp32 (or bf16, cfg->history_bf16) [P][history+1][N] each; mats: isx_lbfgs_mats_bytes(P, history); scratch: isx_lbfgs_scratch_bytes. */
 typedef struct {
   int32_t epochs;            /* closure evaluations requested (pipelines.py:16,79) */
   int32_t max_iter;          /* 20 */
   int32_t max_eval;          /* 25 */
   int32_t history;           /* 100 (<= 100) */
+  int32_t history_bf16;      /* 0: S,Y fp32 like the reference; 1: bf16 (halves the traffic of both history passes) */
+  int32_t reserved_;
   double lr;                 /* 1.0 */
   double tolerance_grad;     /* 1e-7 */
   double tolerance_change;   /* 1e-9 */
@@ -127,7 +134,7 @@ int isx_lbfgs_init(void* state, int P, isx_stream stream);
  * memory update + direction + x = clamp(x + t d, 0, 1) (lbfgs.py:396-526 + pipelines.py:82), or the
  * early-exit bookkeeping.  loss_c/loss_s: double [P*images_per_problem]; hist_c/hist_s: double
  * [ticks][P] loss logs (pipelines.py:94-95). */
-int isx_lbfgs_tick(float* x, const float* grad, float* grad_prev, float* S, float* Y, void* state, void* mats,
+int isx_lbfgs_tick(float* x, const float* grad, float* grad_prev, void* S, void* Y, void* state, void* mats,
                    void* scratch, const double* loss_c, const double* loss_s, int images_per_problem, int P,
                    int64_t N, const isx_lbfgs_config* cfg, double* hist_c, double* hist_s, int tick,
                    isx_stream stream);

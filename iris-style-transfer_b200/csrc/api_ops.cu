@@ -92,6 +92,17 @@ extern "C" int isx_conv3x3_dgrad(const isx_bf16* dy, const isx_bf16* w_dgrad, is
   return conv_tc(a, S(stream));
 }
 
+extern "C" int isx_conv3x3_dgrad_gram(const isx_bf16* dy, const isx_bf16* w_dgrad, isx_bf16* dx, int B, int H, int W,
+                                      int Cin, int Cout, const isx_bf16* act_below, const isx_bf16* gram_D,
+                                      isx_stream stream) {
+  ISX_REQUIRE(dy && w_dgrad && dx && act_below && gram_D, "isx_conv3x3_dgrad_gram: null pointer");
+  ConvArgs a;
+  a.in = P(dy); a.weight = P(w_dgrad); a.out = P(dx);
+  a.B = B; a.H = H; a.W = W; a.Cin = Cout; a.Cout = Cin; a.ntaps = 9;
+  a.mask_act = P(act_below); a.gram_act = P(act_below); a.gram_D = P(gram_D);
+  return conv_tc(a, S(stream));
+}
+
 extern "C" int isx_maxpool2x2_fwd(const isx_bf16* in, isx_bf16* out, int B, int H, int W, int C, isx_stream stream) {
   ISX_REQUIRE(in && out, "isx_maxpool2x2_fwd: null pointer");
   return maxpool_fwd(P(in), P(out), B, H, W, C, S(stream));

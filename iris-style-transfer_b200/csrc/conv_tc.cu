@@ -28,6 +28,7 @@ struct ConvParams {
   int tiles_x, tiles_y, tiles_b;
   int n_tiles;               // Cout / BN
   int w_rows_per_image;      // 0, or Cout when every image has its own [Cout x Cin] matrix (Gram bwd)
+  int extra_kb;              // fused Gram backward: extra K blocks (C/64) of  act(centre tap) x D_b  after the taps
   int stages;
   int relu;
   const float* bias;         // [Cout] or null
@@ -47,7 +48,8 @@ static constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
 template <int BN, int MT, int EPI>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmM,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const ConvParams p) {
   constexpr int kBTileBytes = BN * 128;
   constexpr int kStageBytes = MT * kATileBytes + kBTileBytes;
   constexpr int kTmemCols = (MT * BN) <= 32 ? 32 : (MT * BN) <= 64 ? 64 : (MT * BN) <= 128 ? 128 : (MT * BN) <= 256 ? 256 : 512;
@@ -59,7 +61,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * kStageBytes);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full_bar = empty_bar + stages;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* epi_bar = tmem_full_bar + 1;  // [2]: TMA loads of the ReLU-mask activation tile for the epilogue
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(epi_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -85,11 +88,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (EPI == 0) tma_prefetch_desc(&tmO);
+    if (EPI == 0 && p.mask_act != nullptr) tma_prefetch_desc(&tmM);
+    if (p.extra_kb > 0) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(&epi_bar[0], 1);
+    mbar_init(&epi_bar[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr_smem);
@@ -99,7 +106,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int cin_blocks = p.Cin >> 6;
-  const int num_kb = p.ntaps * cin_blocks;
+  const int num_kb_conv = p.ntaps * cin_blocks;
+  const int num_kb = num_kb_conv + p.extra_kb;
 
   if (warp == 0) {
     // ================================ TMA producer =========================================
@@ -110,15 +118,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = (kb / stages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-        const int tap = kb / cin_blocks;
-        const int cb = kb - tap * cin_blocks;
-        const int ky = p.ntaps == 9 ? tap / 3 : 1;
-        const int kx = p.ntaps == 9 ? tap - ky * 3 : 1;
         uint8_t* st = smem + s * kStageBytes;
+        if (kb < num_kb_conv) {
+          const int tap = kb / cin_blocks;
+          const int cb = kb - tap * cin_blocks;
+          const int ky = p.ntaps == 9 ? tap / 3 : 1;
+          const int kx = p.ntaps == 9 ? tap - ky * 3 : 1;
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-          tma_load_4d(st + mt * kATileBytes, &tmA, &full_bar[s], cb * 64, x0[mt] + kx - 1, y0[mt] + ky - 1, b0[mt]);
-        tma_load_2d(st + MT * kATileBytes, &tmB, &full_bar[s], cb * 64, tap * p.Cout + wrow0);
+          for (int mt = 0; mt < MT; ++mt)
+            tma_load_4d(st + mt * kATileBytes, &tmA, &full_bar[s], cb * 64, x0[mt] + kx - 1, y0[mt] + ky - 1, b0[mt]);
+          tma_load_2d(st + MT * kATileBytes, &tmB, &full_bar[s], cb * 64, tap * p.Cout + wrow0);
+        } else {
+          // fused Gram backward: dX += F . D_b  (F = activation of the layer below, D_b = dL/dG of image b)
+          const int cb = kb - num_kb_conv;
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            tma_load_4d(st + mt * kATileBytes, &tmA2, &full_bar[s], cb * 64, x0[mt], y0[mt], b0[mt]);
+          tma_load_2d(st + MT * kATileBytes, &tmB2, &full_bar[s], cb * 64, b0[0] * p.Cout + n0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -180,6 +197,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     } else {
+    constexpr int NG = MT * (BN / 64);                 // 64-channel output groups of this CTA
+    uint8_t* scratch = smem + NG * kATileBytes;          // 2 x 16 KB: ReLU-mask activation tiles (TMA, swizzled)
+    const bool use_mask = p.mask_act != nullptr;
+    auto issue_mask_load = [&](int gi) {
+      const int mt_ = gi / (BN / 64), g_ = gi % (BN / 64);
+      mbar_arrive_expect_tx(&epi_bar[gi & 1], kATileBytes);
+      tma_load_4d(scratch + (gi & 1) * kATileBytes, &tmM, &epi_bar[gi & 1], n0 + g_ * 64, x0[mt_], y0[mt_], b0[mt_]);
+    };
+    if (use_mask && threadIdx.x == 64) {
+      issue_mask_load(0);
+      if (NG > 1) issue_mask_load(1);
+    }
 #pragma unroll 1
     for (int mt = 0; mt < MT; ++mt) {
       const int x = x0[mt] + tw, y = y0[mt] + th, b = b0[mt] + tb;
@@ -187,7 +216,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const size_t pix = valid ? ((static_cast<size_t>(b) * p.H + y) * p.W + x) * p.Cout : 0;
 #pragma unroll 1
       for (int g = 0; g < BN / 64; ++g) {
-        uint8_t* stg = smem + (mt * (BN / 64) + g) * kATileBytes;  // pipeline smem is drained by now
+        const int gi = mt * (BN / 64) + g;
+        uint8_t* stg = smem + gi * kATileBytes;  // pipeline smem is drained by now
+        const uint8_t* mrow = scratch + (gi & 1) * kATileBytes + row * 128;
+        if (use_mask) mbar_wait(&epi_bar[gi & 1], (gi >> 1) & 1);
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
           const int nloc = g * 64 + h * 32;
@@ -216,26 +248,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               t = unpack_bf16x2(u.w); f[i + 6] += t.x; f[i + 7] += t.y;
             }
           }
-          if (p.mask_act != nullptr) {
-            if (valid) {
+          if (use_mask) {
+            // out-of-bounds rows of the box were zero-filled by TMA: act = 0 -> gradient 0 (never stored anyway)
 #pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.mask_act + pix + n + i));
-                float a[8];
-                float2 t;
-                t = unpack_bf16x2(u.x); a[0] = t.x; a[1] = t.y;
-                t = unpack_bf16x2(u.y); a[2] = t.x; a[3] = t.y;
-                t = unpack_bf16x2(u.z); a[4] = t.x; a[5] = t.y;
-                t = unpack_bf16x2(u.w); a[6] = t.x; a[7] = t.y;
-                if (p.aff_a != nullptr) {
-                  const float* pa = p.aff_a + static_cast<size_t>(b) * p.Cout + n + i;
-                  const float* pb = p.aff_b + static_cast<size_t>(b) * p.Cout + n + i;
+            for (int i = 0; i < 32; i += 8) {
+              const int chunk = (h * 4 + (i >> 3)) ^ (row & 7);
+              const uint4 u = *reinterpret_cast<const uint4*>(mrow + chunk * 16);
+              float a[8];
+              float2 t;
+              t = unpack_bf16x2(u.x); a[0] = t.x; a[1] = t.y;
+              t = unpack_bf16x2(u.y); a[2] = t.x; a[3] = t.y;
+              t = unpack_bf16x2(u.z); a[4] = t.x; a[5] = t.y;
+              t = unpack_bf16x2(u.w); a[6] = t.x; a[7] = t.y;
+              if (p.aff_a != nullptr && valid) {
+                const float* pa = p.aff_a + static_cast<size_t>(b) * p.Cout + n + i;
+                const float* pb = p.aff_b + static_cast<size_t>(b) * p.Cout + n + i;
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) f[i + j] += __ldg(pa + j) + __ldg(pb + j) * a[j];
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[i + j] = a[j] > 0.f ? f[i + j] : 0.f;
+                for (int j = 0; j < 8; ++j) f[i + j] += __ldg(pa + j) + __ldg(pb + j) * a[j];
               }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[i + j] = a[j] > 0.f ? f[i + j] : 0.f;
             }
           }
           if (p.relu) {
@@ -260,6 +292,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (threadIdx.x == 64) {
           tma_store_4d(&tmO, stg, n0 + g * 64, x0[mt], y0[mt], b0[mt]);
           tma_store_commit();
+          if (use_mask && gi + 2 < NG) issue_mask_load(gi + 2);  // scratch slot (gi & 1) has been read by everyone
         }
       }
     }
@@ -296,7 +329,8 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
   ConvParams p;
   memset(&p, 0, sizeof(p));
   p.B = a.B; p.H = a.H; p.W = a.W; p.Cin = a.Cin; p.Cout = a.Cout; p.ntaps = a.ntaps;
-  choose_patch(a.B, a.H, a.W, a.per_image_weights, &p.TW, &p.TH, &p.TB);
+  const bool per_image = a.per_image_weights || a.gram_act != nullptr;
+  choose_patch(a.B, a.H, a.W, per_image, &p.TW, &p.TH, &p.TB);
   p.tiles_x = (a.W + p.TW - 1) / p.TW;
   p.tiles_y = (a.H + p.TH - 1) / p.TH;
   p.tiles_b = (a.B + p.TB - 1) / p.TB;
@@ -305,21 +339,22 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
   p.relu = a.relu; p.bias = a.bias; p.mask_act = a.mask_act; p.add_buf = a.add_buf;
   p.aff_a = a.aff_a; p.aff_b = a.aff_b;
   p.dx_nchw = a.dx_nchw; p.xc = a.xc; p.in_mask = a.in_mask; p.mask_b = a.mask_b;
-  if (a.per_image_weights && MT != 1)
-    ISX_REQUIRE(p.tiles_b == a.B, "per-image weights need one image per tile");
+  p.extra_kb = a.gram_act != nullptr ? a.Cout / 64 : 0;
+  if (per_image && MT != 1)  // both M-tiles of a CTA must lie in one image (they share the per-image B slab)
+    ISX_REQUIRE(p.TB == 1 && (p.tiles_x * p.tiles_y) % MT == 0, "per-image weights: an odd tile count per image needs MT = 1");
 
   constexpr int kStageBytes = MT * kATileBytes + BN * 128;
   int stages = stages_override > 0 ? stages_override : (200 * 1024) / kStageBytes;
   if (stages > 8) stages = 8;
-  while (stages * kStageBytes < MT * (BN / 64) * kATileBytes) ++stages;  // epilogue staging aliases the pipeline
-  const int num_kb = a.ntaps * (a.Cin / 64);
-  if (stages > num_kb && num_kb * kStageBytes >= MT * (BN / 64) * kATileBytes) stages = num_kb;
+  // epilogue staging (one 16 KB tile per 64-channel group) + 2 mask-tile slots alias the drained pipeline
+  const int epi_bytes = (MT * (BN / 64) + (a.mask_act ? 2 : 0)) * kATileBytes;
   if (stages < 2) stages = 2;
+  while (stages * kStageBytes < epi_bytes) ++stages;
   p.stages = stages;
   const size_t smem_bytes = 1024 + static_cast<size_t>(stages) * kStageBytes + 256;
   ISX_REQUIRE(smem_bytes <= 227 * 1024, "conv_tc: %zu B of shared memory exceed 227 KB", smem_bytes);
 
-  CUtensorMap tmA, tmB, tmO;
+  CUtensorMap tmA, tmB, tmO, tmM, tmA2, tmB2;
   {
     uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
     uint64_t str[3] = {(uint64_t)a.Cin * 2, (uint64_t)a.W * a.Cin * 2, (uint64_t)a.H * a.W * a.Cin * 2};
@@ -341,12 +376,30 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
   } else {
     tmO = tmA;  // unused by the image-gradient epilogue
   }
+  tmM = tmO; tmA2 = tmA; tmB2 = tmB;
+  if (EPI == 0 && a.mask_act != nullptr) {
+    uint64_t dims[4] = {(uint64_t)a.Cout, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
+    uint64_t str[3] = {(uint64_t)a.Cout * 2, (uint64_t)a.W * a.Cout * 2, (uint64_t)a.H * a.W * a.Cout * 2};
+    uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
+    if (isx_make_tmap_bf16(&tmM, a.mask_act, 4, dims, str, box, true)) return 3;
+  }
+  if (a.gram_act != nullptr) {  // K = Cout channels of the layer below (its activation is [B,H,W,Cout] too)
+    uint64_t dims[4] = {(uint64_t)a.Cout, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
+    uint64_t str[3] = {(uint64_t)a.Cout * 2, (uint64_t)a.W * a.Cout * 2, (uint64_t)a.H * a.W * a.Cout * 2};
+    uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
+    if (isx_make_tmap_bf16(&tmA2, a.gram_act, 4, dims, str, box, true)) return 3;
+    uint64_t dims2[2] = {(uint64_t)a.Cout, (uint64_t)a.Cout * a.B};
+    uint64_t str2[1] = {(uint64_t)a.Cout * 2};
+    uint32_t box2[2] = {64, (uint32_t)BN};
+    if (isx_make_tmap_bf16(&tmB2, a.gram_D, 2, dims2, str2, box2, true)) return 3;
+  }
   const long sp_tiles = static_cast<long>(p.tiles_x) * p.tiles_y * p.tiles_b;
   const long grid = ((sp_tiles + MT - 1) / MT) * p.n_tiles;
   auto kern = conv_tc_kernel<BN, MT, EPI>;
   ISX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  isx_prof_begin(ISX_PROF_CONV, 2.0 * a.ntaps * a.Cin * a.Cout * static_cast<double>(a.B) * a.H * a.W, stream);
-  kern<<<(unsigned)grid, 192, smem_bytes, stream>>>(tmA, tmB, tmO, p);
+  isx_prof_begin(ISX_PROF_CONV,
+                 2.0 * (a.ntaps * a.Cin + (a.gram_act ? a.Cout : 0)) * a.Cout * static_cast<double>(a.B) * a.H * a.W, stream);
+  kern<<<(unsigned)grid, 192, smem_bytes, stream>>>(tmA, tmB, tmO, tmM, tmA2, tmB2, p);
   isx_prof_end(ISX_PROF_CONV, stream);
   ISX_LAUNCH_CHECK();
   return 0;
@@ -364,6 +417,7 @@ int conv_tc(const ConvArgs& a, cudaStream_t stream) {
   ISX_REQUIRE(a.ntaps == 9 || a.ntaps == 1, "conv_tc: ntaps must be 9 or 1");
   ISX_REQUIRE(a.B > 0 && a.H > 0 && a.W > 0, "conv_tc: empty input");
   ISX_REQUIRE((a.aff_a == nullptr) || (a.mask_act != nullptr), "conv_tc: affine tap gradient needs the activation");
+  ISX_REQUIRE((a.gram_act == nullptr) || (a.gram_D != nullptr && !a.per_image_weights), "conv_tc: bad fused-Gram arguments");
   int bn = a.force_bn, mt = a.force_mt;
   int st = a.force_stages;
   if (bn == 0) {
@@ -380,6 +434,11 @@ int conv_tc(const ConvArgs& a, cudaStream_t stream) {
     auto ctas = [&](int BN_, int MT_) { return ((pix_tiles + MT_ - 1) / MT_) * (a.Cout / BN_); };
     if (ctas(bn, mt) < 2 * kNumSMs && mt == 2) mt = 1;
     if (ctas(bn, mt) < 2 * kNumSMs && bn == 256) bn = 128;
+    if (a.gram_act != nullptr && mt == 2) {  // fused Gram backward: both M-tiles must share one image
+      int tw, th, tb;
+      choose_patch(a.B, a.H, a.W, true, &tw, &th, &tb);
+      if ((((a.W + tw - 1) / tw) * ((a.H + th - 1) / th)) % 2 != 0) mt = 1;
+    }
   }
   if (mt == 0) mt = 1;
 #define ISX_CONV_CASE(BN_, MT_) \

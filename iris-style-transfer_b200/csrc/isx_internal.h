@@ -20,6 +20,9 @@ struct ConvArgs {
   const float* aff_a = nullptr;
   const float* aff_b = nullptr;
   int force_bn = 0, force_mt = 0, force_stages = 0;  // tuning / test hooks (0 = heuristic)
+  // fused Gram backward: out += gram_act . gram_D[b]   (gram_act [B,H,W,Cout], gram_D bf16 [B,Cout,Cout])
+  const __nv_bfloat16* gram_act = nullptr;
+  const __nv_bfloat16* gram_D = nullptr;
   // image-gradient tail (conv1_1 dgrad): when dx_nchw != null the epilogue writes fp32 NCHW instead of `out`
   float* dx_nchw = nullptr;
   int xc = 3;

@@ -49,13 +49,46 @@ __device__ __forceinline__ void store8(float* p, long i, long n, const float (&v
   }
 }
 
+// history element type: float (the reference's fp32 state) or bf16 (opt-in: halves the HBM traffic of both passes)
+__device__ __forceinline__ void hload8(const float* p, long i, long n, float (&v)[8]) { load8(p, i, n, v); }
+__device__ __forceinline__ void hstore8(float* p, long i, long n, const float (&v)[8]) { store8(p, i, n, v); }
+__device__ __forceinline__ void hload8(const __nv_bfloat16* p, long i, long n, float (&v)[8]) {
+  if (i + 8 <= n) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p + i));
+    float2 t;
+    t = unpack_bf16x2(u.x); v[0] = t.x; v[1] = t.y;
+    t = unpack_bf16x2(u.y); v[2] = t.x; v[3] = t.y;
+    t = unpack_bf16x2(u.z); v[4] = t.x; v[5] = t.y;
+    t = unpack_bf16x2(u.w); v[6] = t.x; v[7] = t.y;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (i + j < n) ? __bfloat162float(p[i + j]) : 0.f;
+  }
+}
+__device__ __forceinline__ void hstore8(__nv_bfloat16* p, long i, long n, const float (&v)[8]) {
+  if (i + 8 <= n) {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p + i) = u;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (i + j < n) p[i + j] = __float2bfloat16_rn(v[j]);
+  }
+}
+// what the stored (possibly rounded) value reads back as: the inner products must see exactly the stored pair
+__device__ __forceinline__ float hround(float v, const float*) { return v; }
+__device__ __forceinline__ float hround(float v, const __nv_bfloat16*) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
 // ---------------------------------------------------------------------------------------------
 // pass 1
 // partial layout: part[p][blk][slot][4] floats then extras: ext[p][blk][4] = {sum g^2, sum |g|, max |g|, 0}
 // ---------------------------------------------------------------------------------------------
+template <typename HT>
 __global__ void __launch_bounds__(kDotThreads)
-lbfgs_dots_kernel(const float* __restrict__ g, const float* __restrict__ g_prev, const float* __restrict__ S,
-                  float* __restrict__ Y, const LbfgsState* __restrict__ states, long N, int M1, int nblk,
+lbfgs_dots_kernel(const float* __restrict__ g, const float* __restrict__ g_prev, const HT* __restrict__ S,
+                  HT* __restrict__ Y, const LbfgsState* __restrict__ states, long N, int M1, int nblk,
                   float* __restrict__ part, float* __restrict__ ext) {
   const int p = blockIdx.y;
   const LbfgsState& st = states[p];
@@ -72,8 +105,8 @@ lbfgs_dots_kernel(const float* __restrict__ g, const float* __restrict__ g_prev,
     float pv[8];
     load8(g_prev + p * N, i0, N, pv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) yv[j] = gv[j] - pv[j];  // lbfgs.py:404
-    store8(Y + (static_cast<long>(p) * M1 + cand) * N, i0, N, yv);
+    for (int j = 0; j < 8; ++j) yv[j] = hround(gv[j] - pv[j], Y);  // lbfgs.py:404
+    hstore8(Y + (static_cast<long>(p) * M1 + cand) * N, i0, N, yv);
   } else {
 #pragma unroll
     for (int j = 0; j < 8; ++j) yv[j] = 0.f;
@@ -94,12 +127,12 @@ lbfgs_dots_kernel(const float* __restrict__ g, const float* __restrict__ g_prev,
   for (int k = 0; k < nlive; ++k) {
     const int slot = k < st.hist_count ? (st.hist_head + k) % M1 : cand;
     float sv[8], hv[8];
-    load8(S + (static_cast<long>(p) * M1 + slot) * N, i0, N, sv);
+    hload8(S + (static_cast<long>(p) * M1 + slot) * N, i0, N, sv);
     if (slot == cand) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) hv[j] = yv[j];
     } else {
-      load8(Y + (static_cast<long>(p) * M1 + slot) * N, i0, N, hv);
+      hload8(Y + (static_cast<long>(p) * M1 + slot) * N, i0, N, hv);
     }
     float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
@@ -371,9 +404,10 @@ lbfgs_control_kernel(LbfgsState* __restrict__ states, double* __restrict__ mats,
 // ---------------------------------------------------------------------------------------------
 // pass 2
 // ---------------------------------------------------------------------------------------------
+template <typename HT>
 __global__ void __launch_bounds__(kDotThreads)
 lbfgs_update_kernel(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ g_prev,
-                    float* __restrict__ S, const float* __restrict__ Y, LbfgsState* __restrict__ states, long N,
+                    HT* __restrict__ S, const HT* __restrict__ Y, LbfgsState* __restrict__ states, long N,
                     int M1) {
   const int p = blockIdx.y;
   LbfgsState& st = states[p];
@@ -389,8 +423,8 @@ lbfgs_update_kernel(float* __restrict__ x, const float* __restrict__ g, float* _
     const int slot = (head + k) % M1;
     const float a = st.coef_s[slot], b = st.coef_y[slot];
     float sv[8], yv[8];
-    load8(S + (static_cast<long>(p) * M1 + slot) * N, i0, N, sv);
-    load8(Y + (static_cast<long>(p) * M1 + slot) * N, i0, N, yv);
+    hload8(S + (static_cast<long>(p) * M1 + slot) * N, i0, N, sv);
+    hload8(Y + (static_cast<long>(p) * M1 + slot) * N, i0, N, yv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) d[j] = fmaf(a, sv[j], fmaf(b, yv[j], d[j]));
   }
@@ -399,7 +433,7 @@ lbfgs_update_kernel(float* __restrict__ x, const float* __restrict__ g, float* _
   float mx = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sv[j] = d[j] * t; mx = fmaxf(mx, fabsf(sv[j])); }  // s = d.mul(t), lbfgs.py:405
-  store8(S + (static_cast<long>(p) * M1 + st.cand_slot) * N, i0, N, sv);
+  hstore8(S + (static_cast<long>(p) * M1 + st.cand_slot) * N, i0, N, sv);
   store8(g_prev + p * N, i0, N, gv);  // lbfgs.py:444-447
   if (st.apply) {
     float xv[8];
@@ -443,7 +477,7 @@ int clamp01(float* x, long n, cudaStream_t s) {
   return 0;
 }
 
-int lbfgs_tick(float* x, const float* g, float* g_prev, float* S, float* Y, LbfgsState* states, double* mats,
+int lbfgs_tick(float* x, const float* g, float* g_prev, void* S, void* Y, int history_bf16, LbfgsState* states, double* mats,
                float* part, float* ext, double* dots, const double* loss_c, const double* loss_s, int images_per_problem, int P,
                long N, const LbfgsConfig& cfg, double* hist_c, double* hist_s, int tick, cudaStream_t s) {
   const int M1 = cfg.history + 1;
@@ -453,14 +487,25 @@ int lbfgs_tick(float* x, const float* g, float* g_prev, float* S, float* Y, Lbfg
   dim3 grid(nblk, P);
   const size_t sm1 = static_cast<size_t>(M1) * 8 * 4 * sizeof(float);
   isx_prof_begin(ISX_PROF_LBFGS, 0.0, s);  // both history passes + control; bytes are derived by the caller
-  lbfgs_dots_kernel<<<grid, kDotThreads, sm1, s>>>(g, g_prev, S, Y, states, N, M1, nblk, part, ext);
+  ISX_REQUIRE(!history_bf16 || N % 8 == 0, "lbfgs: bf16 history needs a problem size that is a multiple of 8");
+  if (history_bf16)
+    lbfgs_dots_kernel<__nv_bfloat16><<<grid, kDotThreads, sm1, s>>>(g, g_prev, static_cast<const __nv_bfloat16*>(S),
+                                                                    static_cast<__nv_bfloat16*>(Y), states, N, M1, nblk, part, ext);
+  else
+    lbfgs_dots_kernel<float><<<grid, kDotThreads, sm1, s>>>(g, g_prev, static_cast<const float*>(S), static_cast<float*>(Y),
+                                                            states, N, M1, nblk, part, ext);
   ISX_LAUNCH_CHECK();
   lbfgs_reduce_kernel<<<dim3(M1 + 1, P), 128, 0, s>>>(states, part, ext, M1, nblk, dots);
   ISX_LAUNCH_CHECK();
   lbfgs_control_kernel<<<P, 128, 0, s>>>(states, mats, dots, loss_c, loss_s, images_per_problem, M1, cfg, hist_c, hist_s,
                                          tick, P);
   ISX_LAUNCH_CHECK();
-  lbfgs_update_kernel<<<grid, kDotThreads, 0, s>>>(x, g, g_prev, S, Y, states, N, M1);
+  if (history_bf16)
+    lbfgs_update_kernel<__nv_bfloat16><<<grid, kDotThreads, 0, s>>>(x, g, g_prev, static_cast<__nv_bfloat16*>(S),
+                                                                    static_cast<const __nv_bfloat16*>(Y), states, N, M1);
+  else
+    lbfgs_update_kernel<float><<<grid, kDotThreads, 0, s>>>(x, g, g_prev, static_cast<float*>(S), static_cast<const float*>(Y),
+                                                            states, N, M1);
   isx_prof_end(ISX_PROF_LBFGS, s);
   ISX_LAUNCH_CHECK();
   return 0;

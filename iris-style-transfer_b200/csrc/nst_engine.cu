@@ -263,10 +263,13 @@ extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, c
     const long HWj = static_cast<long>(L.H[lvj]) * L.W[lvj];
     const int st = style_tap_of(c, j), ct = content_tap_of(c, j);
     const bool through_pool = pool_after(j);
-    // tap gradient of layer j (computed before the dgrad that consumes it)
+    // tap gradient of layer j (computed before the dgrad that consumes it, or fused into it)
     const bf16* add = nullptr;
     const float *aa = nullptr, *ab = nullptr;
-    if (st >= 0 && c->style_mode == 0) {
+    const bf16* fused_gram_D = nullptr;
+    if (st >= 0 && c->style_mode == 0 && !through_pool && ct < 0) {
+      fused_gram_D = at(b, L.D[st]);  // dF = F . D rides the dgrad main loop as extra K blocks
+    } else if (st >= 0 && c->style_mode == 0) {
       ConvArgs a;
       a.in = at(b, L.act[j]); a.weight = at(b, L.D[st]); a.out = tapbuf;
       a.B = B; a.H = L.H[lvj]; a.W = L.W[lvj]; a.Cin = Cj; a.Cout = Cj; a.ntaps = 1; a.per_image_weights = true;
@@ -288,6 +291,7 @@ extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, c
     a.out = ping;
     if (!through_pool) {
       a.mask_act = at(b, L.act[j]); a.add_buf = add; a.aff_a = aa; a.aff_b = ab;
+      if (fused_gram_D) { a.gram_act = at(b, L.act[j]); a.gram_D = fused_gram_D; }
       if (int rc = conv_tc(a, s)) return rc;
       gm = ping;
       std::swap(ping, pong);
@@ -329,7 +333,7 @@ extern "C" int isx_lbfgs_init(void* state, int P, isx_stream stream) {
   ISX_REQUIRE(state && P > 0, "isx_lbfgs_init: bad arguments");
   return lbfgs_init(static_cast<LbfgsState*>(state), P, S(stream));
 }
-extern "C" int isx_lbfgs_tick(float* x, const float* grad, float* grad_prev, float* Sh, float* Yh, void* state,
+extern "C" int isx_lbfgs_tick(float* x, const float* grad, float* grad_prev, void* Sh, void* Yh, void* state,
                               void* mats, void* scratch, const double* loss_c, const double* loss_s,
                               int images_per_problem, int P, int64_t N, const isx_lbfgs_config* cfg, double* hist_c,
                               double* hist_s, int tick, isx_stream stream) {
@@ -345,7 +349,7 @@ extern "C" int isx_lbfgs_tick(float* x, const float* grad, float* grad_prev, flo
   float* ext = part + static_cast<int64_t>(P) * nblk * (cfg->history + 1) * 4;
   const int64_t floats = static_cast<int64_t>(P) * nblk * (static_cast<int64_t>(cfg->history + 1) * 4 + 4);
   double* dots = reinterpret_cast<double*>(static_cast<char*>(scratch) + ((floats * 4 + 255) / 256) * 256);
-  return lbfgs_tick(x, grad, grad_prev, Sh, Yh, static_cast<LbfgsState*>(state), static_cast<double*>(mats), part, ext,
+  return lbfgs_tick(x, grad, grad_prev, Sh, Yh, cfg->history_bf16, static_cast<LbfgsState*>(state), static_cast<double*>(mats), part, ext,
                     dots, loss_c, loss_s, images_per_problem, P, N, lc, hist_c, hist_s, tick, S(stream));
 }
 

@@ -71,7 +71,8 @@ class NstBuffers(ctypes.Structure):
 class LbfgsConfig(ctypes.Structure):
     _fields_ = [
         ("epochs", ctypes.c_int32), ("max_iter", ctypes.c_int32), ("max_eval", ctypes.c_int32),
-        ("history", ctypes.c_int32), ("lr", ctypes.c_double), ("tolerance_grad", ctypes.c_double),
+        ("history", ctypes.c_int32), ("history_bf16", ctypes.c_int32), ("reserved_", ctypes.c_int32),
+        ("lr", ctypes.c_double), ("tolerance_grad", ctypes.c_double),
         ("tolerance_change", ctypes.c_double), ("c_weight", ctypes.c_double), ("s_weight", ctypes.c_double),
     ]
 

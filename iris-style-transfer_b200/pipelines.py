@@ -30,7 +30,8 @@ class NstJob:
     `tick()` = one closure evaluation (pipelines.py:80-101) + one L-BFGS iteration for the whole batch."""
 
     def __init__(self, c_img, s_img, vgg, dev, clone_content=True, BN_loss=True, c_loss_weight=1.0,
-                 s_loss_weight=1.0, lr=1.0, epochs=200, independent=False, history_size=100, x_init=None):
+                 s_loss_weight=1.0, lr=1.0, epochs=200, independent=False, history_size=100, x_init=None,
+                 history_dtype=torch.float32):
         c_img, _ = _prep_images(c_img, dev)
         s_img, s_unbatched = _prep_images(s_img, dev)
         if clone_content:
@@ -76,7 +77,10 @@ class NstJob:
         self.P, self.ipp, self.N = P, B // P, self.x.numel() // P
         # one (y, s) pair per iteration, so a short job never needs all 100 slots
         hist = max(1, min(int(history_size), self.epochs + 20))
-        self.cfg = LbfgsConfig(epochs=self.epochs, max_iter=20, max_eval=25, history=hist, lr=float(lr),
+        if history_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("history_dtype must be torch.float32 (reference) or torch.bfloat16")
+        self.cfg = LbfgsConfig(epochs=self.epochs, max_iter=20, max_eval=25, history=hist,
+                               history_bf16=int(history_dtype == torch.bfloat16), reserved_=0, lr=float(lr),
                                tolerance_grad=1e-7, tolerance_change=1e-9, c_weight=float(c_loss_weight),
                                s_weight=float(s_loss_weight))
         self.max_ticks = self.epochs + 20
@@ -86,8 +90,8 @@ class NstJob:
         self.mats = torch.zeros(_lib.call_i64("isx_lbfgs_mats_bytes", P, hist), device=dev, dtype=torch.uint8)
         self.scratch = torch.empty(_lib.call_i64("isx_lbfgs_scratch_bytes", P, _lib.i64(N), hist), device=dev,
                                    dtype=torch.uint8)
-        self.Sh = torch.empty(P, M1, N, device=dev, dtype=torch.float32)
-        self.Yh = torch.empty(P, M1, N, device=dev, dtype=torch.float32)
+        self.Sh = torch.empty(P, M1, N, device=dev, dtype=history_dtype)
+        self.Yh = torch.empty(P, M1, N, device=dev, dtype=history_dtype)
         self.grad = torch.empty_like(self.x)
         self.grad_prev = torch.empty_like(self.x)
         self.hist_c = torch.zeros(self.max_ticks, P, device=dev, dtype=torch.float64)
@@ -135,6 +139,7 @@ def nst(c_img: torch.Tensor,
         x_hist_stride: int = 1,
         history_size: int = 100,
         x_init: Optional[torch.Tensor] = None,
+        history_dtype: torch.dtype = torch.float32,
         ) -> tuple[torch.Tensor, list, list, list]:
     """Neural style transfer pipeline (pipelines.py:8-110).
 
@@ -145,6 +150,8 @@ def nst(c_img: torch.Tensor,
       x_hist_stride keep every k-th evaluated image in x_hist (1 = reference behaviour, 0 = none).
       history_size  L-BFGS history (torch default 100).
       x_init        replaces torch.rand (pipelines.py:54) when clone_content is False.
+      history_dtype torch.float32 (the reference's optimiser state) or torch.bfloat16: the (s, y) history is then
+                    stored in bf16, halving the HBM traffic and footprint of the L-BFGS passes (opt-in).
     c_loss_hist / s_loss_hist hold one float per closure evaluation, aggregated over the batch the way
     the reference's batched losses are (content: mean over images, style: sum over images); per-image
     values are left in `pipelines.last_info`."""
@@ -159,7 +166,7 @@ def nst(c_img: torch.Tensor,
     with torch.cuda.device(dev), torch.no_grad():
         job = NstJob(c_img, s_img, vgg, dev, clone_content=clone_content, BN_loss=BN_loss,
                      c_loss_weight=c_loss_weight, s_loss_weight=s_loss_weight, lr=lr, epochs=epochs,
-                     independent=independent, history_size=history_size, x_init=x_init)
+                     independent=independent, history_size=history_size, x_init=x_init, history_dtype=history_dtype)
         x_hist: List[torch.Tensor] = []
         pbar = None
         if use_tqdm:

@@ -99,6 +99,26 @@ def test_conv3x3_dgrad(isx, shape, mode):
     assert_close_bf16(dx, ref, "dgrad %s %s" % (shape, mode))
 
 
+@pytest.mark.parametrize("shape", [(2, 20, 24, 64, 64), (3, 13, 9, 128, 128), (1, 50, 80, 256, 256), (2, 25, 40, 512, 512),
+                                   (2, 16, 24, 64, 128)])
+def test_conv3x3_dgrad_fused_gram(isx, shape):
+    """dx = relu'(act) * (dgrad(dy) + act . D[b]): the Gram tap gradient as extra K blocks of the dgrad GEMM."""
+    B, H, W, Cin, Cout = shape
+    dy = nhwc_bf16(B, H, W, Cout, 2)
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") * (2.0 / (9 * Cout)) ** 0.5
+    _, wd = pack(isx, w)
+    act = nhwc_bf16(B, H, W, Cin, 3, relu=True)
+    D = torch.randn(B, Cin, Cin, device="cuda") * 0.05
+    D = (D + D.transpose(1, 2)).to(torch.bfloat16).contiguous()
+    dx = torch.full((B, H, W, Cin), float("nan"), device="cuda", dtype=torch.bfloat16)
+    isx.call("isx_conv3x3_dgrad_gram", dy, wd, dx, B, H, W, Cin, Cout, act, D, isx.stream_ptr())
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), padding=1).permute(0, 2, 3, 1)
+    ref = ref + torch.bmm(act.float().reshape(B, H * W, Cin), D.float()).reshape(B, H, W, Cin)
+    ref = torch.where(act.float() > 0, ref, torch.zeros_like(ref))
+    assert_close_bf16(dx, ref, "dgrad + fused gram %s" % (shape,))
+
+
 @pytest.mark.parametrize("C", [64, 128, 256, 512])
 @pytest.mark.parametrize("B,H,W", [(1, 50, 80), (3, 17, 23), (2, 100, 160)])
 def test_gram_fwd_and_loss(isx, C, B, H, W):

@@ -91,7 +91,7 @@ def test_lbfgs_matches_oracle(mods, epochs, history):
     # ---- device optimiser fed by the same torch objective ----
     x = x0.clone().contiguous()
     M1 = history + 1
-    cfg = E.LbfgsConfig(epochs=epochs, max_iter=20, max_eval=25, history=history, lr=1.0, tolerance_grad=1e-7,
+    cfg = E.LbfgsConfig(epochs=epochs, max_iter=20, max_eval=25, history=history, history_bf16=0, reserved_=0, lr=1.0, tolerance_grad=1e-7,
                         tolerance_change=1e-9, c_weight=1.0, s_weight=0.0)
     state = torch.empty(lib.call_i64("isx_lbfgs_state_bytes", P), device=dev, dtype=torch.uint8)
     mats = torch.zeros(lib.call_i64("isx_lbfgs_mats_bytes", P, history), device=dev, dtype=torch.uint8)
@@ -344,6 +344,23 @@ def test_nst_eye_final_image_within_1e2(mods, H, W, epochs, BN, beta):
     assert moved > 5e-3, "degenerate problem: the oracle image did not move"
     assert mae <= 1e-2 and mae <= 0.5 * moved
     assert sh[-1] <= 3 * sr[-1] + 1e-12
+
+
+def test_nst_bf16_history_option(mods):
+    """Opt-in bf16 (s, y) history: same evaluation count, final image still within 1e-2 of the fp32 oracle."""
+    from iris_b200 import synthetic
+
+    O = mods["O"]
+    fr, _ = synthetic.synthetic_batch([1, 2], 160, 100)
+    c = torch.from_numpy(fr[0]).repeat(3, 1, 1)[None]
+    s = torch.from_numpy(fr[1]).repeat(3, 1, 1)[None]
+    xr, _, cr, sr = O.nst(c, s, mods["weights"], BN_loss=False, s_loss_weight=1e6, epochs=40, keep_hist=False)
+    x, _, ch, sh = _run(mods, c, s, BN_loss=False, s_loss_weight=1e6, epochs=40, x_hist_stride=0,
+                        history_dtype=torch.bfloat16)
+    mae = float((x - xr).abs().mean())
+    print("bf16 history: evals %d MAE %.5f s_final %.4g/%.4g" % (len(sh), mae, sh[-1], sr[-1]))
+    assert len(sh) == len(sr) == 40
+    assert mae <= 1e-2 and sh[-1] <= 3 * sr[-1] + 1e-12
 
 
 def test_cpu_device_is_refused(mods):
