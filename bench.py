@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-features", action="store_true")
+    ap.add_argument("--streams", type=int, default=1, help="sub-batches on separate CUDA streams (overlap L-BFGS and convs)")
     ap.add_argument("--history-bf16", action="store_true", help="opt-in: store the L-BFGS (s, y) history in bf16")
     ap.add_argument("--feature-images", type=int, default=512, help="images per GPU of the feature-extraction leg")
     args = ap.parse_args()
@@ -208,10 +209,16 @@ def main():
 
     # ------------------------------------------------------------------ device-resident leg
     with torch.cuda.device(dev), torch.no_grad():
-        job = pipelines.NstJob(c_host.to(dev), s_host.to(dev), vgg, dev, clone_content=True, BN_loss=False,
-                               c_loss_weight=1.0, s_loss_weight=1e6, lr=1.0, epochs=K + Wm + 40, independent=True,
-                               history_dtype=torch.bfloat16 if args.history_bf16 else torch.float32)
-        x0 = job.x.clone()
+        jkw = dict(clone_content=True, BN_loss=False, c_loss_weight=1.0, s_loss_weight=1e6, lr=1.0, epochs=K + Wm + 40,
+                   independent=True, history_dtype=torch.bfloat16 if args.history_bf16 else torch.float32)
+        if args.streams > 1:
+            job = pipelines.NstJobGroup(c_host.to(dev), s_host.to(dev), vgg, dev, streams=args.streams, **jkw)
+            subjobs = job.jobs
+        else:
+            job = pipelines.NstJob(c_host.to(dev), s_host.to(dev), vgg, dev, **jkw)
+            subjobs = [job]
+        torch.cuda.synchronize()
+        x0 = torch.cat([j.x for j in subjobs]).clone()
         for _ in range(Wm):
             job.tick()
         barrier()
@@ -222,8 +229,12 @@ def main():
         launches0 = lib.isx_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        if args.streams > 1:
+            job.fork(dev)
         for _ in range(K):
             job.tick()
+        if args.streams > 1:
+            job.join(dev)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -232,11 +243,11 @@ def main():
         _lib.call("isx_prof_collect", prof, 9)
         lib.isx_prof_enable(0)
         clocks = sampler.stop() if rank == 0 else None
-        moved = float((job.x - x0).abs().mean())
-        loss_first = float(job.hist_s[0].sum())
-        loss_last = float(job.hist_s[job.ticks - 1].sum())
-        hist_slots = job.cfg.history
-        del job
+        moved = float((torch.cat([j.x for j in subjobs]) - x0).abs().mean())
+        loss_first = float(sum(j.hist_s[0].sum() for j in subjobs))
+        loss_last = float(sum(j.hist_s[j.ticks - 1].sum() for j in subjobs))
+        hist_slots = subjobs[0].cfg.history
+        del job, subjobs
         torch.cuda.empty_cache()
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -251,7 +262,7 @@ def main():
         t0 = time.perf_counter()
         x, _, c_hist, s_hist = iris_b200.nst(c_host, s_host, BN_loss=False, c_loss_weight=1.0, s_loss_weight=1e6,
                                               epochs=K, vgg=vgg, use_tqdm=False, device=str(dev), independent=True,
-                                              x_hist_stride=0,
+                                              x_hist_stride=0, streams=args.streams,
                                               history_dtype=torch.bfloat16 if args.history_bf16 else torch.float32)
         x_host = x.cpu()
         torch.cuda.synchronize()
@@ -350,7 +361,7 @@ def main():
                                "3-channel, random-init VGG-19, Gram style loss (relu1_1..relu4_1) + content relu4_2, "
                                "alpha=1 beta=1e6, L-BFGS(lr=1, history 100), every image its own problem" % B,
                    "batch_per_gpu": B, "image": "3x%dx%d" % (H, W), "l2": "inputs larger than L2 (activations %.1f GB per step)"
-                   % (B * 139e6 / 1e9), "history_slots": hist_slots, "history_dtype": "bf16" if args.history_bf16 else "f32",
+                   % (B * 139e6 / 1e9), "history_slots": hist_slots, "history_dtype": "bf16" if args.history_bf16 else "f32", "streams": args.streams,
                    "flops_per_image_step": FLOPS_PER_IMAGE_STEP,
                    "model_tflops": value * FLOPS_PER_IMAGE_STEP / 1e12 / world},
         "e2e": e2e, "secondary": feat, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

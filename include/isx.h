@@ -133,7 +133,8 @@ int isx_lbfgs_init(void* state, int P, isx_stream stream);
 /* One tick AFTER a closure evaluation produced grad and the per-image losses:
  * memory update + direction + x = clamp(x + t d, 0, 1) (lbfgs.py:396-526 + pipelines.py:82), or the
  * early-exit bookkeeping.  loss_c/loss_s: double [P*images_per_problem]; hist_c/hist_s: double
- * [ticks][P] loss logs (pipelines.py:94-95). */
+ * [evaluations][P] loss logs (pipelines.py:94-95), row = the problem's own evaluation counter (`tick` is
+ * informational: every launch parameter is tick-invariant so one tick can be captured in a CUDA graph). */
 int isx_lbfgs_tick(float* x, const float* grad, float* grad_prev, void* S, void* Y, void* state, void* mats,
                    void* scratch, const double* loss_c, const double* loss_s, int images_per_problem, int P,
                    int64_t N, const isx_lbfgs_config* cfg, double* hist_c, double* hist_s, int tick,
@@ -215,6 +216,9 @@ int isx_composite(const float* new_iris, int src_c, int SH, int SW, float* frame
  * stream; after a device sync isx_prof_collect fills out[3*family + {0,1,2}] = {launches, total ms,
  * total algorithmic work (FLOPs for 0/1, bytes for 2)}. */
 unsigned long long isx_launch_count(void);
+/* tuning knobs: "halo_mode" (0 = one TMA box per tap, 1/2 = halo patch + shifted descriptor views for 3x3 convs),
+ * "halo_max_cout" (widest Cout the halo variant is used for) */
+int isx_set_option(const char* name, int value);
 int isx_prof_enable(int on);
 int isx_prof_collect(double* out, int n_out);
 

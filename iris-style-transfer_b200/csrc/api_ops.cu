@@ -11,8 +11,14 @@ static inline cudaStream_t S(isx_stream s) { return reinterpret_cast<cudaStream_
 static inline const bf16* P(const isx_bf16* p) { return reinterpret_cast<const bf16*>(p); }
 static inline bf16* P(isx_bf16* p) { return reinterpret_cast<bf16*>(p); }
 
-// tile_cfg (test / tuning hook): BN*100 + MT*10 + stages, 0 = heuristic (e.g. 25623 = BN 256, MT 2, 3 stages)
+// tile_cfg (test / tuning hook): halo*1000000 + BN*100 + MT*10 + stages, 0 = heuristic (e.g. 25623 = BN 256, MT 2, 3 stages)
 static void decode_tile_cfg(int cfg, ConvArgs* a) {
+  if (cfg >= 1000000) {  // 1, 2: halo variants; 3: persistent kernel; 4: force one tile per CTA
+    const int mode = cfg / 1000000;
+    if (mode <= 2) a->halo_mode = mode;
+    else a->persist = mode == 3 ? 1 : -1;
+    cfg %= 1000000;
+  }
   if (cfg > 0) {
     a->force_bn = cfg / 100;
     a->force_mt = (cfg % 100) / 10;
@@ -166,4 +172,17 @@ extern "C" int isx_tap_add_mask(const isx_bf16* g, const isx_bf16* add, const fl
                                 const isx_bf16* act, isx_bf16* out, int B, int64_t HW, int C, isx_stream stream) {
   ISX_REQUIRE(act && out, "isx_tap_add_mask: null pointer");
   return tap_add_mask(P(g), P(add), aff_a, aff_b, P(act), P(out), B, HW, C, S(stream));
+}
+
+namespace isx {
+extern int g_isx_halo_mode;
+extern int g_isx_halo_max_cout;
+extern int g_isx_persist;
+}
+extern "C" int isx_set_option(const char* name, int value) {
+  ISX_REQUIRE(name != nullptr, "isx_set_option: null name");
+  if (strcmp(name, "halo_mode") == 0) { isx::g_isx_halo_mode = value; return 0; }
+  if (strcmp(name, "halo_max_cout") == 0) { isx::g_isx_halo_max_cout = value; return 0; }
+  if (strcmp(name, "persist") == 0) { isx::g_isx_persist = value; return 0; }
+  ISX_REQUIRE(false, "isx_set_option: unknown option '%s'", name);
 }

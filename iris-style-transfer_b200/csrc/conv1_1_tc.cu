@@ -1,8 +1,9 @@
 // K0 + K1 head on the tensor cores: Normalize -> [* mask] -> conv1_1 (3 -> 64, K = 27) + bias + ReLU
 // (models/vgg/vgg.py:81-87).  The 27-tap patch of every pixel is gathered by the pixel's own thread from the
-// fp32 NCHW image, normalised, and split into bf16 hi + lo parts (16 mantissa bits survive), giving one
-// 128-byte K-major row [hi(27) | lo(27) | 0(10)] of the A tile in tcgen05's SWIZZLE_128B layout; the weight
-// slab [64][w(27) | w(27) | 0] is loaded once per CTA by TMA.  One 128x64x64 MMA per 128 pixels, fp32
+// fp32 NCHW image: a CTA first normalises the (TH+2) x (TW+2) x 3 input patch of its TW x TH pixel tile ONCE
+// into shared memory as (bf16 hi, bf16 lo) word pairs (16 mantissa bits survive), then every thread copies
+// the 27 words of its pixel into one 128-byte K-major row [hi0 lo0 hi1 lo1 ... | 0] of the A tile in tcgen05's
+// SWIZZLE_128B layout; the weight slab [64][w0 w0 w1 w1 ... | 0] is loaded once per CTA by TMA.  One 128x64x64 MMA per 128 pixels, fp32
 // accumulation in TMEM, bias + ReLU + bf16 in the epilogue, TMA store of the NHWC rows.
 #include <algorithm>
 
@@ -15,9 +16,7 @@ __global__ void pack_w0_fwd_kernel(const float* __restrict__ w, __nv_bfloat16* _
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // [64][64]
   if (i >= 64 * 64) return;
   const int k = i % 64, o = i / 64;
-  float v = 0.f;
-  if (k < 27) v = w[o * 27 + k];
-  else if (k < 54) v = w[o * 27 + k - 27];
+  const float v = k < 54 ? w[o * 27 + (k >> 1)] : 0.f;  // K index 2j (x hi_j) and 2j+1 (x lo_j) share w_j
   wp[i] = __float2bfloat16_rn(v);
 }
 
@@ -32,16 +31,10 @@ struct C11Params {
   const float* mask;
   const float* bias;
   int xc, mask_b, B, H, W;
-  long npix;
+  int TW, TH, tiles_x, tiles_y;
   int n_tiles;
 };
 
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(m)),
-               "r"(smem_u32(smem)), "r"(c0), "r"(c1)
-               : "memory");
-}
 
 __global__ void __launch_bounds__(128)
 conv1_1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const C11Params p) {
@@ -49,11 +42,12 @@ conv1_1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                 // 128 rows x 128 B
   uint8_t* sB = smem + 16384;         // 64 rows x 128 B
-  uint8_t* sO = smem + 16384 + 8192;  // 128 rows x 128 B staging
-  uint64_t* w_bar = reinterpret_cast<uint64_t*>(smem + 16384 + 8192 + 16384);
+  uint8_t* sO = sA;                   // output staging aliases the A tile (free once the MMA has completed)
+  uint64_t* w_bar = reinterpret_cast<uint64_t*>(smem + 16384 + 8192);
   uint64_t* mma_bar = w_bar + 1;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mma_bar + 1);
   __shared__ float s_bias[64];
+  __shared__ uint32_t s_patch[3 * 3 * 130];  // worst case TW = 128, TH = 1
   const int tid = threadIdx.x, warp = tid >> 5;
   const float mean[3] = {0.485f, 0.456f, 0.406f};
   const float stdv[3] = {0.229f, 0.224f, 0.225f};
@@ -79,53 +73,45 @@ conv1_1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   constexpr uint32_t idesc = umma_idesc_bf16(128, 64, false, false);
   uint32_t phase = 0;
   bool w_ready = false;
+  const int PW = p.TW + 2, PH = p.TH + 2;
+  const int npatch = 3 * PH * PW;
+  const int tw = tid % p.TW, th = tid / p.TW;
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    // ---- gather + normalise + split this thread's pixel ----
-    const long pix = static_cast<long>(tile) * 128 + tid;
-    uint32_t packed[32];  // 64 bf16: hi[27], lo[27], zero[10]
-    {
-      float v[27];
-      if (pix < p.npix) {
-        const int xx = static_cast<int>(pix % p.W);
-        const int yy = static_cast<int>((pix / p.W) % p.H);
-        const int b = static_cast<int>(pix / hw);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float* xp = p.x + (static_cast<long>(b) * p.xc + (p.xc == 3 ? c : 0)) * hw;
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const int y = yy + ky - 1, xq = xx + kx - 1;
-              float t = 0.f;
-              if (y >= 0 && y < p.H && xq >= 0 && xq < p.W) {
-                t = (__ldg(xp + static_cast<long>(y) * p.W + xq) - mean[c]) / stdv[c];
-                if (p.mask) t *= __ldg(p.mask + (static_cast<long>(p.mask_b > 1 ? b : 0) * p.H + y) * p.W + xq);
-              }
-              v[c * 9 + ky * 3 + kx] = t;
-            }
-          }
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 27; ++k) v[k] = 0.f;
+    const int tx = tile % p.tiles_x;
+    const int ty = (tile / p.tiles_x) % p.tiles_y;
+    const int b = tile / (p.tiles_x * p.tiles_y);
+    const int x0 = tx * p.TW, y0 = ty * p.TH;
+    // ---- normalise + split the input patch once (zero padding applies to the NORMALISED image) ----
+    for (int i = tid; i < npatch; i += 128) {
+      const int px = i % PW;
+      const int py = (i / PW) % PH;
+      const int c = i / (PW * PH);
+      const int y = y0 + py - 1, xq = x0 + px - 1;
+      float t = 0.f;
+      if (y >= 0 && y < p.H && xq >= 0 && xq < p.W) {
+        const float* xp = p.x + (static_cast<long>(b) * p.xc + (p.xc == 3 ? c : 0)) * hw;
+        t = (__ldg(xp + static_cast<long>(y) * p.W + xq) - mean[c]) / stdv[c];
+        if (p.mask) t *= __ldg(p.mask + (static_cast<long>(p.mask_b > 1 ? b : 0) * p.H + y) * p.W + xq);
       }
-      __nv_bfloat16 h[64];
-#pragma unroll
-      for (int k = 0; k < 27; ++k) {
-        h[k] = __float2bfloat16_rn(v[k]);
-        h[27 + k] = __float2bfloat16_rn(v[k] - __bfloat162float(h[k]));
-      }
-#pragma unroll
-      for (int k = 54; k < 64; ++k) h[k] = __float2bfloat16_rn(0.f);
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        __nv_bfloat162 t2;
-        t2.x = h[2 * k];
-        t2.y = h[2 * k + 1];
-        packed[k] = *reinterpret_cast<uint32_t*>(&t2);
-      }
+      const __nv_bfloat16 hi = __float2bfloat16_rn(t);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(t - __bfloat162float(hi));
+      __nv_bfloat162 w2;
+      w2.x = hi;
+      w2.y = lo;
+      s_patch[i] = *reinterpret_cast<uint32_t*>(&w2);
     }
+    if (tid == 0) tma_store_wait_read<0>();  // previous tile's TMA store has finished reading sA (== staging)
+    __syncthreads();
+    // ---- this thread's pixel: 27 (hi, lo) words -> one swizzled 128-byte row ----
+    uint32_t packed[32];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) packed[c * 9 + ky * 3 + kx] = s_patch[(c * PH + th + ky) * PW + tw + kx];
+#pragma unroll
+    for (int k = 27; k < 32; ++k) packed[k] = 0u;
     uint8_t* rowp = sA + tid * 128;
 #pragma unroll
     for (int c = 0; c < 8; ++c)
@@ -142,13 +128,11 @@ conv1_1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         umma_bf16(tmem_base, umma_desc_sw128(a_addr + k * 32, 16, 1024), umma_desc_sw128(b_addr + k * 32, 16, 1024),
                   idesc, k != 0 ? 1u : 0u);
       umma_commit(mma_bar);
-      tma_store_wait_read<0>();  // previous tile's staging buffer has been read by its TMA store
     }
     w_ready = true;
     mbar_wait(mma_bar, phase);
     phase ^= 1;
     tc_fence_after();
-    __syncthreads();  // staging free (thread 0 waited above)
     // ---- epilogue: bias + ReLU -> bf16 -> swizzled staging -> TMA store ----
 #pragma unroll 1
     for (int hlf = 0; hlf < 2; ++hlf) {
@@ -171,7 +155,7 @@ conv1_1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
-      tma_store_2d(&tmO, sO, 0, tile * 128);
+      tma_store_4d(&tmO, sO, 0, x0, y0, b);
       tma_store_commit();
     }
   }
@@ -188,9 +172,18 @@ int conv1_1_fwd_tc(const float* x, int xc, const float* mask, int mask_b, const 
   ISX_REQUIRE(xc == 1 || xc == 3, "conv1_1: image must have 1 or 3 channels, got %d", xc);
   C11Params p;
   p.x = x; p.mask = mask; p.bias = bias; p.xc = xc; p.mask_b = mask_b; p.B = B; p.H = H; p.W = W;
-  p.npix = static_cast<long>(B) * H * W;
-  ISX_REQUIRE(p.npix < (1L << 31) - 256, "conv1_1: too many pixels for 32-bit TMA coordinates");
-  p.n_tiles = static_cast<int>((p.npix + 127) / 128);
+  // 128-pixel patch with the least padding (wide rows first: coalesced image reads)
+  long best = -1;
+  for (int twc = 128; twc >= 1; twc >>= 1) {
+    const int thc = 128 / twc;
+    const long padded = static_cast<long>((W + twc - 1) / twc * twc) * ((H + thc - 1) / thc * thc);
+    if (best < 0 || padded < best) { best = padded; p.TW = twc; p.TH = thc; }
+  }
+  p.tiles_x = (W + p.TW - 1) / p.TW;
+  p.tiles_y = (H + p.TH - 1) / p.TH;
+  const long nt = static_cast<long>(p.tiles_x) * p.tiles_y * B;
+  ISX_REQUIRE(nt < (1L << 31), "conv1_1: too many tiles");
+  p.n_tiles = static_cast<int>(nt);
   CUtensorMap tmW, tmO;
   {
     uint64_t dims[2] = {64, 64};
@@ -199,14 +192,14 @@ int conv1_1_fwd_tc(const float* x, int xc, const float* mask, int mask_b, const 
     if (isx_make_tmap_bf16(&tmW, w0_packed, 2, dims, str, box, true)) return 3;
   }
   {
-    uint64_t dims[2] = {64, (uint64_t)p.npix};
-    uint64_t str[1] = {128};
-    uint32_t box[2] = {64, 128};
-    if (isx_make_tmap_bf16(&tmO, out, 2, dims, str, box, true)) return 3;
+    uint64_t dims[4] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128};
+    uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+    if (isx_make_tmap_bf16(&tmO, out, 4, dims, str, box, true)) return 3;
   }
-  const size_t smem_bytes = 1024 + 16384 + 8192 + 16384 + 64;
+  const size_t smem_bytes = 1024 + 16384 + 8192 + 64;
   ISX_CHECK_CUDA(cudaFuncSetAttribute(conv1_1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  const int grid = std::min(p.n_tiles, kNumSMs * 5);
+  const int grid = std::min(p.n_tiles, kNumSMs * 7);
   conv1_1_tc_kernel<<<grid, 128, smem_bytes, s>>>(tmW, tmO, p);
   ISX_LAUNCH_CHECK();
   return 0;

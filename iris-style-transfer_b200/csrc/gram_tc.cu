@@ -139,7 +139,9 @@ static int gram_kp(int C) { return C <= 128 ? 64 : 32; }
 int gram_pick_splits(int B, int HW, int C) {
   const int mblks = C <= 128 ? 1 : C / 128;
   const int kp = gram_kp(C);
-  int want = (2 * kNumSMs + B * mblks - 1) / (B * mblks);
+  // latency-bound kernel (small MMAs per K block): several small-footprint CTAs per SM, so ~6 CTAs per SM in total
+  const int per_sm = C >= 512 ? 2 : 6;
+  int want = (per_sm * kNumSMs + B * mblks - 1) / (B * mblks);
   int max_splits = HW / (kp * 4);  // keep >= 4 K blocks per split
   if (max_splits < 1) max_splits = 1;
   if (want > max_splits) want = max_splits;
@@ -158,8 +160,11 @@ static int launch_gram(const __nv_bfloat16* feat, int B, int HW, int C, int spli
   p.mblks = C <= 128 ? 1 : C / 128;
   p.partial = partial;
   constexpr int kStageBytes = NB * KP * 128;
-  int stages = (160 * 1024) / kStageBytes;
+  // C <= 256: <= 64 KB of pipeline per CTA so that 2-3 CTAs share an SM (TMEM: 128/256 columns each);
+  // C = 512 owns all 512 TMEM columns, one CTA per SM, deeper pipeline instead
+  int stages = NB == 8 ? 5 : (64 * 1024) / kStageBytes;
   if (stages > 8) stages = 8;
+  if (stages < 3) stages = 3;
   p.stages = stages;
   const size_t smem_bytes = 1024 + static_cast<size_t>(stages) * kStageBytes + 256;
   CUtensorMap tmF;

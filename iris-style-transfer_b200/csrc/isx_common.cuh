@@ -204,8 +204,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Shared-memory matrix descriptor (sm_100: version=1 at bits 46-47), SWIZZLE_128B (layout type 2).
 //   K-major : rows of 128 B (64 bf16 of K), 8-row swizzle atoms, SBO = byte stride between 8-row groups.
 //   MN-major: rows of 128 B (64 bf16 of M/N) indexed by K, 8-K-row atoms at SBO, 64-wide MN blocks at LBO.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t base_offset = 0) {
   uint64_t d = 0;
+  d |= static_cast<uint64_t>(base_offset & 7) << 49;  // swizzle phase of the first row when start is not 1024-B aligned
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;

@@ -242,12 +242,9 @@ lbfgs_control_kernel(LbfgsState* __restrict__ states, double* __restrict__ mats,
   }
   lc = block_sum_128(lc, red);
   ls = block_sum_128(ls, red);
+  (void)tick;  // the log row is the problem's own evaluation counter, so a captured CUDA graph can be replayed
   if (st.done) {
-    if (tid == 0) {
-      hist_c[static_cast<long>(tick) * P + p] = st.last_c;
-      hist_s[static_cast<long>(tick) * P + p] = st.last_s;
-      st.compute_d = 0; st.apply = 0;
-    }
+    if (tid == 0) { st.compute_d = 0; st.apply = 0; }
     return;
   }
   // ---- reduce the pass-1 partials ----
@@ -270,8 +267,8 @@ lbfgs_control_kernel(LbfgsState* __restrict__ states, double* __restrict__ mats,
   if (tid == 0) {
     const double loss = cfg.c_weight * lc + cfg.s_weight * ls;
     st.last_c = lc; st.last_s = ls;
-    hist_c[static_cast<long>(tick) * P + p] = lc;
-    hist_s[static_cast<long>(tick) * P + p] = ls;
+    hist_c[static_cast<long>(st.func_evals) * P + p] = lc;
+    hist_s[static_cast<long>(st.func_evals) * P + p] = ls;
     st.func_evals += 1;
     st.loss = loss;
     int iterate = 0, end_step = 0;

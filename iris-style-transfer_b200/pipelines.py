@@ -98,15 +98,34 @@ class NstJob:
         self.hist_s = torch.zeros(self.max_ticks, P, device=dev, dtype=torch.float64)
         self.done = torch.zeros(P, device=dev, dtype=torch.int32)
         self.ticks = 0
+        self._graph = None
         _lib.call("isx_lbfgs_init", self.state, P, _lib.stream_ptr())
         _lib.call("isx_clamp01", self.x, _lib.i64(self.x.numel()), _lib.stream_ptr())  # pipelines.py:82 (first closure)
 
-    def tick(self):
+    def _tick_body(self):
         self.eng.eval(self.x, self.grad)
         _lib.call("isx_lbfgs_tick", self.x, self.grad, self.grad_prev, self.Sh, self.Yh, self.state, self.mats,
                   self.scratch, self.eng.loss_c, self.eng.loss_s, self.ipp, self.P, _lib.i64(self.N),
                   ctypes.byref(self.cfg), self.hist_c, self.hist_s, self.ticks, _lib.stream_ptr())
+
+    def tick(self):
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._tick_body()
         self.ticks += 1
+
+    def enable_graph(self):
+        """Capture one tick (~45 kernel launches, all parameters tick-invariant, no host synchronisation) in a CUDA
+        graph and replay it from then on -- removes the launch gaps that dominate small batches."""
+        if self._graph is not None:
+            return
+        self.tick()  # eager first tick: function attributes, driver entry points, allocator warm-up
+        torch.cuda.current_stream().synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._tick_body()
+        self._graph = g
 
     def evals_done(self):
         """Per-problem evaluation counts (0 while a problem is still running); one small D2H read."""
@@ -118,9 +137,79 @@ class NstJob:
         n_evals = int(evals.max().item()) if bool((evals > 0).all().item()) else self.ticks
         hc = self.hist_c[:n_evals].cpu()
         hs = self.hist_s[:n_evals].cpu()
+        for p_, e_ in enumerate(evals.tolist()):  # a problem that finished early keeps its last logged losses
+            if 0 < e_ < n_evals:
+                hc[e_:, p_] = hc[e_ - 1, p_]
+                hs[e_:, p_] = hs[e_ - 1, p_]
         x = self.x.detach()
         _lib.call("isx_clamp01", x, _lib.i64(x.numel()), _lib.stream_ptr())  # pipelines.py:108-109
         return x, n_evals, evals, hc, hs
+
+
+class NstJobGroup:
+    """`streams` sub-batches of an independent-problems job, each an NstJob on its own CUDA stream.  Ticks of the
+    sub-jobs are issued round-robin, so the HBM-bound L-BFGS passes of one sub-batch overlap the tensor-core
+    convolutions of another (the two kernel families stress different units)."""
+
+    def __init__(self, c_img, s_img, vgg, dev, streams=2, **kw):
+        if not kw.get("independent", False):
+            raise ValueError("multi-stream execution needs independent=True (one problem per image)")
+        B = c_img.shape[0]
+        n = max(1, min(int(streams), B))
+        bounds = [(B * i) // n for i in range(n + 1)]
+        main = torch.cuda.current_stream(dev)
+        self.streams = [torch.cuda.Stream(dev) for _ in range(n)]
+        self.jobs: List[NstJob] = []
+        x_init = kw.pop("x_init", None)
+        for i, st in enumerate(self.streams):
+            lo, hi = bounds[i], bounds[i + 1]
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                si = s_img if (s_img.dim() == 3 or s_img.shape[0] == 1) else s_img[lo:hi]
+                xi = x_init[lo:hi] if x_init is not None else None
+                self.jobs.append(NstJob(c_img[lo:hi], si, vgg, dev, x_init=xi, **kw))
+        self.max_ticks = self.jobs[0].max_ticks
+        self.P = B
+
+    @property
+    def ticks(self):
+        return self.jobs[0].ticks
+
+    def tick(self):
+        for job, st in zip(self.jobs, self.streams):
+            with torch.cuda.stream(st):
+                job.tick()
+
+    def join(self, dev):
+        main = torch.cuda.current_stream(dev)
+        for st in self.streams:
+            main.wait_stream(st)
+
+    def fork(self, dev):
+        main = torch.cuda.current_stream(dev)
+        for st in self.streams:
+            st.wait_stream(main)
+
+    def evals_done(self):
+        outs = []
+        for job, st in zip(self.jobs, self.streams):
+            with torch.cuda.stream(st):
+                outs.append(job.evals_done())
+        return torch.cat(outs)
+
+    def finish(self):
+        xs, hcs, hss, evs = [], [], [], []
+        n_evals = 0
+        for job, st in zip(self.jobs, self.streams):
+            with torch.cuda.stream(st):
+                x, n, ev, hc, hs = job.finish()
+            xs.append(x); evs.append(ev); hcs.append(hc); hss.append(hs)
+            n_evals = max(n_evals, n)
+        pad = lambda h: torch.cat([h, h[-1:].expand(n_evals - h.shape[0], -1)]) if h.shape[0] < n_evals else h
+        dev = xs[0].device
+        self.join(dev)
+        return (torch.cat(xs), n_evals, torch.cat(evs), torch.cat([pad(h) for h in hcs], dim=1),
+                torch.cat([pad(h) for h in hss], dim=1))
 
 
 def nst(c_img: torch.Tensor,
@@ -140,6 +229,8 @@ def nst(c_img: torch.Tensor,
         history_size: int = 100,
         x_init: Optional[torch.Tensor] = None,
         history_dtype: torch.dtype = torch.float32,
+        streams: int = 1,
+        cuda_graph: Optional[bool] = None,
         ) -> tuple[torch.Tensor, list, list, list]:
     """Neural style transfer pipeline (pipelines.py:8-110).
 
@@ -150,6 +241,11 @@ def nst(c_img: torch.Tensor,
       x_hist_stride keep every k-th evaluated image in x_hist (1 = reference behaviour, 0 = none).
       history_size  L-BFGS history (torch default 100).
       x_init        replaces torch.rand (pipelines.py:54) when clone_content is False.
+      streams       > 1 (with independent=True): split the batch into that many sub-batches on separate CUDA
+                    streams so L-BFGS passes (HBM-bound) overlap convolutions (tensor-bound) of another sub-batch.
+      cuda_graph    replay each tick from a captured CUDA graph.  Off by default: a tick has no host synchronisation,
+                    so eager launches already queue ahead of the GPU; capture + instantiation (~0.25 s) only pays off
+                    for very long single-image jobs (measured, profiles/r01_README.md).
       history_dtype torch.float32 (the reference's optimiser state) or torch.bfloat16: the (s, y) history is then
                     stored in bf16, halving the HBM traffic and footprint of the L-BFGS passes (opt-in).
     c_loss_hist / s_loss_hist hold one float per closure evaluation, aggregated over the batch the way
@@ -164,17 +260,33 @@ def nst(c_img: torch.Tensor,
         vgg = VGG19()
     vgg.to(dev)
     with torch.cuda.device(dev), torch.no_grad():
-        job = NstJob(c_img, s_img, vgg, dev, clone_content=clone_content, BN_loss=BN_loss,
-                     c_loss_weight=c_loss_weight, s_loss_weight=s_loss_weight, lr=lr, epochs=epochs,
-                     independent=independent, history_size=history_size, x_init=x_init, history_dtype=history_dtype)
+        kw = dict(clone_content=clone_content, BN_loss=BN_loss, c_loss_weight=c_loss_weight,
+                  s_loss_weight=s_loss_weight, lr=lr, epochs=epochs, independent=independent,
+                  history_size=history_size, x_init=x_init, history_dtype=history_dtype)
+        if streams > 1 and independent and c_img.dim() == 4 and c_img.shape[0] > 1:
+            c_dev, _ = _prep_images(c_img, dev)
+            s_dev = s_img.detach().to(dev, torch.float32)
+            job = NstJobGroup(c_dev, s_dev, vgg, dev, streams=streams, **kw)
+        else:
+            job = NstJob(c_img, s_img, vgg, dev, **kw)
+            if cuda_graph:
+                if x_hist_stride:
+                    x_hist_first = job.x.detach().to('cpu')
+                job.enable_graph()
         x_hist: List[torch.Tensor] = []
+        if getattr(job, "_graph", None) is not None and x_hist_stride:
+            x_hist.append(x_hist_first)  # image of the eager first evaluation
         pbar = None
         if use_tqdm:
             import tqdm
             pbar = tqdm.tqdm(total=epochs)
         while job.ticks < job.max_ticks:
             if x_hist_stride and job.ticks % x_hist_stride == 0:
-                x_hist.append(job.x.detach().to('cpu'))  # pipelines.py:93
+                if isinstance(job, NstJobGroup):
+                    job.join(dev)
+                    x_hist.append(torch.cat([j.x.detach().to('cpu') for j in job.jobs]))
+                else:
+                    x_hist.append(job.x.detach().to('cpu'))  # pipelines.py:93
             job.tick()
             if pbar is not None:
                 pbar.update(1)
