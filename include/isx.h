@@ -106,6 +106,12 @@ int isx_content_mse_fwd_bwd(const isx_bf16* pred, const isx_bf16* target, int ta
 int isx_bn_stats_fwd(const isx_bf16* feat, int B, int64_t HW, int C, double* sums, float* mean, float* std_,
                      const float* t_mean, const float* t_std, int target_b, double loss_scale, double grad_scale,
                      double* loss, float* aff_a, float* aff_b, isx_stream stream);
+/* ---- G' (extension; hooks models/vgg/vgg.py:84-85, pipelines.py:83): mask-weighted Gram input.  fm = feat * m,
+ * fm2 = feat * m^2 (optional) with m fp32 [mask_b,HW] the iris mask at the layer's resolution; the mask pyramid is
+ * m_{l+1} = 2x2 average pool of m_l (isx_avgpool2x2_f32).  Gram(fm) == utils.GramMatrix(F * m_l). */
+int isx_mask_features(const isx_bf16* feat, const float* m, int mask_b, isx_bf16* fm, isx_bf16* fm2, int B, int64_t HW,
+                      int C, isx_stream stream);
+int isx_avgpool2x2_f32(const float* in, float* out, int B, int H, int W, isx_stream stream);
 /* out = (g + add + aff) * (act > 0) -- tap gradient at a layer that no dgrad epilogue feeds; g/add/aff may be NULL */
 int isx_tap_add_mask(const isx_bf16* g, const isx_bf16* add, const float* aff_a, const float* aff_b,
                      const isx_bf16* act, isx_bf16* out, int B, int64_t HW, int C, isx_stream stream);
@@ -161,6 +167,8 @@ typedef struct {
   int32_t content_target_b;             /* 1 or B */
   int32_t coupled;                      /* 1: batch is ONE problem -> content loss is a mean over the batch too */
   int32_t mask_b;                       /* 0: no input mask, else 1 or B */
+  int32_t style_mask_b;                 /* 0: plain Gram; 1 or B: mask-weighted Gram (row G'), see style_mask */
+  int32_t reserved_;
   double c_weight, s_weight;            /* alpha, beta */
 } isx_nst_config;
 
@@ -177,6 +185,7 @@ typedef struct {
   const float* bn_target_mean[ISX_MAX_TAPS];     /* fp32 [style_target_b,C] */
   const float* bn_target_std[ISX_MAX_TAPS];
   const float* input_mask;              /* fp32 [mask_b,1,H,W] or NULL (VGG19.forward(x, mask), vgg.py:84-85) */
+  const float* style_mask[ISX_MAX_TAPS];/* fp32 [style_mask_b,h_l,w_l]: iris mask at each style layer's resolution (G') */
 } isx_nst_buffers;
 
 int64_t isx_nst_workspace_bytes(const isx_nst_config* cfg);

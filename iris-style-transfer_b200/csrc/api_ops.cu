@@ -168,6 +168,18 @@ extern "C" int isx_bn_stats_fwd(const isx_bf16* feat, int B, int64_t HW, int C, 
                      S(stream));
 }
 
+extern "C" int isx_mask_features(const isx_bf16* feat, const float* m, int mask_b, isx_bf16* fm, isx_bf16* fm2, int B,
+                                 int64_t HW, int C, isx_stream stream) {
+  ISX_REQUIRE(feat && m && fm && C % 8 == 0, "isx_mask_features: bad arguments");
+  ISX_REQUIRE(mask_b == 1 || mask_b == B, "isx_mask_features: mask batch %d must be 1 or %d", mask_b, B);
+  return mask_features(P(feat), m, mask_b, P(fm), P(fm2), B, HW, C, S(stream));
+}
+
+extern "C" int isx_avgpool2x2_f32(const float* in, float* out, int B, int H, int W, isx_stream stream) {
+  ISX_REQUIRE(in && out && H >= 2 && W >= 2, "isx_avgpool2x2_f32: bad arguments");
+  return avgpool2x2_f32(in, out, B, H, W, S(stream));
+}
+
 extern "C" int isx_tap_add_mask(const isx_bf16* g, const isx_bf16* add, const float* aff_a, const float* aff_b,
                                 const isx_bf16* act, isx_bf16* out, int B, int64_t HW, int C, isx_stream stream) {
   ISX_REQUIRE(act && out, "isx_tap_add_mask: null pointer");

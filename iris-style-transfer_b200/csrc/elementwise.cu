@@ -281,6 +281,56 @@ int maxpool_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* act, __nv_bfloat16
   return 0;
 }
 
+// Row G' (mask-weighted Gram, SURVEY.md note N5): Fm = F * m_l (Gram input), Fm2 = F * m_l^2 (its backward operand:
+// m * ((F*m) . D) == (F*m^2) . D because m is a per-pixel scalar).  F bf16 [B,HW,C], m fp32 [mask_b,HW].
+__global__ void mask_features_kernel(const __nv_bfloat16* __restrict__ f, const float* __restrict__ m, int mask_b,
+                                     __nv_bfloat16* __restrict__ fm, __nv_bfloat16* __restrict__ fm2, long HW, int C8,
+                                     long n8) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long pix = i / C8;            // b * HW + p
+    const long b = pix / HW, pp = pix - b * HW;
+    const float mv = __ldg(m + (mask_b > 1 ? b : 0) * HW + pp);
+    float a[8], o1[8], o2[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(f) + i), a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o1[j] = a[j] * mv; o2[j] = o1[j] * mv; }
+    reinterpret_cast<uint4*>(fm)[i] = pack8(o1);
+    if (fm2) reinterpret_cast<uint4*>(fm2)[i] = pack8(o2);
+  }
+}
+
+int mask_features(const __nv_bfloat16* f, const float* m, int mask_b, __nv_bfloat16* fm, __nv_bfloat16* fm2, int B,
+                  long HW, int C, cudaStream_t s) {
+  const long n8 = static_cast<long>(B) * HW * C / 8;
+  const int blocks = static_cast<int>(std::min<long>((n8 + 255) / 256, 148L * 16));
+  mask_features_kernel<<<blocks, 256, 0, s>>>(f, m, mask_b, fm, fm2, HW, C / 8, n8);
+  ISX_LAUNCH_CHECK();
+  return 0;
+}
+
+// 2x2 stride-2 average pool of an fp32 mask pyramid level: in [B,H,W] -> out [B,H/2,W/2]
+__global__ void avgpool2x2_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long n = static_cast<long>(B) * Ho * Wo;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int xo = i % Wo;
+    const int yo = (i / Wo) % Ho;
+    const long b = i / (static_cast<long>(Wo) * Ho);
+    const float* p = in + (b * H + 2 * yo) * W + 2 * xo;
+    out[i] = (p[0] + p[1] + p[W] + p[W + 1]) * 0.25f;
+  }
+}
+
+int avgpool2x2_f32(const float* in, float* out, int B, int H, int W, cudaStream_t s) {
+  const long n = static_cast<long>(B) * (H / 2) * (W / 2);
+  const int blocks = static_cast<int>(std::min<long>((n + 255) / 256, 148L * 8));
+  avgpool2x2_f32_kernel<<<blocks, 256, 0, s>>>(in, out, B, H, W);
+  ISX_LAUNCH_CHECK();
+  return 0;
+}
+
 // dx = (g + add) * (act > 0): tap gradient at a layer whose consumer is not a dgrad epilogue
 __global__ void tap_add_mask_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ add,
                                     const float* __restrict__ aff_a, const float* __restrict__ aff_b,

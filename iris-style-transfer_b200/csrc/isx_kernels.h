@@ -20,6 +20,9 @@ int maxpool_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* act, __nv_bfloat16
                 cudaStream_t s);
 int tap_add_mask(const __nv_bfloat16* g, const __nv_bfloat16* add, const float* aff_a, const float* aff_b,
                  const __nv_bfloat16* act, __nv_bfloat16* out, int B, long HW, int C, cudaStream_t s);
+int mask_features(const __nv_bfloat16* f, const float* m, int mask_b, __nv_bfloat16* fm, __nv_bfloat16* fm2, int B,
+                  long HW, int C, cudaStream_t s);
+int avgpool2x2_f32(const float* in, float* out, int B, int H, int W, cudaStream_t s);
 int gram_finalize(const float* partial, int B, int splits, int C, float inv_n, float* G_out, const float* target,
                   int target_b, double loss_scale, double* loss, float grad_scale, __nv_bfloat16* D_out,
                   cudaStream_t s);

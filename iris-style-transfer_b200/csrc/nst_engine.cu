@@ -28,6 +28,7 @@ struct Layout {
   size_t gradA, gradB, tapbuf;
   size_t cgrad[ISX_MAX_TAPS];
   size_t gram_ws, D[ISX_MAX_TAPS], sums, aff_a[ISX_MAX_TAPS], aff_b[ISX_MAX_TAPS];
+  size_t fm[ISX_MAX_TAPS], fm2[ISX_MAX_TAPS];  // masked features (row G')
   size_t total;
 };
 
@@ -82,6 +83,12 @@ int make_layout(const isx_nst_config* c, Layout* L) {
     L->D[t] = off; off += align_up(static_cast<size_t>(c->B) * C * C * 2);
     L->aff_a[t] = off; off += align_up(static_cast<size_t>(c->B) * C * 4);
     L->aff_b[t] = off; off += align_up(static_cast<size_t>(c->B) * C * 4);
+    L->fm[t] = L->fm2[t] = 0;
+    if (c->style_mask_b > 0) {
+      const size_t act_bytes = static_cast<size_t>(c->B) * HW * C * 2;
+      L->fm[t] = off; off += align_up(act_bytes);
+      L->fm2[t] = off; off += align_up(act_bytes);
+    }
   }
   L->gram_ws = off; off += align_up(gram_ws);
   L->sums = off; off += align_up(static_cast<size_t>(c->B) * 512 * 2 * 8);
@@ -167,6 +174,8 @@ extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, c
                             double* loss_s, float* grad, isx_stream stream) {
   ISX_REQUIRE(c && b && x && loss_c && loss_s && grad && b->workspace, "isx_nst_eval: null pointer");
   ISX_REQUIRE(c->n_style + c->n_content > 0, "isx_nst_eval: no loss taps");
+  ISX_REQUIRE(c->style_mask_b == 0 || c->style_mode == 0, "isx_nst_eval: the mask-weighted variant exists for the Gram loss only");
+  ISX_REQUIRE(c->style_mask_b == 0 || c->style_mask_b == 1 || c->style_mask_b == c->B, "isx_nst_eval: style mask batch %d", c->style_mask_b);
   Layout L;
   if (int rc = make_layout(c, &L)) return rc;
   cudaStream_t s = S(stream);
@@ -193,7 +202,13 @@ extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, c
       if (c->style_mode == 0) {  // StyleLoss_Gram (utils.py:317-322); GramMatrix n = C*H*W (utils.py:254)
         ISX_REQUIRE(b->gram_target[st], "nst: Gram target %d missing", st);
         const double inv_n = 1.0 / (static_cast<double>(C) * HW);
-        int rc = gram_tc_partial(at(b, L.act[i]), B, static_cast<int>(HW), C, gram_pick_splits(B, static_cast<int>(HW), C),
+        const bf16* gin = at(b, L.act[i]);
+        if (c->style_mask_b > 0) {  // row G': Gram of F * m_l
+          ISX_REQUIRE(b->style_mask[st], "nst: style mask %d missing", st);
+          if (int rc = mask_features(gin, b->style_mask[st], c->style_mask_b, at(b, L.fm[st]), at(b, L.fm2[st]), B, HW, C, s)) return rc;
+          gin = at(b, L.fm[st]);
+        }
+        int rc = gram_tc_partial(gin, B, static_cast<int>(HW), C, gram_pick_splits(B, static_cast<int>(HW), C),
                                  atf(b, L.gram_ws), s);
         if (rc) return rc;
         rc = gram_finalize(atf(b, L.gram_ws), B, gram_pick_splits(B, static_cast<int>(HW), C), C,
@@ -240,7 +255,7 @@ extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, c
       const bf16* gsrc = ct >= 0 ? at(b, L.cgrad[ct]) : nullptr;
       if (c->style_mode == 0) {
         ConvArgs a;  // Gram backward dF = F . D  (+ mask when it is the only source)
-        a.in = at(b, L.act[i]); a.weight = at(b, L.D[st]); a.out = gsrc ? tapbuf : ping;
+        a.in = c->style_mask_b > 0 ? at(b, L.fm2[st]) : at(b, L.act[i]); a.weight = at(b, L.D[st]); a.out = gsrc ? tapbuf : ping;
         a.B = B; a.H = L.H[lv]; a.W = L.W[lv]; a.Cin = C; a.Cout = C; a.ntaps = 1; a.per_image_weights = true;
         a.mask_act = gsrc ? nullptr : at(b, L.act[i]);
         if (int rc = conv_tc(a, s)) return rc;
@@ -271,7 +286,7 @@ extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, c
       fused_gram_D = at(b, L.D[st]);  // dF = F . D rides the dgrad main loop as extra K blocks
     } else if (st >= 0 && c->style_mode == 0) {
       ConvArgs a;
-      a.in = at(b, L.act[j]); a.weight = at(b, L.D[st]); a.out = tapbuf;
+      a.in = c->style_mask_b > 0 ? at(b, L.fm2[st]) : at(b, L.act[j]); a.weight = at(b, L.D[st]); a.out = tapbuf;
       a.B = B; a.H = L.H[lvj]; a.W = L.W[lvj]; a.Cin = Cj; a.Cout = Cj; a.ntaps = 1; a.per_image_weights = true;
       if (int rc = conv_tc(a, s)) return rc;
       add = tapbuf;
@@ -291,7 +306,7 @@ extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, c
     a.out = ping;
     if (!through_pool) {
       a.mask_act = at(b, L.act[j]); a.add_buf = add; a.aff_a = aa; a.aff_b = ab;
-      if (fused_gram_D) { a.gram_act = at(b, L.act[j]); a.gram_D = fused_gram_D; }
+      if (fused_gram_D) { a.gram_act = c->style_mask_b > 0 ? at(b, L.fm2[st]) : at(b, L.act[j]); a.gram_D = fused_gram_D; }
       if (int rc = conv_tc(a, s)) return rc;
       gm = ping;
       std::swap(ping, pong);

@@ -47,6 +47,7 @@ class NstConfig(ctypes.Structure):
         ("content_w", ctypes.c_float * MAX_TAPS),
         ("style_target_b", ctypes.c_int32), ("content_target_b", ctypes.c_int32),
         ("coupled", ctypes.c_int32), ("mask_b", ctypes.c_int32),
+        ("style_mask_b", ctypes.c_int32), ("reserved_", ctypes.c_int32),
         ("c_weight", ctypes.c_double), ("s_weight", ctypes.c_double),
     ]
 
@@ -65,6 +66,7 @@ class NstBuffers(ctypes.Structure):
         ("bn_target_mean", ctypes.c_void_p * MAX_TAPS),
         ("bn_target_std", ctypes.c_void_p * MAX_TAPS),
         ("input_mask", ctypes.c_void_p),
+        ("style_mask", ctypes.c_void_p * MAX_TAPS),
     ]
 
 
@@ -112,7 +114,7 @@ class NstEngine:
     def __init__(self, packed: PackedVGG, B: int, H: int, W: int, xc: int, content_convs: Sequence[int],
                  style_convs: Sequence[int], style_mode: int = 0, content_w: Optional[Sequence[float]] = None,
                  style_w: Optional[Sequence[float]] = None, c_weight: float = 1.0, s_weight: float = 1.0,
-                 coupled: bool = False, n_conv: Optional[int] = None):
+                 coupled: bool = False, n_conv: Optional[int] = None, style_mask_b: int = 0):
         self.packed = packed
         self.device = packed.device
         cfg = NstConfig()
@@ -134,6 +136,7 @@ class NstEngine:
         cfg.content_target_b = B
         cfg.coupled = int(coupled)
         cfg.mask_b = 0
+        cfg.style_mask_b = int(style_mask_b)
         cfg.c_weight, cfg.s_weight = float(c_weight), float(s_weight)
         self.cfg = cfg
         nbytes = _lib.call_i64("isx_nst_workspace_bytes", ctypes.byref(cfg))
@@ -167,6 +170,15 @@ class NstEngine:
         self._keep.append(m)
         self.cfg.mask_b = m.shape[0]
         self.bufs.input_mask = m.data_ptr()
+
+    def set_style_masks(self, masks: Sequence[torch.Tensor]):
+        """Row G': one fp32 mask [style_mask_b, h_l, w_l] per style tap (see mask_pyramid)."""
+        assert self.cfg.style_mask_b > 0 and len(masks) == self.cfg.n_style
+        for t, m in enumerate(masks):
+            m = m.detach().to(self.device, torch.float32).contiguous()
+            assert m.shape[0] == self.cfg.style_mask_b
+            self._keep.append(m)
+            self.bufs.style_mask[t] = m.data_ptr()
 
     def set_content_targets(self, feats: Sequence[torch.Tensor]):
         for t, f in enumerate(feats):
@@ -214,6 +226,35 @@ class NstEngine:
     def eval(self, x: torch.Tensor, grad: torch.Tensor):
         _lib.call("isx_nst_eval", ctypes.byref(self.cfg), ctypes.byref(self.bufs), x, self.loss_c, self.loss_s, grad,
                   _lib.stream_ptr())
+
+
+def mask_pyramid(mask: torch.Tensor, levels: Sequence[int]) -> List[torch.Tensor]:
+    """SURVEY.md note N5: m_1 = iris mask at frame resolution, m_{l+1} = 2x2 stride-2 average pool of m_l.
+    mask: [Bm,1,H,W] or [Bm,H,W] (bool / float) on the device; returns fp32 [Bm,h,w] per requested level."""
+    m = mask.detach().to(torch.float32)
+    if m.dim() == 4:
+        m = m[:, 0]
+    m = m.contiguous()
+    out, cur, lvl = {}, m, 0
+    for want in sorted(set(levels)):
+        while lvl < want:
+            Bm, H, W = cur.shape
+            nxt = torch.empty(Bm, H // 2, W // 2, device=cur.device, dtype=torch.float32)
+            _lib.call("isx_avgpool2x2_f32", cur, nxt, Bm, H, W, _lib.stream_ptr())
+            cur, lvl = nxt, lvl + 1
+        out[want] = cur
+    return [out[l] for l in levels]
+
+
+def masked_features(feat_nhwc: torch.Tensor, m: torch.Tensor) -> torch.Tensor:
+    B, H, W, C = feat_nhwc.shape
+    fm = torch.empty_like(feat_nhwc)
+    _lib.call("isx_mask_features", feat_nhwc, m.contiguous(), m.shape[0], fm, None, B, _lib.i64(H * W), C,
+              _lib.stream_ptr())
+    return fm
+
+
+CONV_LEVEL = [0, 0, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4]  # number of 2x2 pools before each conv
 
 
 def gram_of(feat_nhwc: torch.Tensor, inv_n: Optional[float] = None) -> torch.Tensor:

@@ -12,7 +12,7 @@ from typing import List, Optional, Tuple
 import torch
 
 from . import _lib
-from .engine import LbfgsConfig, NstEngine, gram_of, stats_of
+from .engine import CONV_LEVEL, LbfgsConfig, NstEngine, gram_of, mask_pyramid, masked_features, stats_of
 from .vgg import VGG19
 
 last_info: dict = {}
@@ -31,7 +31,7 @@ class NstJob:
 
     def __init__(self, c_img, s_img, vgg, dev, clone_content=True, BN_loss=True, c_loss_weight=1.0,
                  s_loss_weight=1.0, lr=1.0, epochs=200, independent=False, history_size=100, x_init=None,
-                 history_dtype=torch.float32):
+                 history_dtype=torch.float32, c_mask=None, s_mask=None):
         c_img, _ = _prep_images(c_img, dev)
         s_img, s_unbatched = _prep_images(s_img, dev)
         if clone_content:
@@ -48,8 +48,19 @@ class NstJob:
         self.epochs = int(epochs)
 
         # ---- targets (pipelines.py:62-68) ----
+        if (c_mask is not None or s_mask is not None) and BN_loss:
+            raise ValueError("mask-weighted style loss (c_mask / s_mask) exists for the Gram loss only (BN_loss=False)")
+        levels = [CONV_LEVEL[i] for i in sc]
+        cmask_b = 0
+        if c_mask is not None:
+            c_mask = c_mask.to(dev)
+            cmask_b = c_mask.shape[0] if c_mask.dim() >= 3 and c_mask.shape[0] in (1, B) else 1
+            if c_mask.dim() == 2:
+                c_mask = c_mask[None]
         eng = NstEngine(packed, B, H, W, xc, cc, sc, style_mode=1 if BN_loss else 0, c_weight=c_loss_weight,
-                        s_weight=s_loss_weight, coupled=not independent)
+                        s_weight=s_loss_weight, coupled=not independent, style_mask_b=cmask_b)
+        if cmask_b:
+            eng.set_style_masks(mask_pyramid(c_mask, levels))
         eng.forward(c_img)
         eng.set_content_targets([eng.feature(0, i) for i in cc])
         Bs, xs, Hs, Ws = s_img.shape
@@ -67,6 +78,11 @@ class NstJob:
             st = [stats_of(f) for f in s_feats]
             eng.set_bn_targets([m for m, _ in st], [s for _, s in st])
         else:
+            if s_mask is not None:  # row G': targets are Gram matrices of the style features weighted by the style's mask
+                s_mask = s_mask.to(dev)
+                if s_mask.dim() == 2:
+                    s_mask = s_mask[None]
+                s_feats = [masked_features(f, m) for f, m in zip(s_feats, mask_pyramid(s_mask, levels))]
             # unbatched style image (…2020.py:103-104): GramMatrix divides by H*W only (SURVEY note N3)
             eng.set_gram_targets([gram_of(f, 1.0 / (f.shape[1] * f.shape[2]) if s_unbatched else None) for f in s_feats])
         del s_feats
@@ -231,6 +247,8 @@ def nst(c_img: torch.Tensor,
         history_dtype: torch.dtype = torch.float32,
         streams: int = 1,
         cuda_graph: Optional[bool] = None,
+        c_mask: Optional[torch.Tensor] = None,
+        s_mask: Optional[torch.Tensor] = None,
         ) -> tuple[torch.Tensor, list, list, list]:
     """Neural style transfer pipeline (pipelines.py:8-110).
 
@@ -243,6 +261,9 @@ def nst(c_img: torch.Tensor,
       x_init        replaces torch.rand (pipelines.py:54) when clone_content is False.
       streams       > 1 (with independent=True): split the batch into that many sub-batches on separate CUDA
                     streams so L-BFGS passes (HBM-bound) overlap convolutions (tensor-bound) of another sub-batch.
+      c_mask/s_mask iris masks [B|1,1,H,W] of the content / style frames: the style loss then compares MASK-WEIGHTED Gram
+                    matrices GramMatrix(F * m_l), m_l = the mask average-pooled to layer l (row G' of SURVEY.md §8a; the
+                    reference only has the dormant hooks vgg.py:84-85 / pipelines.py:83).  All-ones masks == plain Gram.
       cuda_graph    replay each tick from a captured CUDA graph.  Off by default: a tick has no host synchronisation,
                     so eager launches already queue ahead of the GPU; capture + instantiation (~0.25 s) only pays off
                     for very long single-image jobs (measured, profiles/r01_README.md).
@@ -262,7 +283,7 @@ def nst(c_img: torch.Tensor,
     with torch.cuda.device(dev), torch.no_grad():
         kw = dict(clone_content=clone_content, BN_loss=BN_loss, c_loss_weight=c_loss_weight,
                   s_loss_weight=s_loss_weight, lr=lr, epochs=epochs, independent=independent,
-                  history_size=history_size, x_init=x_init, history_dtype=history_dtype)
+                  history_size=history_size, x_init=x_init, history_dtype=history_dtype, c_mask=c_mask, s_mask=s_mask)
         if streams > 1 and independent and c_img.dim() == 4 and c_img.shape[0] > 1:
             c_dev, _ = _prep_images(c_img, dev)
             s_dev = s_img.detach().to(dev, torch.float32)

@@ -44,7 +44,7 @@ def test_struct_mirrors_match_header():
 
     assert [f[0] for f in engine.NstConfig._fields_] == c_struct_fields("isx_nst_config")
     assert [f[0] for f in engine.LbfgsConfig._fields_] == c_struct_fields("isx_lbfgs_config")
-    assert ctypes.sizeof(engine.NstConfig) == 4 * 7 + 4 * 8 * 2 + 4 + 4 * 8 * 2 + 4 * 4 + 8 * 2
+    assert ctypes.sizeof(engine.NstConfig) == 4 * 7 + 4 * 8 * 2 + 4 + 4 * 8 * 2 + 4 * 6 + 8 * 2
     assert ctypes.sizeof(engine.LbfgsConfig) == 24 + 8 * 5
     # pure-host size queries work without a device
     assert _lib.call_i64("isx_lbfgs_mats_bytes", 2, 100) == 2 * 3 * 101 * 101 * 8

@@ -365,6 +365,78 @@ def test_nst_bf16_history_option(mods):
     assert mae <= 1e-2 and sh[-1] <= 3 * sr[-1] + 1e-12
 
 
+def test_masked_gram_eval_matches_oracle(mods):
+    """Row G' (extension): mask-weighted Gram == utils.GramMatrix(F * m_l) of the oracle, m_l = average-pooled mask;
+    an all-ones mask reproduces the plain Gram loss exactly."""
+    from iris_b200 import synthetic
+
+    E, net, O = mods["engine"], mods["vgg"], mods["O"]
+    dev = torch.device("cuda:0")
+    H, W = 64, 48
+    fr, seg = synthetic.synthetic_batch([7, 8], H, W)
+    c = torch.from_numpy(fr).repeat(1, 3, 1, 1)
+    s = rand_img(61, (2, 3, H, W))
+    xq = (0.6 * c + 0.4 * rand_img(62, (2, 3, H, W))).clamp(0, 1)
+    mask = torch.from_numpy((seg == 2) | (seg == 3)).float()          # [2,1,H,W]
+    levels = [E.CONV_LEVEL[i] for i in net.style_convs]
+
+    def run(m):
+        eng = E.NstEngine(net.packed(dev), 2, H, W, 3, net.content_convs, net.style_convs, style_mode=0, c_weight=1.0,
+                          s_weight=1e6, coupled=True, style_mask_b=0 if m is None else 2)
+        if m is not None:
+            eng.set_style_masks(E.mask_pyramid(m.to(dev), levels))
+        eng.forward(c.to(dev))
+        eng.set_content_targets([eng.feature(0, i) for i in net.content_convs])
+        eng.forward(s.to(dev))
+        eng.set_gram_targets([E.gram_of(eng.feature(0, i)) for i in net.style_convs])
+        g = torch.empty(2, 3, H, W, device=dev)
+        eng.eval(xq.to(dev), g)
+        torch.cuda.synchronize()
+        return float(eng.loss_c.sum()), float(eng.loss_s.sum()), g.cpu()
+
+    W_ = mods["weights"]
+    with torch.no_grad():
+        _, cf, _ = O.vgg19_forward(c, W_, full=False)
+        _, _, sf = O.vgg19_forward(s, W_, full=False)
+        tg = [O.gram_matrix(t) for t in sf]
+    cl, sl, g = run(mask)
+    rcl, rsl, rg = O.nst_eval(xq, cf, tg, W_, False, 1.0, 1e6, layer_mask=mask)
+    cos = float((g * rg).sum() / (g.norm() * rg.norm()))
+    print("masked gram: c %.5g/%.5g s %.5g/%.5g grad cos %.4f" % (cl, rcl, sl, rsl, cos))
+    assert sl == pytest.approx(rsl, rel=1e-2) and cl == pytest.approx(rcl, rel=1e-2)
+    assert cos > 0.97
+    # all-ones mask == plain Gram (bit-identical features; the per-image loss is a double atomicAdd, so compare to 1e-12)
+    ones = torch.ones(2, 1, H, W)
+    _, sl1, g1 = run(ones)
+    _, sl0, g0 = run(None)
+    assert sl1 == pytest.approx(sl0, rel=1e-12) and torch.equal(g1, g0)
+    # and through the public API
+    x, _, ch, sh = _run(mods, c, s, BN_loss=False, s_loss_weight=1e6, epochs=20, c_mask=mask, s_mask=torch.ones(2, 1, H, W),
+                        x_hist_stride=0)
+    assert len(sh) == 20 and np.isfinite(sh).all()
+
+
+def test_feature_extraction_matches_oracle(mods):
+    """classifiers.py:71 style features (mean | unbiased std per channel -> 1920 floats) + Gram upper triangles."""
+    from iris_b200 import features, synthetic
+    import iris_b200
+
+    O = mods["O"]
+    fr, _ = synthetic.synthetic_batch([1, 2, 3, 4, 5], 96, 64)
+    x = torch.from_numpy(fr)                                   # [5,1,96,64] grayscale like iris_classification.py:96
+    net = iris_b200.VGG19(content_layers=[], weights=mods["weights"])
+    rows = features.extract_features_sharded(net, x, batch=2, device="cuda:0").cpu()
+    assert rows.shape == (5, 1920 + sum(c * (c + 1) // 2 for c in (64, 128, 256, 512)))
+    with torch.no_grad():
+        _, _, sf = O.vgg19_forward(x, mods["weights"], content_layers=[], full=False)
+    ref = O.style_features(sf)
+    assert torch.allclose(rows[:, :1920], ref, rtol=1e-2, atol=1e-2 * float(ref.abs().max()))
+    G0 = O.gram_matrix(sf[0])
+    iu = torch.triu_indices(64, 64)
+    got = rows[:, 1920:1920 + 64 * 65 // 2]
+    assert float((got - G0[:, iu[0], iu[1]]).norm() / G0[:, iu[0], iu[1]].norm()) < 1e-2
+
+
 def test_cpu_device_is_refused(mods):
     with pytest.raises(Exception):
         mods["pipelines"].nst(rand_img(1, (1, 3, 32, 32)), rand_img(2, (1, 3, 32, 32)), vgg=mods["vgg"],
