@@ -189,6 +189,11 @@ typedef struct {
 } isx_nst_buffers;
 
 int64_t isx_nst_workspace_bytes(const isx_nst_config* cfg);
+/* autograd of VGG19.forward alone (pipelines.py:90 when the caller owns the loss): feat_grads[j] = bf16 NHWC gradient
+ * w.r.t. the ReLU output of conv j (NULL where none), last_pool_grad = gradient w.r.t. the pool after the deepest conv
+ * (or NULL); uses the activations the preceding isx_nst_forward left in the workspace; grad fp32 [B,xc,H,W]. */
+int isx_nst_backward(const isx_nst_config* cfg, const isx_nst_buffers* bufs, const isx_bf16* const* feat_grads,
+                     const isx_bf16* last_pool_grad, float* grad, isx_stream stream);
 /* forward only (VGG19.forward, models/vgg/vgg.py:69-92) up to conv index n_conv-1 (+ trailing pool when
  * with_last_pool); activations stay in the workspace, see isx_nst_feature. */
 int isx_nst_forward(const isx_nst_config* cfg, const isx_nst_buffers* bufs, const float* x, int with_last_pool,

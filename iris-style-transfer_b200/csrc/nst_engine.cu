@@ -170,6 +170,126 @@ extern "C" int isx_nst_feature(const isx_nst_config* c, const isx_nst_buffers* b
   return 0;
 }
 
+namespace {
+// Gradient sources arriving at the ReLU output of a conv (all optional): a ready bf16 gradient map, the per-channel
+// affine form of the BN-statistics loss, and the Gram term D_b applied to gram_A (the activation or its masked copy).
+struct TapSrc {
+  const bf16* add = nullptr;
+  const float* aa = nullptr;
+  const float* ab = nullptr;
+  const bf16* gram_D = nullptr;
+  const bf16* gram_A = nullptr;
+  bool add_is_masked = false;  // `add` is already multiplied by relu'(act) (content_mse output)
+  bool any() const { return add || aa || gram_D; }
+};
+
+// Backward of the stored forward pass to the image: conv dgrad (tcgen05) chained through ReLU / max-pool backward with
+// the tap gradients injected where they arise.  gm = ReLU-masked gradient w.r.t. a conv's output, ready for its dgrad.
+int run_backward(const isx_nst_config* c, const isx_nst_buffers* b, const Layout& L, const TapSrc* src,
+                 const bf16* last_pool_grad, float* grad, cudaStream_t s) {
+  const int B = c->B;
+  int deepest = c->n_conv - 1;  // start at the deepest conv that receives a gradient (layers above it contribute nothing)
+  if (!last_pool_grad)
+    while (deepest > 0 && !src[deepest].any()) --deepest;
+  bf16* ping = at(b, L.gradA);
+  bf16* pong = at(b, L.gradB);
+  bf16* tapbuf = at(b, L.tapbuf);
+  const bf16* gm = nullptr;
+  auto gram_1x1 = [&](int j, bf16* out, bool mask) -> int {  // out = gram_A . D_b  [* relu'(act_j)]
+    const int lv = kLevel[j];
+    ConvArgs a;
+    a.in = src[j].gram_A; a.weight = src[j].gram_D; a.out = out;
+    a.B = B; a.H = L.H[lv]; a.W = L.W[lv]; a.Cin = kCout[j]; a.Cout = kCout[j]; a.ntaps = 1; a.per_image_weights = true;
+    a.mask_act = mask ? at(b, L.act[j]) : nullptr;
+    return conv_tc(a, s);
+  };
+  {
+    const int i = deepest, lv = kLevel[i], C = kCout[i];
+    const long HW = static_cast<long>(L.H[lv]) * L.W[lv];
+    const TapSrc& t = src[i];
+    const bf16* up = nullptr;  // gradient arriving from above (only through the trailing pool)
+    if (last_pool_grad) {
+      if (int rc = maxpool_bwd(last_pool_grad, at(b, L.act[i]), pong, B, L.H[lv], L.W[lv], C, s)) return rc;
+      up = pong;
+    }
+    ISX_REQUIRE(up || t.any(), "nst backward: conv %d carries no gradient", i);
+    if (!up && t.add && !t.aa && !t.gram_D) {
+      if (t.add_is_masked) {
+        gm = t.add;
+      } else {  // a lone gradient map must be ReLU-masked before the dgrad
+        if (int rc = tap_add_mask(t.add, nullptr, nullptr, nullptr, at(b, L.act[i]), ping, B, HW, C, s)) return rc;
+        gm = ping;
+      }
+    } else if (!up && !t.add && !t.aa && t.gram_D) {
+      if (int rc = gram_1x1(i, ping, true)) return rc;
+      gm = ping;
+    } else {
+      const bf16* add2 = nullptr;
+      if (t.gram_D) {
+        if (int rc = gram_1x1(i, tapbuf, false)) return rc;
+        add2 = tapbuf;
+      }
+      // (up | add) + (gram | nothing) + affine, masked
+      const bf16* g1 = up ? up : t.add;
+      if (up && t.add && add2) {  // three maps: fold the given gradient into the tap buffer first
+        if (int rc = tap_add_mask(t.add, tapbuf, nullptr, nullptr, at(b, L.act[i]), tapbuf, B, HW, C, s)) return rc;
+      } else if (up && t.add) {
+        add2 = t.add;
+      }
+      if (int rc = tap_add_mask(g1, add2, t.aa, t.ab, at(b, L.act[i]), ping, B, HW, C, s)) return rc;
+      gm = ping;
+    }
+  }
+  for (int i = deepest; i >= 1; --i) {
+    const int lv = kLevel[i];
+    const int j = i - 1;  // layer below
+    const int lvj = kLevel[j];
+    const int Cj = kCout[j];
+    const long HWj = static_cast<long>(L.H[lvj]) * L.W[lvj];
+    const TapSrc& t = src[j];
+    const bool through_pool = pool_after(j);
+    ConvArgs a;
+    a.in = gm; a.weight = reinterpret_cast<const bf16*>(b->w_dgrad[i]);
+    ISX_REQUIRE(b->w_dgrad[i] != nullptr, "nst: packed dgrad weights of conv %d missing", i);
+    a.B = B; a.H = L.H[lv]; a.W = L.W[lv]; a.Cin = kCout[i]; a.Cout = kCin[i]; a.ntaps = 9;
+    a.out = (gm == ping) ? pong : ping;
+    bf16* other = (a.out == ping) ? pong : ping;
+    if (!through_pool) {
+      // tap gradients ride the dgrad: Gram term as extra K blocks of the main loop, map / affine terms in the epilogue
+      a.mask_act = at(b, L.act[j]); a.add_buf = t.add; a.aff_a = t.aa; a.aff_b = t.ab;
+      if (t.gram_D) { a.gram_act = t.gram_A; a.gram_D = t.gram_D; }
+      if (int rc = conv_tc(a, s)) return rc;
+      gm = a.out;
+    } else {
+      if (int rc = conv_tc(a, s)) return rc;  // gradient w.r.t. the pooled map: no ReLU, no tap
+      // `other` held this dgrad's input, which is consumed now
+      if (int rc = maxpool_bwd(a.out, at(b, L.act[j]), other, B, L.H[lvj], L.W[lvj], Cj, s)) return rc;
+      gm = other;
+      if (t.any()) {
+        const bf16* add2 = t.add;
+        if (t.gram_D) {
+          if (int rc = gram_1x1(j, tapbuf, false)) return rc;
+          if (t.add) {
+            if (int rc = tap_add_mask(t.add, tapbuf, nullptr, nullptr, at(b, L.act[j]), tapbuf, B, HWj, Cj, s)) return rc;
+          }
+          add2 = tapbuf;
+        }
+        if (int rc = tap_add_mask(other, add2, t.aa, t.ab, at(b, L.act[j]), a.out, B, HWj, Cj, s)) return rc;
+        gm = a.out;
+      }
+    }
+  }
+  if (b->w0_dgrad != nullptr) {
+    ConvArgs a;
+    a.in = gm; a.weight = reinterpret_cast<const bf16*>(b->w0_dgrad);
+    a.B = B; a.H = L.H[0]; a.W = L.W[0]; a.Cin = 64; a.Cout = 16; a.ntaps = 9;
+    a.dx_nchw = grad; a.xc = c->xc; a.in_mask = c->mask_b ? b->input_mask : nullptr; a.mask_b = c->mask_b;
+    return conv_tc(a, s);
+  }
+  return conv1_1_dgrad(gm, b->w0, c->mask_b ? b->input_mask : nullptr, c->mask_b, grad, c->xc, B, L.H[0], L.W[0], s);
+}
+}  // namespace
+
 extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, const float* x, double* loss_c,
                             double* loss_s, float* grad, isx_stream stream) {
   ISX_REQUIRE(c && b && x && loss_c && loss_s && grad && b->workspace, "isx_nst_eval: null pointer");
@@ -240,96 +360,35 @@ extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, c
   }
 
   // ---------------- backward ----------------
-  // gm = masked gradient w.r.t. the ReLU output of conv i (ready to be fed to conv i's dgrad)
-  bf16* ping = at(b, L.gradA);
-  bf16* pong = at(b, L.gradB);
-  bf16* tapbuf = at(b, L.tapbuf);
-  const bf16* gm = nullptr;
-  {
-    const int i = deepest, lv = kLevel[i], C = kCout[i];
-    const long HW = static_cast<long>(L.H[lv]) * L.W[lv];
-    const int st = style_tap_of(c, i), ct = content_tap_of(c, i);
-    if (ct >= 0 && st < 0) {
-      gm = at(b, L.cgrad[ct]);  // already masked by content_mse
-    } else {
-      const bf16* gsrc = ct >= 0 ? at(b, L.cgrad[ct]) : nullptr;
-      if (c->style_mode == 0) {
-        ConvArgs a;  // Gram backward dF = F . D  (+ mask when it is the only source)
-        a.in = c->style_mask_b > 0 ? at(b, L.fm2[st]) : at(b, L.act[i]); a.weight = at(b, L.D[st]); a.out = gsrc ? tapbuf : ping;
-        a.B = B; a.H = L.H[lv]; a.W = L.W[lv]; a.Cin = C; a.Cout = C; a.ntaps = 1; a.per_image_weights = true;
-        a.mask_act = gsrc ? nullptr : at(b, L.act[i]);
-        if (int rc = conv_tc(a, s)) return rc;
-        if (gsrc) {
-          if (int rc = tap_add_mask(gsrc, tapbuf, nullptr, nullptr, at(b, L.act[i]), ping, B, HW, C, s)) return rc;
-        }
-      } else {
-        if (int rc = tap_add_mask(gsrc, nullptr, atf(b, L.aff_a[st]), atf(b, L.aff_b[st]), at(b, L.act[i]), ping, B, HW, C, s))
-          return rc;
-      }
-      gm = ping;
-      std::swap(ping, pong);
-    }
-  }
-  for (int i = deepest; i >= 1; --i) {
-    const int lv = kLevel[i];
-    const int j = i - 1;  // layer below
-    const int lvj = kLevel[j];
-    const int Cj = kCout[j];
-    const long HWj = static_cast<long>(L.H[lvj]) * L.W[lvj];
+  TapSrc src[16];
+  for (int j = 0; j < c->n_conv; ++j) {
     const int st = style_tap_of(c, j), ct = content_tap_of(c, j);
-    const bool through_pool = pool_after(j);
-    // tap gradient of layer j (computed before the dgrad that consumes it, or fused into it)
-    const bf16* add = nullptr;
-    const float *aa = nullptr, *ab = nullptr;
-    const bf16* fused_gram_D = nullptr;
-    if (st >= 0 && c->style_mode == 0 && !through_pool && ct < 0) {
-      fused_gram_D = at(b, L.D[st]);  // dF = F . D rides the dgrad main loop as extra K blocks
-    } else if (st >= 0 && c->style_mode == 0) {
-      ConvArgs a;
-      a.in = c->style_mask_b > 0 ? at(b, L.fm2[st]) : at(b, L.act[j]); a.weight = at(b, L.D[st]); a.out = tapbuf;
-      a.B = B; a.H = L.H[lvj]; a.W = L.W[lvj]; a.Cin = Cj; a.Cout = Cj; a.ntaps = 1; a.per_image_weights = true;
-      if (int rc = conv_tc(a, s)) return rc;
-      add = tapbuf;
-      if (ct >= 0) {  // both taps on one layer: fold the content gradient into the tap buffer
-        if (int rc = tap_add_mask(at(b, L.cgrad[ct]), tapbuf, nullptr, nullptr, at(b, L.act[j]), tapbuf, B, HWj, Cj, s)) return rc;
-      }
+    if (ct >= 0) { src[j].add = at(b, L.cgrad[ct]); src[j].add_is_masked = true; }  // content_mse masks its gradient
+    if (st >= 0 && c->style_mode == 0) {
+      src[j].gram_D = at(b, L.D[st]);
+      src[j].gram_A = c->style_mask_b > 0 ? at(b, L.fm2[st]) : at(b, L.act[j]);
     } else if (st >= 0) {
-      aa = atf(b, L.aff_a[st]); ab = atf(b, L.aff_b[st]);
-      if (ct >= 0) add = at(b, L.cgrad[ct]);
-    } else if (ct >= 0) {
-      add = at(b, L.cgrad[ct]);
-    }
-    ConvArgs a;
-    a.in = gm; a.weight = reinterpret_cast<const bf16*>(b->w_dgrad[i]);
-    ISX_REQUIRE(b->w_dgrad[i] != nullptr, "nst: packed dgrad weights of conv %d missing", i);
-    a.B = B; a.H = L.H[lv]; a.W = L.W[lv]; a.Cin = kCout[i]; a.Cout = kCin[i]; a.ntaps = 9;
-    a.out = ping;
-    if (!through_pool) {
-      a.mask_act = at(b, L.act[j]); a.add_buf = add; a.aff_a = aa; a.aff_b = ab;
-      if (fused_gram_D) { a.gram_act = c->style_mask_b > 0 ? at(b, L.fm2[st]) : at(b, L.act[j]); a.gram_D = fused_gram_D; }
-      if (int rc = conv_tc(a, s)) return rc;
-      gm = ping;
-      std::swap(ping, pong);
-    } else {
-      if (int rc = conv_tc(a, s)) return rc;  // gradient w.r.t. the pooled map: no ReLU, no tap
-      if (int rc = maxpool_bwd(ping, at(b, L.act[j]), pong, B, L.H[lvj], L.W[lvj], Cj, s)) return rc;
-      if (add || aa) {
-        if (int rc = tap_add_mask(pong, add, aa, ab, at(b, L.act[j]), ping, B, HWj, Cj, s)) return rc;
-        gm = ping;
-        std::swap(ping, pong);
-      } else {
-        gm = pong;  // next dgrad writes into ping
-      }
+      src[j].aa = atf(b, L.aff_a[st]);
+      src[j].ab = atf(b, L.aff_b[st]);
     }
   }
-  if (b->w0_dgrad != nullptr) {
-    ConvArgs a;
-    a.in = gm; a.weight = reinterpret_cast<const bf16*>(b->w0_dgrad);
-    a.B = B; a.H = L.H[0]; a.W = L.W[0]; a.Cin = 64; a.Cout = 16; a.ntaps = 9;
-    a.dx_nchw = grad; a.xc = c->xc; a.in_mask = c->mask_b ? b->input_mask : nullptr; a.mask_b = c->mask_b;
-    return conv_tc(a, s);
+  return run_backward(c, b, L, src, nullptr, grad, s);
+}
+
+extern "C" int isx_nst_backward(const isx_nst_config* c, const isx_nst_buffers* b, const isx_bf16* const* feat_grads,
+                                const isx_bf16* last_pool_grad, float* grad, isx_stream stream) {
+  ISX_REQUIRE(c && b && feat_grads && grad && b->workspace, "isx_nst_backward: null pointer");
+  Layout L;
+  if (int rc = make_layout(c, &L)) return rc;
+  TapSrc src[16];
+  bool any = last_pool_grad != nullptr;
+  for (int j = 0; j < c->n_conv; ++j) {
+    src[j].add = reinterpret_cast<const bf16*>(feat_grads[j]);
+    any = any || src[j].add != nullptr;
   }
-  return conv1_1_dgrad(gm, b->w0, c->mask_b ? b->input_mask : nullptr, c->mask_b, grad, c->xc, B, L.H[0], L.W[0], s);
+  ISX_REQUIRE(any, "isx_nst_backward: no gradient given");
+  ISX_REQUIRE(!last_pool_grad || pool_after(c->n_conv - 1), "isx_nst_backward: conv %d is not followed by a pool", c->n_conv - 1);
+  return run_backward(c, b, L, src, reinterpret_cast<const bf16*>(last_pool_grad), grad, S(stream));
 }
 
 // ---------------------------------------------------------------------------------------------

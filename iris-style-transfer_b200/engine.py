@@ -223,6 +223,18 @@ class NstEngine:
         view = self.workspace[off:off + 2 * n].view(torch.bfloat16).view(self.cfg.B, h.value, w.value, c.value)
         return view.clone()
 
+    def backward(self, feat_grads: Dict[int, torch.Tensor], last_pool_grad: Optional[torch.Tensor], grad: torch.Tensor):
+        """isx_nst_backward: feat_grads {conv index: bf16 NHWC gradient w.r.t. its ReLU output}; uses the activations of
+        the forward() that ran last on this engine."""
+        arr = (ctypes.c_void_p * N_CONVS)()
+        keep = []
+        for j, g in feat_grads.items():
+            g = g.contiguous()
+            keep.append(g)
+            arr[j] = g.data_ptr()
+        lp = last_pool_grad.contiguous() if last_pool_grad is not None else None
+        _lib.call("isx_nst_backward", ctypes.byref(self.cfg), ctypes.byref(self.bufs), arr, lp, grad, _lib.stream_ptr())
+
     def eval(self, x: torch.Tensor, grad: torch.Tensor):
         _lib.call("isx_nst_eval", ctypes.byref(self.cfg), ctypes.byref(self.bufs), x, self.loss_c, self.loss_s, grad,
                   _lib.stream_ptr())

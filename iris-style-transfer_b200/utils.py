@@ -19,9 +19,40 @@ def _to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
     return x.detach().permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
 
 
+class _GramFunction(torch.autograd.Function):
+    """G = F F^T / n on tcgen05 (isx_gram_fwd); backward dF = (dG + dG^T) F / n through the 1x1 tcgen05 path (isx_gram_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        unbatched = x.dim() == 3
+        f = _to_nhwc_bf16(x)
+        B, H, W, C = f.shape
+        inv_n = 1.0 / (H * W) if unbatched else 1.0 / (C * H * W)
+        G = gram_of(f, inv_n)
+        ctx.save_for_backward(f)
+        ctx.inv_n, ctx.unbatched = inv_n, unbatched
+        return G[0] if unbatched else G
+
+    @staticmethod
+    def backward(ctx, dG):
+        (f,) = ctx.saved_tensors
+        B, H, W, C = f.shape
+        if ctx.unbatched:
+            dG = dG[None]
+        D = ((dG + dG.transpose(-2, -1)) * ctx.inv_n).to(torch.bfloat16).contiguous()
+        dF = torch.empty_like(f)
+        with torch.cuda.device(f.device):
+            _lib.call("isx_gram_bwd", f, D, dF, B, H, W, C, None, _lib.stream_ptr())
+        g = dF.permute(0, 3, 1, 2).float()
+        return g[0] if ctx.unbatched else g
+
+
 def GramMatrix(x: torch.Tensor) -> torch.Tensor:
     """utils.py:242-257: flatten (H,W), x @ x^T / n with n = x[0].numel() after the flatten, i.e.
-    C*H*W for a batched (B,C,H,W) input and H*W for an unbatched (C,H,W) one (SURVEY note N3)."""
+    C*H*W for a batched (B,C,H,W) input and H*W for an unbatched (C,H,W) one (SURVEY note N3).
+    Differentiable (custom autograd Function) when x requires grad."""
+    if torch.is_grad_enabled() and x.requires_grad:
+        return _GramFunction.apply(x)
     unbatched = x.dim() == 3
     f = _to_nhwc_bf16(x)
     B, H, W, C = f.shape
@@ -38,8 +69,16 @@ class ContentLoss_L2(torch.nn.Module):
         self.targets = targets
         self.weights = [1.0] * len(targets) if weights is None else weights
 
-    @torch.no_grad()
     def forward(self, preds: List[torch.Tensor]) -> torch.Tensor:
+        if torch.is_grad_enabled() and any(p.requires_grad for p in preds):
+            loss = 0  # the reference's own expression (utils.py:285-290); autograd supplies d/dp
+            for p, t, w in zip(preds, self.targets, self.weights):
+                loss = loss + torch.nn.functional.mse_loss(p, t) * w
+            return loss * 0.5
+        with torch.no_grad():
+            return self._forward_kernels(preds)
+
+    def _forward_kernels(self, preds: List[torch.Tensor]) -> torch.Tensor:
         total = torch.zeros((), device=preds[0].device, dtype=torch.float64)
         for p, t, w in zip(preds, self.targets, self.weights):
             pn, tn = _to_nhwc_bf16(p), _to_nhwc_bf16(t)
@@ -60,8 +99,8 @@ class StyleLoss_Gram(torch.nn.Module):
         self.targets = [GramMatrix(t) for t in targets]
         self.weights = [1.0] * len(targets) if weights is None else weights
 
-    @torch.no_grad()
     def forward(self, preds: List[torch.Tensor]) -> torch.Tensor:
+        # utils.py:317-322; GramMatrix carries its own backward, the C x C arithmetic is plain torch
         total = torch.zeros((), device=preds[0].device, dtype=torch.float64)
         for p, t, w in zip(preds, self.targets, self.weights):
             total = total + ((GramMatrix(p) - t).double() ** 2).sum() * w
@@ -78,8 +117,17 @@ class StyleLoss_BN(torch.nn.Module):
         self.targets_std = [s if t.dim() == 4 else s[0] for (_, s), t in zip(stats, targets)]
         self.weights = [1.0] * len(targets) if weights is None else weights
 
-    @torch.no_grad()
     def forward(self, preds: List[torch.Tensor]) -> torch.Tensor:
+        if torch.is_grad_enabled() and any(p.requires_grad for p in preds):
+            loss = 0  # the reference's own expression (utils.py:350-355); autograd supplies d/dp
+            for p, tm, ts, w in zip(preds, self.targets_mean, self.targets_std, self.weights):
+                pm, ps = p.mean(dim=(-2, -1)), p.std(dim=(-2, -1))
+                loss = loss + ((pm - tm) ** 2 + (ps - ts) ** 2).sum() * w / pm.shape[-1]
+            return loss
+        with torch.no_grad():
+            return self._forward_kernels(preds)
+
+    def _forward_kernels(self, preds: List[torch.Tensor]) -> torch.Tensor:
         total = torch.zeros((), device=preds[0].device, dtype=torch.float64)
         for p, tm, ts, w in zip(preds, self.targets_mean, self.targets_std, self.weights):
             pm, ps = stats_of(_to_nhwc_bf16(p))

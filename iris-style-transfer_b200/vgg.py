@@ -21,6 +21,51 @@ def random_vgg19_weights(seed: int = 0) -> List[Tuple[torch.Tensor, torch.Tensor
     return [(m.weight.detach().clone(), m.bias.detach().clone()) for m in net if isinstance(m, torch.nn.Conv2d)]
 
 
+class _VGGForward(torch.autograd.Function):
+    """Differentiable VGG19.forward: forward = isx_nst_forward, backward = isx_nst_backward (tcgen05 dgrad chain)."""
+
+    @staticmethod
+    def forward(ctx, x, vgg, mask):
+        last, c, s, unbatched = vgg.features_nhwc(x, mask, full=True)
+        ctx.vgg, ctx.eng, ctx.version, ctx.unbatched = vgg, vgg._last_engine, vgg._fwd_version, unbatched
+        ctx.x_shape = tuple(x.shape)
+
+        def nchw(t):
+            t = t.permute(0, 3, 1, 2).float()
+            return t[0] if unbatched else t
+
+        return (nchw(last),) + tuple(nchw(t) for t in c) + tuple(nchw(t) for t in s)
+
+    @staticmethod
+    def backward(ctx, g_last, *g_feats):
+        vgg, eng = ctx.vgg, ctx.eng
+        if vgg._fwd_version != ctx.version:
+            raise RuntimeError("iris_b200.VGG19: backward() after another forward() of the same module -- the stored "
+                               "activations were overwritten (the module is not re-entrant, like the reference's "
+                               "FeatureExtractor, models/vgg/vgg.py:107)")
+
+        def nhwc(g):
+            if ctx.unbatched:
+                g = g[None]
+            return g.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
+
+        grads = {}
+        convs = list(vgg.content_convs) + list(vgg.style_convs)
+        for conv, g in zip(convs, g_feats):
+            if g is None:
+                continue
+            gn = nhwc(g)
+            grads[conv] = grads[conv] + gn if conv in grads else gn
+        lp = nhwc(g_last) if g_last is not None and bool((g_last != 0).any()) else None
+        if not grads and lp is None:
+            return torch.zeros(ctx.x_shape, device=g_last.device), None, None
+        B, xc, H, W = eng.cfg.B, eng.cfg.xc, eng.cfg.H, eng.cfg.W
+        dx = torch.empty(B, xc, H, W, device=eng.device, dtype=torch.float32)
+        with torch.cuda.device(eng.device):
+            eng.backward(grads, lp, dx)
+        return (dx[0] if ctx.unbatched else dx), None, None
+
+
 class VGG19(torch.nn.Module):
     """models/vgg/vgg.py:19-92.  `weights`: 'imagenet' (the reference's IMAGENET1K_V1 via torchvision; needs the
     checkpoint to be available), 'random' (torchvision init under `seed`), or the 16 (weight, bias) pairs."""
@@ -55,6 +100,8 @@ class VGG19(torch.nn.Module):
         self._packed: Dict[str, PackedVGG] = {}
         self._engines: Dict[tuple, NstEngine] = {}
         self._device = torch.device("cuda:0")
+        self._last_engine: Optional[NstEngine] = None
+        self._fwd_version = 0
 
     # the reference calls vgg.to(device) (pipelines.py:46)
     def to(self, device=None, *args, **kwargs):  # noqa: D401
@@ -94,6 +141,8 @@ class VGG19(torch.nn.Module):
         n_conv = N_CONVS if full else max(taps) + 1
         eng = self._engine(B, H, W, xc, n_conv, dev)
         eng.set_input_mask(mask)
+        self._last_engine = eng
+        self._fwd_version += 1
         with torch.cuda.device(dev):
             eng.forward(x, with_last_pool=full)
             last = eng.feature(1, 4) if full else None
@@ -101,10 +150,18 @@ class VGG19(torch.nn.Module):
             s = [eng.feature(0, i) for i in self.style_convs]
         return last, c, s, unbatched
 
-    @torch.no_grad()
     def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None):
-        """models/vgg/vgg.py:69-92.  Returns fp32 NCHW tensors like the reference (not differentiable: the
-        backward of this stack lives in the fused nst() driver)."""
+        """models/vgg/vgg.py:69-92.  Returns fp32 NCHW tensors like the reference.  Differentiable w.r.t. x (the weights are
+        frozen, vgg.py:52-53): autograd runs the tcgen05 dgrad chain (isx_nst_backward).  nst() does not go through
+        here -- its closure is the fused isx_nst_eval."""
+        if torch.is_grad_enabled() and x.requires_grad:
+            outs = _VGGForward.apply(x, self, mask)
+            nc = len(self.content_convs)
+            return outs[0], list(outs[1:1 + nc]), list(outs[1 + nc:])
+        with torch.no_grad():
+            return self._forward_nograd(x, mask)
+
+    def _forward_nograd(self, x, mask):
         last, c, s, unbatched = self.features_nhwc(x, mask, full=True)
 
         def nchw(t):

@@ -499,6 +499,60 @@ def test_nst_five_style_layers_eval(mods):
     assert cos > 0.97
 
 
+@pytest.mark.parametrize("BN", [False, True])
+def test_modules_are_differentiable_like_the_reference(mods, BN):
+    """pipelines.py:85-90 written by hand with the drop-in modules: vgg(x) -> ContentLoss_L2 / StyleLoss_* -> backward().
+    The image gradient must match the oracle's autograd gradient (and VGG19.forward returns pool5 like the reference)."""
+    import iris_b200
+
+    O, net = mods["O"], mods["vgg"]
+    dev = torch.device("cuda:0")
+    H, W = 64, 80
+    c, s, xq = (rand_img(k, (2, 3, H, W)) for k in (81, 82, 83))
+    with torch.no_grad():
+        _, c_f, _ = net(c.to(dev))
+        _, _, s_f = net(s.to(dev))
+    closs = iris_b200.ContentLoss_L2(targets=c_f)
+    sloss = (iris_b200.StyleLoss_BN if BN else iris_b200.StyleLoss_Gram)(targets=s_f)
+    beta = 1e4 if BN else 1e6
+    x = xq.to(dev).requires_grad_(True)
+    p5, x_c, x_s = net(x)
+    assert p5.shape == (2, 512, H // 32, W // 32) and p5.requires_grad
+    cl, sl = closs(x_c), sloss(x_s)
+    loss = cl * 1.0 + sl * beta
+    loss.backward()
+    torch.cuda.synchronize()
+    W_ = mods["weights"]
+    with torch.no_grad():
+        _, cf, _ = O.vgg19_forward(c, W_, full=False)
+        _, _, sf = O.vgg19_forward(s, W_, full=False)
+    targets = ([t.mean(dim=(-2, -1)) for t in sf], [t.std(dim=(-2, -1)) for t in sf]) if BN else [O.gram_matrix(t) for t in sf]
+    rcl, rsl, rg = O.nst_eval(xq, cf, targets, W_, BN, 1.0, beta)
+    g = x.grad.cpu()
+    cos = float((g * rg).sum() / (g.norm() * rg.norm()))
+    print("modules autograd BN=%s: c %.5g/%.5g s %.5g/%.5g cos %.4f |g| ratio %.3f" % (
+        BN, float(cl.detach()), rcl, float(sl.detach()), rsl, cos, float(g.norm() / rg.norm())))
+    assert float(cl) == pytest.approx(rcl, rel=1e-2) and float(sl) == pytest.approx(rsl, rel=1e-2)
+    assert cos > 0.97 and 0.8 < float(g.norm() / rg.norm()) < 1.25
+    # a gradient flowing only through pool5 (Classifier1's input, 2019.py:83) also reaches the image
+    x2 = xq.to(dev).requires_grad_(True)
+    p5, _, _ = net(x2)
+    p5.square().sum().backward()
+    xr = xq.clone().requires_grad_(True)
+    pr, _, _ = O.vgg19_forward(xr, W_, full=True)
+    pr.square().sum().backward()
+    cos5 = float((x2.grad.cpu() * xr.grad).sum() / (x2.grad.cpu().norm() * xr.grad.norm()))
+    print("pool5 path cos %.4f" % cos5)
+    # 16 bf16 convs + 5 max-pools whose arg-max can flip on near-ties after bf16 rounding: looser than the tap paths
+    assert cos5 > 0.93
+    # a second forward invalidates the first graph (the module is stateful like the reference's FeatureExtractor)
+    x3 = xq.to(dev).requires_grad_(True)
+    out3 = net(x3)
+    net(xq.to(dev))
+    with pytest.raises(RuntimeError):
+        out3[0].sum().backward()
+
+
 def test_cpu_device_is_refused(mods):
     with pytest.raises(Exception):
         mods["pipelines"].nst(rand_img(1, (1, 3, 32, 32)), rand_img(2, (1, 3, 32, 32)), vgg=mods["vgg"],
