@@ -337,15 +337,39 @@ def main():
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)"
     if not peak_tf:
         peak_tf, peak_src = 1400.0, "B200_PROFILING.md fallback, sustained (of fallback)"
+    # L-BFGS passes: algorithmic HBM bytes = history streamed twice (16*m*N) + 36*N per image-step, with
+    # m = number of stored pairs at that tick (one pair per iteration, capped at the 100 slots)
+    N_img = 3 * H * W
+    esz = 2 if args.history_bf16 else 4
+    lbfgs_bytes = 0.0
+    for t in range(Wm, Wm + K):
+        m_t = min(max(t - 1, 0), hist_slots)
+        lbfgs_bytes += B * N_img * (4.0 * esz * m_t + 36.0)
+    hbm_peak = peaks.get("hbm_gbs") or 6650.0
+    lbfgs_gbs = lbfgs_bytes / (prof[7] / 1e3) / 1e9 if prof[7] > 0 else None
+    # DRAM traffic of the conv family per launch, from the committed ncu capture of this command (profiles/)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")))
+        if tr.get("batch") == B:
+            traffic = tr["dram_bytes_per_conv_launch"]
+    except Exception:
+        pass
     conv_n, conv_ms, conv_flops = prof[0], prof[1], prof[2]
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else None
     roofline = {
         "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv fwd/dgrad/Gram-bwd)", "bound": "tensor",
         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if achieved else None,
-        "traffic": None, "peak_source": peak_src, "launches": int(conv_n), "avg_launch_ms": conv_ms / max(conv_n, 1),
+        # algorithmic DRAM bytes of the 19 conv launches of one evaluation (bf16 NHWC in + out, ReLU-mask and Gram-operand
+        # reads of the dgrads): 587 MB per 640x400 image
+        "traffic": traffic, "algorithmic_dram_bytes_per_launch": 587e6 * B / 19.0,
+        "peak_source": peak_src, "launches": int(conv_n), "avg_launch_ms": conv_ms / max(conv_n, 1),
         "share_of_step": conv_ms / ms,
         "other": {"gram_tc_ms_share": prof[4] / ms, "lbfgs_ms_share": prof[7] / ms,
-                  "gram_tflops": prof[5] / (prof[4] / 1e3) / 1e12 if prof[4] > 0 else None},
+                  "gram_tflops": prof[5] / (prof[4] / 1e3) / 1e12 if prof[4] > 0 else None,
+                  "lbfgs_hbm": {"bound": "hbm", "achieved": lbfgs_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": lbfgs_gbs / hbm_peak if lbfgs_gbs else None,
+                                "note": "lbfgs_dots + reduce + control + lbfgs_update, algorithmic bytes / CUDA-event time"}},
     }
     cpu = None
     if not args.no_cpu_baseline:
