@@ -63,6 +63,12 @@ int isx_conv1_1_dgrad_tc(const isx_bf16* dy, const isx_bf16* w0_dgrad, const flo
 int isx_conv3x3_bias_relu_fwd(const isx_bf16* in, const isx_bf16* w_fwd, const float* bias, isx_bf16* out, int B,
                               int H, int W, int Cin, int Cout, int relu, int tile_cfg, isx_stream stream);
 
+/* K1 + K2 fused: same conv, and MaxPool2d(2,2) of its ReLU output written to pool_out bf16 [B,H/2,W/2,Cout] from the
+ * epilogue's staged tile (falls back to a separate pool launch when the pixel patch has an odd side). */
+int isx_conv3x3_bias_relu_pool_fwd(const isx_bf16* in, const isx_bf16* w_fwd, const float* bias, isx_bf16* out,
+                                   isx_bf16* pool_out, int B, int H, int W, int Cin, int Cout, int tile_cfg,
+                                   isx_stream stream);
+
 /* ---- K3: conv dgrad (+ tap gradient, x ReLU mask) on tcgen05 (loss.backward(), pipelines.py:90)
  * dy bf16 [B,H,W,Cout] -> dx bf16 [B,H,W,Cin] for the forward conv Cin->Cout; weights frozen so
  * there is no wgrad (models/vgg/vgg.py:52-53).  Epilogue, all optional:

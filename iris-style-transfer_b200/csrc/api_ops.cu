@@ -86,6 +86,18 @@ extern "C" int isx_conv3x3_bias_relu_fwd(const isx_bf16* in, const isx_bf16* w_f
   return conv_tc(a, S(stream));
 }
 
+extern "C" int isx_conv3x3_bias_relu_pool_fwd(const isx_bf16* in, const isx_bf16* w_fwd, const float* bias, isx_bf16* out,
+                                              isx_bf16* pool_out, int B, int H, int W, int Cin, int Cout, int tile_cfg,
+                                              isx_stream stream) {
+  ISX_REQUIRE(in && w_fwd && out && pool_out && H >= 2 && W >= 2, "isx_conv3x3_bias_relu_pool_fwd: bad arguments");
+  ConvArgs a;
+  a.in = P(in); a.weight = P(w_fwd); a.out = P(out); a.pool_out = P(pool_out);
+  a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ntaps = 9;
+  a.bias = bias; a.relu = 1;
+  decode_tile_cfg(tile_cfg, &a);
+  return conv_tc(a, S(stream));
+}
+
 extern "C" int isx_conv3x3_dgrad(const isx_bf16* dy, const isx_bf16* w_dgrad, isx_bf16* dx, int B, int H, int W,
                                  int Cin, int Cout, const isx_bf16* relu_act, const isx_bf16* add_grad,
                                  const float* aff_a, const float* aff_b, int tile_cfg, isx_stream stream) {

@@ -18,6 +18,7 @@
 // TMA store).
 #include "isx_common.cuh"
 #include "isx_internal.h"
+#include "isx_kernels.h"
 
 namespace isx {
 
@@ -39,6 +40,7 @@ struct ConvParams {
   const __nv_bfloat16* add_buf;   // [B,H,W,Cout] or null: out += add
   const float* aff_a;        // [B,Cout] or null: out += aff_a + aff_b * act   (BN-statistics tap gradient)
   const float* aff_b;
+  int fuse_pool;             // epilogue also emits the 2x2 max-pooled tile (TW, TH even) through tmP
   // EPI == 1 (image-gradient tail, BN = 16): dx fp32 NCHW [B,xc,H,W] = acc[c] * mask / std[c]
   float* dx_nchw;
   int xc;
@@ -60,7 +62,8 @@ template <int BN, int MT, int EPI, bool HALO = false>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmM,
-               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const ConvParams p) {
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+               const __grid_constant__ CUtensorMap tmP, const ConvParams p) {
   constexpr int kBTileBytes = BN * 128;
   constexpr int kStageBytes = MT * kATileBytes + kBTileBytes;
   constexpr int kTmemCols = (MT * BN) <= 32 ? 32 : (MT * BN) <= 64 ? 64 : (MT * BN) <= 128 ? 128 : (MT * BN) <= 256 ? 256 : 512;
@@ -105,6 +108,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (EPI == 0) tma_prefetch_desc(&tmO);
     if (EPI == 0 && p.mask_act != nullptr) tma_prefetch_desc(&tmM);
     if (p.extra_kb > 0) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
+    if (p.fuse_pool) tma_prefetch_desc(&tmP);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -377,6 +381,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_store_4d(&tmO, stg, n0 + g * 64, x0[mt], y0[mt], b0[mt]);
           tma_store_commit();
           if (use_mask && gi + 2 < NG) issue_mask_load(gi + 2);  // scratch slot (gi & 1) has been read by everyone
+        }
+        if (p.fuse_pool) {
+          // K2 fused: 2x2 max-pool of the staged bf16 tile -> 32 pooled pixels x 64 channels (MaxPool2d(2,2) after ReLU)
+          uint8_t* pst = smem + (NG + (use_mask ? 2 : 0)) * kATileBytes + gi * 4096;
+          const int twp = p.TW >> 1, thp = p.TH >> 1;
+          const int et = threadIdx.x - 64;  // 0..127
+#pragma unroll
+          for (int it2 = 0; it2 < 2; ++it2) {
+            const int item = et + it2 * 128;
+            const int pr = item >> 3, chunk = item & 7;
+            const int px = pr % twp, py = (pr / twp) % thp, pb = pr / (twp * thp);
+            const int r00 = (pb * p.TH + 2 * py) * p.TW + 2 * px;
+            const int rr[4] = {r00, r00 + 1, r00 + p.TW, r00 + p.TW + 1};
+            uint4 m4 = *reinterpret_cast<const uint4*>(stg + rr[0] * 128 + ((chunk ^ (rr[0] & 7)) * 16));
+#pragma unroll
+            for (int k = 1; k < 4; ++k) {
+              const uint4 u = *reinterpret_cast<const uint4*>(stg + rr[k] * 128 + ((chunk ^ (rr[k] & 7)) * 16));
+              __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&m4);
+              const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) a2[e] = __hmax2(a2[e], b2[e]);
+            }
+            *reinterpret_cast<uint4*>(pst + pr * 128 + ((chunk ^ (pr & 7)) * 16)) = m4;
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (threadIdx.x == 64) {
+            tma_store_4d(&tmP, pst, n0 + g * 64, x0[mt] >> 1, y0[mt] >> 1, b0[mt]);
+            tma_store_commit();
+          }
         }
       }
     }
@@ -739,7 +773,10 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
 
   constexpr int kStageBytes = MT * kATileBytes + BN * 128;
   // epilogue staging (one 16 KB tile per 64-channel group) + 2 mask-tile slots alias the drained pipeline
-  const int epi_bytes = (MT * (BN / 64) + (a.mask_act ? 2 : 0)) * kATileBytes;
+  const bool fuse_pool = !PERSIST && !HALO && EPI == 0 && a.pool_out != nullptr && p.TW % 2 == 0 && p.TH % 2 == 0 &&
+                         a.H >= 2 && a.W >= 2;
+  p.fuse_pool = fuse_pool ? 1 : 0;
+  const int epi_bytes = (MT * (BN / 64) + (a.mask_act ? 2 : 0)) * kATileBytes + (fuse_pool ? MT * (BN / 64) * 4096 : 0);
   int stages;
   size_t ring_bytes;
   if (PERSIST) {
@@ -771,7 +808,7 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
   const size_t smem_bytes = 1024 + ring_bytes + 256;
   ISX_REQUIRE(smem_bytes <= 227 * 1024, "conv_tc: %zu B of shared memory exceed 227 KB", smem_bytes);
 
-  CUtensorMap tmA, tmB, tmO, tmM, tmA2, tmB2;
+  CUtensorMap tmA, tmB, tmO, tmM, tmA2, tmB2, tmP;
   {
     uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
     uint64_t str[3] = {(uint64_t)a.Cin * 2, (uint64_t)a.W * a.Cin * 2, (uint64_t)a.H * a.W * a.Cin * 2};
@@ -794,7 +831,13 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
   } else {
     tmO = tmA;  // unused by the image-gradient epilogue
   }
-  tmM = tmO; tmA2 = tmA; tmB2 = tmB;
+  tmM = tmO; tmA2 = tmA; tmB2 = tmB; tmP = tmO;
+  if (fuse_pool) {
+    uint64_t dims[4] = {(uint64_t)a.Cout, (uint64_t)(a.W / 2), (uint64_t)(a.H / 2), (uint64_t)a.B};
+    uint64_t str[3] = {(uint64_t)a.Cout * 2, (uint64_t)(a.W / 2) * a.Cout * 2, (uint64_t)(a.H / 2) * (a.W / 2) * a.Cout * 2};
+    uint32_t box[4] = {64, (uint32_t)(p.TW / 2), (uint32_t)(p.TH / 2), (uint32_t)p.TB};
+    if (isx_make_tmap_bf16(&tmP, a.pool_out, 4, dims, str, box, true)) return 3;
+  }
   if (EPI == 0 && a.mask_act != nullptr) {
     uint64_t dims[4] = {(uint64_t)a.Cout, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
     uint64_t str[3] = {(uint64_t)a.Cout * 2, (uint64_t)a.W * a.Cout * 2, (uint64_t)a.H * a.W * a.Cout * 2};
@@ -829,9 +872,11 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
   ISX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   isx_prof_begin(ISX_PROF_CONV,
                  2.0 * (a.ntaps * a.Cin + (a.gram_act ? a.Cout : 0)) * a.Cout * static_cast<double>(a.B) * a.H * a.W, stream);
-  kern<<<(unsigned)grid, 192, smem_bytes, stream>>>(tmA, tmB, tmO, tmM, tmA2, tmB2, p);
+  kern<<<(unsigned)grid, 192, smem_bytes, stream>>>(tmA, tmB, tmO, tmM, tmA2, tmB2, tmP, p);
   isx_prof_end(ISX_PROF_CONV, stream);
   ISX_LAUNCH_CHECK();
+  if (a.pool_out != nullptr && !fuse_pool)  // patch shape not poolable in the epilogue: separate kernel
+    return maxpool_fwd(a.out, a.pool_out, a.B, a.H, a.W, a.Cout, stream);
   return 0;
   }
 }

@@ -15,6 +15,7 @@ struct ConvArgs {
   bool per_image_weights = false;
   const float* bias = nullptr;
   int relu = 0;
+  __nv_bfloat16* pool_out = nullptr;  // also write MaxPool2d(2,2)(out) [B,H/2,W/2,Cout] (fused into the epilogue when possible)
   const __nv_bfloat16* mask_act = nullptr;
   const __nv_bfloat16* add_buf = nullptr;
   const float* aff_a = nullptr;

@@ -110,7 +110,7 @@ int content_tap_of(const isx_nst_config* c, int conv) {
 
 // forward through conv `i` (input selection included)
 int run_conv_fwd(const isx_nst_config* c, const isx_nst_buffers* b, const Layout& L, int i, const float* x,
-                 cudaStream_t s) {
+                 bool want_pool, cudaStream_t s) {
   const int lv = kLevel[i];
   if (i == 0 && b->w0_fwd != nullptr)
     return conv1_1_fwd_tc(x, c->xc, c->mask_b ? b->input_mask : nullptr, c->mask_b,
@@ -125,6 +125,10 @@ int run_conv_fwd(const isx_nst_config* c, const isx_nst_buffers* b, const Layout
   a.in = in; a.weight = reinterpret_cast<const bf16*>(b->w_fwd[i]); a.out = at(b, L.act[i]);
   a.B = c->B; a.H = L.H[lv]; a.W = L.W[lv]; a.Cin = kCin[i]; a.Cout = kCout[i]; a.ntaps = 9;
   a.bias = b->bias[i]; a.relu = 1;
+  if (want_pool) {  // MaxPool2d(2,2) of this layer's output rides the conv epilogue
+    ISX_REQUIRE(L.H[lv] >= 2 && L.W[lv] >= 2, "nst: cannot pool a %dx%d map", L.H[lv], L.W[lv]);
+    a.pool_out = at(b, L.pool[lv]);
+  }
   return conv_tc(a, s);
 }
 }  // namespace
@@ -142,10 +146,10 @@ extern "C" int isx_nst_forward(const isx_nst_config* c, const isx_nst_buffers* b
   if (int rc = make_layout(c, &L)) return rc;
   cudaStream_t s = S(stream);
   for (int i = 0; i < c->n_conv; ++i) {
-    if (int rc = run_conv_fwd(c, b, L, i, x, s)) return rc;
-    if (pool_after(i) && (i + 1 < c->n_conv || with_last_pool)) {
+    const bool want_pool = pool_after(i) && (i + 1 < c->n_conv || with_last_pool);
+    if (int rc = run_conv_fwd(c, b, L, i, x, want_pool && i > 0, s)) return rc;
+    if (want_pool && i == 0) {  // (conv1_1 is never followed by a pool in VGG-19; kept for completeness)
       const int lv = kLevel[i];
-      ISX_REQUIRE(L.H[lv] >= 2 && L.W[lv] >= 2, "nst: cannot pool a %dx%d map", L.H[lv], L.W[lv]);
       if (int rc = maxpool_fwd(at(b, L.act[i]), at(b, L.pool[lv]), c->B, L.H[lv], L.W[lv], kCout[i], s)) return rc;
     }
   }
@@ -308,14 +312,10 @@ extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, c
 
   // ---------------- forward + losses ----------------
   for (int i = 0; i < c->n_conv; ++i) {
-    if (int rc = run_conv_fwd(c, b, L, i, x, s)) return rc;
+    if (int rc = run_conv_fwd(c, b, L, i, x, pool_after(i) && i + 1 < c->n_conv, s)) return rc;
     const int lv = kLevel[i];
     const int C = kCout[i];
     const long HW = static_cast<long>(L.H[lv]) * L.W[lv];
-    if (pool_after(i) && i + 1 < c->n_conv) {
-      ISX_REQUIRE(L.H[lv] >= 2 && L.W[lv] >= 2, "nst: cannot pool a %dx%d map", L.H[lv], L.W[lv]);
-      if (int rc = maxpool_fwd(at(b, L.act[i]), at(b, L.pool[lv]), B, L.H[lv], L.W[lv], C, s)) return rc;
-    }
     const int st = style_tap_of(c, i);
     if (st >= 0) {
       const double w = c->style_w[st];

@@ -73,6 +73,28 @@ def test_conv3x3_fwd(isx, shape, cfg):
     assert_close_bf16(out, ref.permute(0, 2, 3, 1), "conv fwd %s cfg %d" % (shape, cfg))
 
 
+@pytest.mark.parametrize("shape", CONV_SHAPES + [(2, 40, 48, 64, 64), (1, 100, 160, 128, 256)])
+@pytest.mark.parametrize("cfg", [0, 6410, 12820, 25610])
+def test_conv3x3_fwd_fused_pool(isx, shape, cfg):
+    """Conv + ReLU with MaxPool2d(2,2) emitted from the epilogue: both outputs against torch (pool is exact on the bf16 tile)."""
+    B, H, W, Cin, Cout = shape
+    bn = cfg // 100
+    if bn and Cout % bn:
+        pytest.skip("BN does not divide Cout")
+    x = nhwc_bf16(B, H, W, Cin, 1, relu=True)
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") * (2.0 / (9 * Cin)) ** 0.5
+    bias = torch.randn(Cout, device="cuda") * 0.1
+    wf, _ = pack(isx, w)
+    out = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    pool = torch.full((B, H // 2, W // 2, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    isx.call("isx_conv3x3_bias_relu_pool_fwd", x, wf, bias, out, pool, B, H, W, Cin, Cout, cfg, isx.stream_ptr())
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), bias, padding=1))
+    assert_close_bf16(out, ref.permute(0, 2, 3, 1), "conv fwd (+pool) %s cfg %d" % (shape, cfg))
+    ref_pool = F.max_pool2d(out.float().permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+    assert torch.equal(pool.float(), ref_pool)
+
+
 @pytest.mark.parametrize("shape", CONV_SHAPES)
 @pytest.mark.parametrize("mode", ["plain", "mask", "mask_add", "mask_affine"])
 def test_conv3x3_dgrad(isx, shape, mode):
