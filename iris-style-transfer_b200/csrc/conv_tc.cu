@@ -58,8 +58,10 @@ static constexpr int kHaloBytes = 18 * 16 * 128;  // (16+2) rows x 16 pixel slot
 // its halo ([18][16] pixel slots, pitch 2048 B) and the nine taps are nine shifted views of it -- the A descriptor
 // simply starts at row (ky*16 + kx) with SBO = 2048 B and swizzle phase kx -- so L2->SM traffic per chunk drops
 // from 9 x 16 KB to 36 KB; only the weight slabs stream per tap (their own smem ring).
+static constexpr int kConvThreads = 64 + 256;  // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant)
+
 template <int BN, int MT, int EPI, bool HALO = false>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kConvThreads, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmM,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
@@ -253,6 +255,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 2) {
     // ================================ epilogue =============================================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int hsel = (warp - 2) >> 2;  // which 32-column half of every 64-channel group this warp converts
     const int row = q * 32 + lane;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
@@ -262,7 +265,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if constexpr (EPI == 1) {
       // image-gradient tail: 3 (of 16) accumulator columns -> fp32 NCHW planes, Normalize backward (1/std), mask
 #pragma unroll 1
-      for (int mt = 0; mt < MT; ++mt) {
+      for (int mt = hsel == 0 ? 0 : MT; mt < MT; ++mt) {
         const int x = x0[mt] + tw, y = y0[mt] + th, b = b0[mt] + tb;
         const bool valid = (x < p.W) && (y < p.H) && (b < p.B);
         uint32_t v[16];
@@ -308,8 +311,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* stg = smem + gi * kATileBytes;  // pipeline smem is drained by now
         const uint8_t* mrow = scratch + (gi & 1) * kATileBytes + row * 128;
         if (use_mask) mbar_wait(&epi_bar[gi & 1], (gi >> 1) & 1);
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
+        {
+          const int h = hsel;
           const int nloc = g * 64 + h * 32;
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mt * BN + nloc, v);
@@ -376,7 +379,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
         if (threadIdx.x == 64) {
           tma_store_4d(&tmO, stg, n0 + g * 64, x0[mt], y0[mt], b0[mt]);
           tma_store_commit();
@@ -386,10 +389,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // K2 fused: 2x2 max-pool of the staged bf16 tile -> 32 pooled pixels x 64 channels (MaxPool2d(2,2) after ReLU)
           uint8_t* pst = smem + (NG + (use_mask ? 2 : 0)) * kATileBytes + gi * 4096;
           const int twp = p.TW >> 1, thp = p.TH >> 1;
-          const int et = threadIdx.x - 64;  // 0..127
-#pragma unroll
-          for (int it2 = 0; it2 < 2; ++it2) {
-            const int item = et + it2 * 128;
+          const int et = threadIdx.x - 64;  // 0..255
+          {
+            const int item = et;
             const int pr = item >> 3, chunk = item & 7;
             const int px = pr % twp, py = (pr / twp) % thp, pb = pr / (twp * thp);
             const int r00 = (pb * p.TH + 2 * py) * p.TW + 2 * px;
@@ -406,7 +408,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             *reinterpret_cast<uint4*>(pst + pr * 128 + ((chunk ^ (pr & 7)) * 16)) = m4;
           }
           fence_proxy_async_smem();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
           if (threadIdx.x == 64) {
             tma_store_4d(&tmP, pst, n0 + g * 64, x0[mt] >> 1, y0[mt] >> 1, b0[mt]);
             tma_store_commit();
@@ -872,7 +874,7 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
   ISX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   isx_prof_begin(ISX_PROF_CONV,
                  2.0 * (a.ntaps * a.Cin + (a.gram_act ? a.Cout : 0)) * a.Cout * static_cast<double>(a.B) * a.H * a.W, stream);
-  kern<<<(unsigned)grid, 192, smem_bytes, stream>>>(tmA, tmB, tmO, tmM, tmA2, tmB2, tmP, p);
+  kern<<<(unsigned)grid, kConvThreads, smem_bytes, stream>>>(tmA, tmB, tmO, tmM, tmA2, tmB2, tmP, p);
   isx_prof_end(ISX_PROF_CONV, stream);
   ISX_LAUNCH_CHECK();
   if (a.pool_out != nullptr && !fuse_pool)  // patch shape not poolable in the epilogue: separate kernel
