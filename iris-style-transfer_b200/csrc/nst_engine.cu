@@ -49,9 +49,10 @@ int make_layout(const isx_nst_config* c, Layout* L) {
   size_t max_act = 0, max_tap = 0;
   for (int i = 0; i < 16; ++i) {
     L->act[i] = off;
-    if (i < c->n_conv || true) {
-      size_t bytes = static_cast<size_t>(c->B) * L->H[kLevel[i]] * L->W[kLevel[i]] * kCout[i] * 2;
-      if (i < c->n_conv) { off += align_up(bytes); max_act = std::max(max_act, bytes); }
+    if (i < c->n_conv) {
+      const size_t bytes = static_cast<size_t>(c->B) * L->H[kLevel[i]] * L->W[kLevel[i]] * kCout[i] * 2;
+      off += align_up(bytes);
+      max_act = std::max(max_act, bytes);
     }
   }
   for (int k = 0; k < 5; ++k) {
