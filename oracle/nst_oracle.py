@@ -379,7 +379,7 @@ def nst_eval(x, c_feats, targets, weights, BN_loss, c_loss_weight, s_loss_weight
             s_loss = style_loss_gram(x_s, targets)
         loss = c_loss * c_loss_weight + s_loss * s_loss_weight
         (g,) = torch.autograd.grad(loss, xv)
-    return float(c_loss.detach()), float(s_loss.detach()), g
+    return float(torch.as_tensor(c_loss).detach()), float(torch.as_tensor(s_loss).detach()), g
 
 
 # --------------------------------------------------------------------------------------

@@ -553,6 +553,69 @@ def test_modules_are_differentiable_like_the_reference(mods, BN):
         out3[0].sum().backward()
 
 
+LAYER_CONFIGS = [
+    # (content layers, style layers): every branch of the source-driven backward
+    (["relu4_2"], ["relu1_1", "relu2_1", "relu3_1", "relu4_1"]),          # reference default
+    (["relu2_2"], ["relu1_1", "relu2_2"]),                                 # content + style on one PRE-POOL layer
+    (["relu3_3"], ["relu1_2", "relu3_3", "relu4_1"]),                      # style deeper than content, style on a pre-pool layer
+    (["relu1_1"], ["relu3_4"]),                                            # deepest layer is a pre-pool style tap, shallow content
+    (["relu2_1", "relu4_2"], ["conv3_1"]),                                 # two content taps, conv* alias of a ReLU tap (note N2)
+    ([], ["relu1_1", "relu2_1"]),                                          # style only
+    (["relu3_2"], []),                                                     # content only
+]
+
+
+@pytest.mark.parametrize("BN", [False, True])
+@pytest.mark.parametrize("cfg_id", range(len(LAYER_CONFIGS)))
+def test_eval_layer_configurations(mods, cfg_id, BN):
+    """One closure evaluation (losses + image gradient) against the oracle for tap sets that exercise every path of the
+    backward: fused Gram K-blocks, affine BN epilogue, taps behind a max-pool, several sources on one layer, 1-channel
+    input broadcast (xc = 1)."""
+    import iris_b200
+
+    E, O = mods["engine"], mods["O"]
+    content, style = LAYER_CONFIGS[cfg_id]
+    if BN and not style:
+        pytest.skip("no style taps")
+    dev = torch.device("cuda:0")
+    net = iris_b200.VGG19(content_layers=content, style_layers=style, weights=mods["weights"])
+    H, W = 56, 72
+    xc = 1 if cfg_id % 2 else 3
+    c, s, xq = (rand_img(k, (2, xc, H, W)) for k in (91 + cfg_id, 92 + cfg_id, 93 + cfg_id))
+    beta = 1e4 if BN else 1e6
+    eng = E.NstEngine(net.packed(dev), 2, H, W, xc, net.content_convs, net.style_convs, style_mode=int(BN), c_weight=1.0,
+                      s_weight=beta, coupled=True)
+    eng.forward(c.to(dev))
+    eng.set_content_targets([eng.feature(0, i) for i in net.content_convs])
+    eng.forward(s.to(dev))
+    feats = [eng.feature(0, i) for i in net.style_convs]
+    if BN:
+        st = [E.stats_of(f) for f in feats]
+        eng.set_bn_targets([m for m, _ in st], [d for _, d in st])
+    else:
+        eng.set_gram_targets([E.gram_of(f) for f in feats])
+    g = torch.empty(2, xc, H, W, device=dev)
+    eng.eval(xq.to(dev), g)
+    torch.cuda.synchronize()
+    W_ = mods["weights"]
+    with torch.no_grad():
+        _, cf, _ = O.vgg19_forward(c, W_, content_layers=content, style_layers=style, full=False)
+        _, _, sf = O.vgg19_forward(s, W_, content_layers=content, style_layers=style, full=False)
+    targets = ([t.mean(dim=(-2, -1)) for t in sf], [t.std(dim=(-2, -1)) for t in sf]) if BN else [O.gram_matrix(t) for t in sf]
+    rcl, rsl, rg = O.nst_eval(xq, cf, targets, W_, BN, 1.0, beta, content_layers=content, style_layers=style)
+    gc = g.cpu()
+    cos = float((gc * rg).sum() / (gc.norm() * rg.norm()))
+    cl, sl = float(eng.loss_c.sum()), float(eng.loss_s.sum())
+    print("cfg %d BN=%s xc=%d: c %.5g/%.5g s %.5g/%.5g cos %.4f |g| ratio %.3f" % (
+        cfg_id, BN, xc, cl, rcl, sl, rsl, cos, float(gc.norm() / rg.norm())))
+    assert tuple(rg.shape) == tuple(gc.shape)
+    if content:
+        assert cl == pytest.approx(rcl, rel=1e-2)
+    if style:
+        assert sl == pytest.approx(rsl, rel=1e-2)
+    assert cos > 0.97 and 0.8 < float(gc.norm() / rg.norm()) < 1.25
+
+
 def test_cpu_device_is_refused(mods):
     with pytest.raises(Exception):
         mods["pipelines"].nst(rand_img(1, (1, 3, 32, 32)), rand_img(2, (1, 3, 32, 32)), vgg=mods["vgg"],
