@@ -202,11 +202,15 @@ namespace isx {
 extern int g_isx_halo_mode;
 extern int g_isx_halo_max_cout;
 extern int g_isx_persist;
+extern int g_isx_c64;
+extern int g_isx_c64_slots;
 }
 extern "C" int isx_set_option(const char* name, int value) {
   ISX_REQUIRE(name != nullptr, "isx_set_option: null name");
   if (strcmp(name, "halo_mode") == 0) { isx::g_isx_halo_mode = value; return 0; }
   if (strcmp(name, "halo_max_cout") == 0) { isx::g_isx_halo_max_cout = value; return 0; }
   if (strcmp(name, "persist") == 0) { isx::g_isx_persist = value; return 0; }
+  if (strcmp(name, "c64") == 0) { isx::g_isx_c64 = value; return 0; }
+  if (strcmp(name, "c64_slots") == 0) { isx::g_isx_c64_slots = value; return 0; }
   ISX_REQUIRE(false, "isx_set_option: unknown option '%s'", name);
 }

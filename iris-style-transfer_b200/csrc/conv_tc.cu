@@ -232,23 +232,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================================ MMA issuer ===========================================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, false, false);
+      // The issuing thread is the bottleneck of the N <= 128 tiles (isx_common.cuh, umma_bf16_lohi): one descriptor is
+      // built here, every MMA adds an immediate to its low word.
+      const uint64_t d0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
+      const uint32_t d_hi = static_cast<uint32_t>(d0 >> 32);
+      uint32_t a_lo = static_cast<uint32_t>(d0);
+      int s = 0;
+      uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (kb / stages) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
-        const uint32_t b_addr = a_addr + MT * kATileBytes;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K(16) = 64 channels
-            const uint64_t da = umma_desc_sw128(a_addr + mt * kATileBytes + k * 32, 16, 1024);
-            const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16(tmem_base + mt * BN, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)  // 4 x UMMA_K(16) = 64 channels
+            umma_bf16_lohi(tmem_base + mt * BN, a_lo + ((mt * kATileBytes + k * 32) >> 4), d_hi,
+                           a_lo + ((MT * kATileBytes + k * 32) >> 4), d_hi, idesc, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+        a_lo += kStageBytes >> 4;
+        if (++s == stages) { s = 0; ph ^= 1; a_lo = static_cast<uint32_t>(d0); }
       }
       umma_commit(tmem_full_bar);
     }
@@ -887,9 +890,15 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
 int g_isx_halo_mode = 0;
 int g_isx_halo_max_cout = 64;
 int g_isx_persist = 0;  // 1: persistent double-buffered kernel for every tensor-core conv
+// Specialised Cin = 64 kernel (resident weights + halo patch, conv_c64.cu).  0: never; 1 (default): the 64 -> 64 layers
+// when there is at least one tile per SM; 2: every applicable call, including the N = 16 tail and tiny inputs (tests).
+int g_isx_c64 = 1;
 
 int conv_tc(const ConvArgs& a_in, cudaStream_t stream) {
   ConvArgs a = a_in;
+  if (g_isx_c64 > 0 && a.force_bn == 0 && a.halo_mode == 0 && a.persist == 0 && conv_c64_applicable(a) &&
+      (g_isx_c64 >= 2 || (a.dx_nchw == nullptr && static_cast<long>(a.B) * ((a.H + 15) / 16) * ((a.W + 7) / 8) >= kNumSMs)))
+    return conv_c64(a, stream);
   if (a.halo_mode == 0 && a.force_bn == 0 && g_isx_halo_mode > 0 && a.ntaps == 9 && !a.per_image_weights &&
       a.Cout <= g_isx_halo_max_cout && static_cast<long>(a.B) * ((a.H + 15) / 16) * ((a.W + 7) / 8) >= 2 * kNumSMs)
     a.halo_mode = g_isx_halo_mode;

@@ -33,6 +33,8 @@ struct ConvArgs {
   int mask_b = 0;
 };
 int conv_tc(const ConvArgs& a, cudaStream_t stream);
+bool conv_c64_applicable(const ConvArgs& a);
+int conv_c64(const ConvArgs& a, cudaStream_t stream);
 
 // Gram partial products: partial[b][split][C][C] (fp32) = sum over the split's pixels of F^T F.
 int gram_tc_partial(const __nv_bfloat16* feat, int B, int HW, int C, int splits, float* partial,

@@ -141,6 +141,75 @@ def test_conv3x3_dgrad_fused_gram(isx, shape):
     assert_close_bf16(dx, ref, "dgrad + fused gram %s" % (shape,))
 
 
+# ---- the specialised Cin = 64 kernel (conv_c64.cu): persistent CTAs, resident weights, halo patch --------------------
+C64_SHAPES = [
+    (2, 20, 24, 64, 64),      # fewer tiles than SMs
+    (3, 13, 9, 64, 64),       # ragged in x and y
+    (4, 160, 200, 64, 64),    # ~7 tiles per CTA: the halo ring and both TMEM accumulator sets wrap
+    (2, 41, 37, 64, 64),      # odd sizes: fused pool drops the last row/column
+]
+
+
+@pytest.fixture
+def c64_forced(isx):
+    """Route every applicable call through conv_c64 (option 2 also takes the N = 16 tail and inputs smaller than one
+    tile per SM, which the default heuristic leaves to the generic kernel)."""
+    lib = isx.load()
+    assert lib.isx_set_option(b"c64", 2) == 0
+    yield
+    assert lib.isx_set_option(b"c64", 1) == 0
+
+
+@pytest.mark.parametrize("shape", C64_SHAPES)
+def test_conv_c64_fwd_and_pool(isx, c64_forced, shape):
+    test_conv3x3_fwd(isx, shape, 0)
+    test_conv3x3_fwd_fused_pool(isx, shape, 0)
+
+
+@pytest.mark.parametrize("shape", C64_SHAPES)
+@pytest.mark.parametrize("mode", ["plain", "mask", "mask_add", "mask_affine", "gram"])
+def test_conv_c64_dgrad(isx, c64_forced, shape, mode):
+    if mode == "gram":
+        test_conv3x3_dgrad_fused_gram(isx, shape)
+    else:
+        test_conv3x3_dgrad(isx, shape, mode)
+
+
+@pytest.mark.parametrize("xc", [3, 1])
+@pytest.mark.parametrize("use_mask", [False, True])
+def test_conv_c64_tail(isx, c64_forced, xc, use_mask):
+    test_conv1_1_fwd_dgrad(isx, xc, use_mask)
+
+
+def test_conv_c64_matches_generic_kernel(isx):
+    """Same inputs through the generic tcgen05 kernel and through conv_c64: the MMAs run in the same order
+    (tap-major, then the Gram block), so the bf16 results must be identical."""
+    lib = isx.load()
+    B, H, W = 3, 48, 56
+    x = nhwc_bf16(B, H, W, 64, 11, relu=True)
+    w = torch.randn(64, 64, 3, 3, device="cuda") * (2.0 / (9 * 64)) ** 0.5
+    bias = torch.randn(64, device="cuda") * 0.1
+    wf, wd = pack(isx, w)
+    act = nhwc_bf16(B, H, W, 64, 3, relu=True)
+    D = torch.randn(B, 64, 64, device="cuda") * 0.05
+    D = (D + D.transpose(1, 2)).to(torch.bfloat16).contiguous()
+    res = {}
+    try:
+        for mode in (0, 2):
+            assert lib.isx_set_option(b"c64", mode) == 0
+            out = torch.empty(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
+            pool = torch.empty(B, H // 2, W // 2, 64, device="cuda", dtype=torch.bfloat16)
+            dx = torch.empty_like(out)
+            isx.call("isx_conv3x3_bias_relu_pool_fwd", x, wf, bias, out, pool, B, H, W, 64, 64, 0, isx.stream_ptr())
+            isx.call("isx_conv3x3_dgrad_gram", x, wd, dx, B, H, W, 64, 64, act, D, isx.stream_ptr())
+            torch.cuda.synchronize()
+            res[mode] = (out, pool, dx)
+    finally:
+        lib.isx_set_option(b"c64", 1)
+    for a, b in zip(res[0], res[2]):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("C", [64, 128, 256, 512])
 @pytest.mark.parametrize("B,H,W", [(1, 50, 80), (3, 17, 23), (2, 100, 160)])
 def test_gram_fwd_and_loss(isx, C, B, H, W):
