@@ -258,13 +258,14 @@ def main():
     # ------------------------------------------------------------------ end-to-end leg (public API, host buffers)
     e2e = None
     if not args.no_e2e:
+        x_host = torch.empty_like(c_host).pin_memory()
         barrier()
         t0 = time.perf_counter()
         x, _, c_hist, s_hist = iris_b200.nst(c_host, s_host, BN_loss=False, c_loss_weight=1.0, s_loss_weight=1e6,
                                               epochs=K, vgg=vgg, use_tqdm=False, device=str(dev), independent=True,
                                               x_hist_stride=0, streams=args.streams,
                                               history_dtype=torch.bfloat16 if args.history_bf16 else torch.float32)
-        x_host = x.cpu()
+        x_host.copy_(x, non_blocking=True)  # result image back into pinned host memory
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         evals = len(s_hist)

@@ -58,6 +58,20 @@ __host__ __device__ inline C64Layout c64_layout(int halo_slots, int use_mask, in
   return L;
 }
 
+// The tiles of a persistent CTA: w = first, first + stride, ... decomposed into (image b, tile r within the image)
+// incrementally -- no 64-bit division per tile.
+struct TileWalk {
+  int b, r, stride, per_img, tiles_x;
+  __device__ TileWalk(int first, int stride_, int per_img_, int tiles_x_)
+      : b(first / per_img_), r(first % per_img_), stride(stride_), per_img(per_img_), tiles_x(tiles_x_) {}
+  __device__ void next() {
+    r += stride;
+    while (r >= per_img) { r -= per_img; ++b; }
+  }
+  __device__ int x0() const { return (r % tiles_x) * 8; }
+  __device__ int y0() const { return (r / tiles_x) * 16; }
+};
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kC64Threads, 1)
 conv_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -109,34 +123,35 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const long total = p.total_items;
-  const long per_img = static_cast<long>(p.tiles_x) * p.tiles_y;
+  const int total = static_cast<int>(p.total_items);  // < 2^31 (checked at launch)
+  const int per_img = p.tiles_x * p.tiles_y;
+  const int n_my = (total - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
   if (warp == 0) {
     // ================================ TMA producer =========================================
     if (lane == 0) {
       mbar_arrive_expect_tx(w_full, 9 * kWSlab);
       for (int tap = 0; tap < 9; ++tap) tma_load_2d(smem + L.w + tap * kWSlab, &tmW, w_full, 0, tap * p.Cout);
-      uint32_t it = 0;
-      for (long w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-        const int b = static_cast<int>(w / per_img);
-        const int r = static_cast<int>(w - b * per_img);
-        const int x0 = (r % p.tiles_x) * 8, y0 = (r / p.tiles_x) * 16;
-        const int hs = it % HS;
-        mbar_wait(&halo_empty[hs], ((it / HS) & 1) ^ 1);
+      TileWalk tw(blockIdx.x, gridDim.x, per_img, p.tiles_x);
+      uint32_t hs = 0, hph = 0, as = 0, aph = 0;
+      for (int i = 0; i < n_my; ++i, tw.next()) {
+        const int b = tw.b, x0 = tw.x0(), y0 = tw.y0();
+        mbar_wait(&halo_empty[hs], hph ^ 1);
         mbar_arrive_expect_tx(&halo_full[hs], kHalo);
         tma_load_4d(smem + L.halo + hs * kHalo, &tmA, &halo_full[hs], 0, x0 - 1, y0 - 1, b);
-        const int as = it & 1;
+        if (++hs == static_cast<uint32_t>(HS)) { hs = 0; hph ^= 1; }
         if (p.use_mask) {
-          mbar_wait(&act_empty[as], ((it >> 1) & 1) ^ 1);
+          mbar_wait(&act_empty[as], aph ^ 1);
           mbar_arrive_expect_tx(&act_full[as], kTile);
           tma_load_4d(smem + L.act + as * kTile, &tmM, &act_full[as], 0, x0, y0, b);
         }
         if (p.use_gram) {
-          mbar_wait(&d_empty[as], ((it >> 1) & 1) ^ 1);
+          mbar_wait(&d_empty[as], aph ^ 1);
           mbar_arrive_expect_tx(&d_full[as], kWSlab);
           tma_load_2d(smem + L.d + as * ((kWSlab + 1023) / 1024) * 1024, &tmD, &d_full[as], 0, b * p.Cout);
         }
+        as ^= 1;
+        if (as == 0) aph ^= 1;
       }
     }
   } else if (warp == 1) {
@@ -148,15 +163,16 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint64_t da0 = umma_desc_sw128(smem_u32(smem + L.halo), 16, 2048);
       const uint32_t w_lo = static_cast<uint32_t>(dw0), w_hi = static_cast<uint32_t>(dw0 >> 32);
       const uint32_t a_lo0 = static_cast<uint32_t>(da0), a_hi = static_cast<uint32_t>(da0 >> 32);
-      uint32_t it = 0;
-      for (long w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-        const uint32_t acc = it & 1;
-        const int hs = it % HS;
-        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
-        mbar_wait(&halo_full[hs], (it / HS) & 1);
+      // Gram block operands: plain 128-row tiles (SBO 1024, same high word as the weight descriptor)
+      constexpr int kDSlab = ((kWSlab + 1023) / 1024) * 1024;
+      const uint32_t act_lo0 = static_cast<uint32_t>(umma_desc_sw128(smem_u32(smem + L.act), 16, 1024));
+      const uint32_t d_lo0 = static_cast<uint32_t>(umma_desc_sw128(smem_u32(smem + L.d), 16, 1024));
+      // running ring / phase counters: no division, no 64-bit arithmetic on the issuing thread's critical path
+      uint32_t hs = 0, hph = 0, acc = 0, aph = 0, a_lo = a_lo0;
+      for (int i = 0; i < n_my; ++i) {
+        mbar_wait2(&tmem_empty[acc], aph ^ 1, &halo_full[hs], hph);
         tc_fence_after();
         const uint32_t d_tm = tmem_base + acc * kAccCols;
-        const uint32_t a_lo = a_lo0 + hs * (kHalo >> 4);
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int ky = tap / 3, kx = tap - ky * 3;
@@ -167,19 +183,19 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         umma_commit(&halo_empty[hs]);
         if (p.use_gram) {  // + act . D_b
-          const int as = it & 1;
-          mbar_wait(&act_full[as], (it >> 1) & 1);
-          mbar_wait(&d_full[as], (it >> 1) & 1);
+          mbar_wait2(&act_full[acc], aph, &d_full[acc], aph);
           tc_fence_after();
-          const uint64_t d2a = umma_desc_sw128(smem_u32(smem + L.act + as * kTile), 16, 1024);
-          const uint64_t d2b = umma_desc_sw128(smem_u32(smem + L.d + as * ((kWSlab + 1023) / 1024) * 1024), 16, 1024);
+          const uint32_t a2_lo = act_lo0 + acc * (kTile >> 4), b2_lo = d_lo0 + acc * (kDSlab >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16_lohi(d_tm, static_cast<uint32_t>(d2a) + 2 * k, static_cast<uint32_t>(d2a >> 32),
-                           static_cast<uint32_t>(d2b) + 2 * k, static_cast<uint32_t>(d2b >> 32), idesc, 1u);
-          umma_commit(&d_empty[as]);
+            umma_bf16_lohi(d_tm, a2_lo + 2 * k, w_hi, b2_lo + 2 * k, w_hi, idesc, 1u);
+          umma_commit(&d_empty[acc]);
         }
         umma_commit(&tmem_full[acc]);
+        a_lo += kHalo >> 4;
+        if (++hs == static_cast<uint32_t>(HS)) { hs = 0; hph ^= 1; a_lo = a_lo0; }
+        acc ^= 1;
+        if (acc == 0) aph ^= 1;
       }
     }
   } else {
@@ -188,11 +204,10 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int hsel = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int tw = row & 7, th = row >> 3;
+    TileWalk tiles(blockIdx.x, gridDim.x, per_img, p.tiles_x);
     uint32_t it = 0, gc = 0;
-    for (long w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-      const int b = static_cast<int>(w / per_img);
-      const int r = static_cast<int>(w - b * per_img);
-      const int x0 = (r % p.tiles_x) * 8, y0 = (r / p.tiles_x) * 16;
+    for (int i = 0; i < n_my; ++i, ++it, tiles.next()) {
+      const int b = tiles.b, x0 = tiles.x0(), y0 = tiles.y0();
       const uint32_t acc = it & 1;
       const int as = it & 1;
       const uint32_t d_tm = tmem_base + acc * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
@@ -355,6 +370,7 @@ static int launch_c64(const ConvArgs& a, cudaStream_t stream) {
   p.tiles_x = (a.W + 7) / 8;
   p.tiles_y = (a.H + 15) / 16;
   p.total_items = static_cast<long>(p.tiles_x) * p.tiles_y * a.B;
+  ISX_REQUIRE(p.total_items < (1L << 31) - kNumSMs, "conv_c64: too many tiles");
   p.relu = a.relu; p.bias = a.bias; p.add_buf = a.add_buf; p.aff_a = a.aff_a; p.aff_b = a.aff_b;
   p.use_mask = (EPI == 0 && a.mask_act != nullptr) ? 1 : 0;
   p.use_gram = (EPI == 0 && a.gram_act != nullptr) ? 1 : 0;

@@ -107,6 +107,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait on two barriers whose try_waits are issued back to back (the second does not wait for the first's result):
+// an mbarrier probe costs ~100+ cycles even when the phase has long completed, and the MMA-issuing thread of a
+// persistent kernel pays it once per barrier per tile.
+__device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t parity_a, uint64_t* bar_b, uint32_t parity_b) {
+  bool a = mbar_try_wait(bar_a, parity_a);
+  bool b = mbar_try_wait(bar_b, parity_b);
+  if (!a) mbar_wait(bar_a, parity_a);
+  if (!b) mbar_wait(bar_b, parity_b);
+}
+
 // ---------------- TMA ----------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

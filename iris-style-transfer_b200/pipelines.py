@@ -185,6 +185,7 @@ class NstJobGroup:
                 xi = x_init[lo:hi] if x_init is not None else None
                 self.jobs.append(NstJob(c_img[lo:hi], si, vgg, dev, x_init=xi, **kw))
         self.max_ticks = self.jobs[0].max_ticks
+        self.epochs = self.jobs[0].epochs
         self.P = B
 
     @property
@@ -311,9 +312,10 @@ def nst(c_img: torch.Tensor,
             job.tick()
             if pbar is not None:
                 pbar.update(1)
-            if job.ticks % 20 == 0 or job.ticks >= job.max_ticks:
-                # a problem finishes at an optimizer.step boundary: every 20 evaluations unless an early exit of
-                # lbfgs.py:370-374,463,511-526 fired (then up to 19 no-op ticks are spent before this check)
+            if job.ticks >= job.epochs:
+                # `while current_epoch[0] < epochs` (pipelines.py:79): no problem can finish before `epochs` evaluations,
+                # so the host never synchronises before that; afterwards it polls the device flags every tick (a problem
+                # whose optimizer.step exited early -- lbfgs.py:370-374,463,511-526 -- overshoots by up to 19).
                 if bool((job.evals_done() > 0).all().item()):
                     break
         if pbar is not None:
