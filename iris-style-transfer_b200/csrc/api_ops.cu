@@ -202,15 +202,21 @@ namespace isx {
 extern int g_isx_halo_mode;
 extern int g_isx_halo_max_cout;
 extern int g_isx_persist;
+extern int g_isx_conv_dbg_skip;
 extern int g_isx_c64;
 extern int g_isx_c64_slots;
+extern int g_isx_halo2;
+extern int g_isx_halo2_stages;
 }
 extern "C" int isx_set_option(const char* name, int value) {
   ISX_REQUIRE(name != nullptr, "isx_set_option: null name");
   if (strcmp(name, "halo_mode") == 0) { isx::g_isx_halo_mode = value; return 0; }
   if (strcmp(name, "halo_max_cout") == 0) { isx::g_isx_halo_max_cout = value; return 0; }
+  if (strcmp(name, "conv_dbg_skip") == 0) { isx::g_isx_conv_dbg_skip = value; return 0; }
   if (strcmp(name, "persist") == 0) { isx::g_isx_persist = value; return 0; }
   if (strcmp(name, "c64") == 0) { isx::g_isx_c64 = value; return 0; }
+  if (strcmp(name, "halo2") == 0) { isx::g_isx_halo2 = value; return 0; }
+  if (strcmp(name, "halo2_stages") == 0) { isx::g_isx_halo2_stages = value; return 0; }
   if (strcmp(name, "c64_slots") == 0) { isx::g_isx_c64_slots = value; return 0; }
   ISX_REQUIRE(false, "isx_set_option: unknown option '%s'", name);
 }

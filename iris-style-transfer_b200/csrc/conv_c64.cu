@@ -169,10 +169,18 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t d_lo0 = static_cast<uint32_t>(umma_desc_sw128(smem_u32(smem + L.d), 16, 1024));
       // running ring / phase counters: no division, no 64-bit arithmetic on the issuing thread's critical path
       uint32_t hs = 0, hph = 0, acc = 0, aph = 0, a_lo = a_lo0;
+      bool t_ready = false, h_ready = false;  // probes of the NEXT tile's barriers, issued before this tile's MMAs
       for (int i = 0; i < n_my; ++i) {
-        mbar_wait2(&tmem_empty[acc], aph ^ 1, &halo_full[hs], hph);
+        if (!t_ready) mbar_wait(&tmem_empty[acc], aph ^ 1);
+        if (!h_ready) mbar_wait(&halo_full[hs], hph);
         tc_fence_after();
         const uint32_t d_tm = tmem_base + acc * kAccCols;
+        {
+          const uint32_t hs_n = hs + 1 == static_cast<uint32_t>(HS) ? 0 : hs + 1;
+          const uint32_t hph_n = hs_n == 0 ? hph ^ 1 : hph;
+          t_ready = mbar_try_wait(&tmem_empty[acc ^ 1], acc == 1 ? aph : aph ^ 1);
+          h_ready = mbar_try_wait(&halo_full[hs_n], hph_n);
+        }
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int ky = tap / 3, kx = tap - ky * 3;

@@ -34,6 +34,7 @@ struct ConvParams {
   int halo_base_offset;      // halo mode: put the swizzle phase (kx) into the descriptor's base-offset field
   int extra_kb;              // fused Gram backward: extra K blocks (C/64) of  act(centre tap) x D_b  after the taps
   int stages;
+  int dbg_skip;              // experiment only (isx_set_option("conv_dbg_skip")): 1 = no A loads, 2 = no B loads (results garbage)
   int relu;
   const float* bias;         // [Cout] or null
   const __nv_bfloat16* mask_act;  // [B,H,W,Cout] or null: out = act > 0 ? out : 0
@@ -47,6 +48,8 @@ struct ConvParams {
   const float* in_mask;      // [mask_b,1,H,W] or null
   int mask_b;
 };
+
+extern int g_isx_conv_dbg_skip;
 
 static constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
 
@@ -203,28 +206,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================================ TMA producer =========================================
     if (lane == 0) {
       const int wrow0 = (p.w_rows_per_image ? b0[0] * p.w_rows_per_image : 0) + n0;
+      // running stage / tap / channel-block counters (no division on the producer's critical path)
+      int s = 0, tap = 0, cb = 0, ky = p.ntaps == 9 ? 0 : 1, kx = p.ntaps == 9 ? 0 : 1;
+      uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (kb / stages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-        uint8_t* st = smem + s * kStageBytes;
+        const int sb = s;
+        mbar_wait(&empty_bar[sb], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[sb], kStageBytes - ((p.dbg_skip & 1) ? MT * kATileBytes : 0) - ((p.dbg_skip & 2) ? kBTileBytes : 0));
+        uint8_t* st = smem + sb * kStageBytes;
+        if (++s == stages) { s = 0; ph ^= 1; }
         if (kb < num_kb_conv) {
-          const int tap = kb / cin_blocks;
-          const int cb = kb - tap * cin_blocks;
-          const int ky = p.ntaps == 9 ? tap / 3 : 1;
-          const int kx = p.ntaps == 9 ? tap - ky * 3 : 1;
+          if (!(p.dbg_skip & 1)) {
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt)
-            tma_load_4d(st + mt * kATileBytes, &tmA, &full_bar[s], cb * 64, x0[mt] + kx - 1, y0[mt] + ky - 1, b0[mt]);
-          tma_load_2d(st + MT * kATileBytes, &tmB, &full_bar[s], cb * 64, tap * p.Cout + wrow0);
+            for (int mt = 0; mt < MT; ++mt)
+              tma_load_4d(st + mt * kATileBytes, &tmA, &full_bar[sb], cb * 64, x0[mt] + kx - 1, y0[mt] + ky - 1, b0[mt]);
+          }
+          if (!(p.dbg_skip & 2)) tma_load_2d(st + MT * kATileBytes, &tmB, &full_bar[sb], cb * 64, tap * p.Cout + wrow0);
+          if (++cb == cin_blocks) {
+            cb = 0; ++tap;
+            if (p.ntaps == 9 && ++kx == 3) { kx = 0; ++ky; }
+          }
         } else {
           // fused Gram backward: dX += F . D_b  (F = activation of the layer below, D_b = dL/dG of image b)
-          const int cb = kb - num_kb_conv;
+          const int cb2 = kb - num_kb_conv;
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
-            tma_load_4d(st + mt * kATileBytes, &tmA2, &full_bar[s], cb * 64, x0[mt], y0[mt], b0[mt]);
-          tma_load_2d(st + MT * kATileBytes, &tmB2, &full_bar[s], cb * 64, b0[0] * p.Cout + n0);
+            tma_load_4d(st + mt * kATileBytes, &tmA2, &full_bar[sb], cb2 * 64, x0[mt], y0[mt], b0[mt]);
+          tma_load_2d(st + MT * kATileBytes, &tmB2, &full_bar[sb], cb2 * 64, b0[0] * p.Cout + n0);
         }
       }
     }
@@ -239,19 +247,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t a_lo = static_cast<uint32_t>(d0);
       int s = 0;
       uint32_t ph = 0;
+      // An mbarrier probe costs ~150 cycles even when its phase completed long ago; the probe of the NEXT stage is issued
+      // before this stage's MMAs and consumed after them (profiles/r01_umma_issue_probe.txt).
+      bool ready = false;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[s], ph);
+        if (!ready) mbar_wait(&full_bar[s], ph);
         tc_fence_after();
+        const uint32_t a_cur = a_lo;
+        const int s_cur = s;
+        a_lo += kStageBytes >> 4;
+        if (++s == stages) { s = 0; ph ^= 1; a_lo = static_cast<uint32_t>(d0); }
+        ready = (kb + 1 < num_kb) && mbar_try_wait(&full_bar[s], ph);
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // 4 x UMMA_K(16) = 64 channels
-            umma_bf16_lohi(tmem_base + mt * BN, a_lo + ((mt * kATileBytes + k * 32) >> 4), d_hi,
-                           a_lo + ((MT * kATileBytes + k * 32) >> 4), d_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_lohi(tmem_base + mt * BN, a_cur + ((mt * kATileBytes + k * 32) >> 4), d_hi,
+                           a_cur + ((MT * kATileBytes + k * 32) >> 4), d_hi, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
-        a_lo += kStageBytes >> 4;
-        if (++s == stages) { s = 0; ph ^= 1; a_lo = static_cast<uint32_t>(d0); }
+        umma_commit(&empty_bar[s_cur]);  // frees the smem stage once these MMAs have read it
       }
       umma_commit(tmem_full_bar);
     }
@@ -810,6 +824,7 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
     ring_bytes = static_cast<size_t>(stages) * kStageBytes;
   }
   p.stages = stages;
+  p.dbg_skip = g_isx_conv_dbg_skip;
   const size_t smem_bytes = 1024 + ring_bytes + 256;
   ISX_REQUIRE(smem_bytes <= 227 * 1024, "conv_tc: %zu B of shared memory exceed 227 KB", smem_bytes);
 
@@ -889,16 +904,25 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
 // tuning knobs (isx_set_option): default halo mode and the widest Cout it applies to
 int g_isx_halo_mode = 0;
 int g_isx_halo_max_cout = 64;
+int g_isx_conv_dbg_skip = 0;
 int g_isx_persist = 0;  // 1: persistent double-buffered kernel for every tensor-core conv
 // Specialised Cin = 64 kernel (resident weights + halo patch, conv_c64.cu).  0: never; 1 (default): the 64 -> 64 layers
 // when there is at least one tile per SM; 2: every applicable call, including the N = 16 tail and tiny inputs (tests).
 int g_isx_c64 = 1;
+
+// Halo-patch pair kernel (conv_halo.cu).  0: never; 1: layers with enough work items and little padding; 2: every
+// applicable call (tests).
+int g_isx_halo2 = 1;
 
 int conv_tc(const ConvArgs& a_in, cudaStream_t stream) {
   ConvArgs a = a_in;
   if (g_isx_c64 > 0 && a.force_bn == 0 && a.halo_mode == 0 && a.persist == 0 && conv_c64_applicable(a) &&
       (g_isx_c64 >= 2 || (a.dx_nchw == nullptr && static_cast<long>(a.B) * ((a.H + 15) / 16) * ((a.W + 7) / 8) >= kNumSMs)))
     return conv_c64(a, stream);
+  if (g_isx_halo2 > 0 && a.force_bn == 0 && a.halo_mode == 0 && a.persist == 0 && conv_halo_applicable(a)) {
+    const long items = static_cast<long>(a.B) * ((a.H + 15) / 16) * ((a.W + 15) / 16) * (a.Cout / (a.Cout % 128 == 0 ? 128 : 64));
+    if (g_isx_halo2 >= 2 || (items >= 2 * kNumSMs && conv_halo_efficiency(a) >= 0.85)) return conv_halo(a, stream);
+  }
   if (a.halo_mode == 0 && a.force_bn == 0 && g_isx_halo_mode > 0 && a.ntaps == 9 && !a.per_image_weights &&
       a.Cout <= g_isx_halo_max_cout && static_cast<long>(a.B) * ((a.H + 15) / 16) * ((a.W + 7) / 8) >= 2 * kNumSMs)
     a.halo_mode = g_isx_halo_mode;

@@ -35,6 +35,10 @@ struct ConvArgs {
 int conv_tc(const ConvArgs& a, cudaStream_t stream);
 bool conv_c64_applicable(const ConvArgs& a);
 int conv_c64(const ConvArgs& a, cudaStream_t stream);
+// halo-patch kernel for the mid layers (conv_halo.cu)
+bool conv_halo_applicable(const ConvArgs& a);
+double conv_halo_efficiency(const ConvArgs& a);
+int conv_halo(const ConvArgs& a, cudaStream_t stream);
 
 // Gram partial products: partial[b][split][C][C] (fp32) = sum over the split's pixels of F^T F.
 int gram_tc_partial(const __nv_bfloat16* feat, int B, int HW, int C, int splits, float* partial,

@@ -181,6 +181,43 @@ def test_conv_c64_tail(isx, c64_forced, xc, use_mask):
     test_conv1_1_fwd_dgrad(isx, xc, use_mask)
 
 
+# ---- the halo-patch pair kernel (conv_halo.cu): persistent CTAs, 16x16 / 8x32 pixel pairs, streamed weight slabs ------
+HALO_SHAPES = [
+    (2, 20, 24, 64, 64),       # BN = 64, fewer items than SMs
+    (3, 13, 9, 128, 128),      # ragged in x and y; second tile of the pair entirely outside the image
+    (1, 50, 80, 128, 256),     # two Cout tiles
+    (2, 37, 41, 256, 128),     # odd sizes (fused pool drops the last row/column), four input blocks
+    (2, 100, 200, 64, 128),    # 16x16 pairs, several items per CTA: rings and both accumulator sets wrap
+    (3, 160, 100, 128, 64),    # 8x32 pairs (100 = 12.5 x 8), BN = 64
+    (1, 25, 40, 512, 512),
+]
+
+
+@pytest.fixture
+def halo2_forced(isx):
+    lib = isx.load()
+    assert lib.isx_set_option(b"halo2", 2) == 0
+    assert lib.isx_set_option(b"c64", 0) == 0
+    yield
+    assert lib.isx_set_option(b"halo2", 1) == 0
+    assert lib.isx_set_option(b"c64", 1) == 0
+
+
+@pytest.mark.parametrize("shape", HALO_SHAPES)
+def test_conv_halo_fwd_and_pool(isx, halo2_forced, shape):
+    test_conv3x3_fwd(isx, shape, 0)
+    test_conv3x3_fwd_fused_pool(isx, shape, 0)
+
+
+@pytest.mark.parametrize("shape", HALO_SHAPES)
+@pytest.mark.parametrize("mode", ["plain", "mask", "mask_add", "mask_affine", "gram"])
+def test_conv_halo_dgrad(isx, halo2_forced, shape, mode):
+    if mode == "gram":
+        test_conv3x3_dgrad_fused_gram(isx, shape)
+    else:
+        test_conv3x3_dgrad(isx, shape, mode)
+
+
 def test_conv_c64_matches_generic_kernel(isx):
     """Same inputs through the generic tcgen05 kernel and through conv_c64: the MMAs run in the same order
     (tap-major, then the Gram block), so the bf16 results must be identical."""
