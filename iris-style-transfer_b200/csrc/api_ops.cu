@@ -206,6 +206,7 @@ extern int g_isx_conv_dbg_skip;
 extern int g_isx_c64;
 extern int g_isx_c64_slots;
 extern int g_isx_halo2;
+extern int g_isx_tail_n;
 extern int g_isx_halo2_stages;
 }
 extern "C" int isx_set_option(const char* name, int value) {
@@ -215,6 +216,7 @@ extern "C" int isx_set_option(const char* name, int value) {
   if (strcmp(name, "conv_dbg_skip") == 0) { isx::g_isx_conv_dbg_skip = value; return 0; }
   if (strcmp(name, "persist") == 0) { isx::g_isx_persist = value; return 0; }
   if (strcmp(name, "c64") == 0) { isx::g_isx_c64 = value; return 0; }
+  if (strcmp(name, "tail_n") == 0) { isx::g_isx_tail_n = value; return 0; }
   if (strcmp(name, "halo2") == 0) { isx::g_isx_halo2 = value; return 0; }
   if (strcmp(name, "halo2_stages") == 0) { isx::g_isx_halo2_stages = value; return 0; }
   if (strcmp(name, "c64_slots") == 0) { isx::g_isx_c64_slots = value; return 0; }

@@ -914,8 +914,13 @@ int g_isx_c64 = 1;
 // applicable call (tests).
 int g_isx_halo2 = 1;
 
+extern int g_isx_tail_n;
+
 int conv_tc(const ConvArgs& a_in, cudaStream_t stream) {
   ConvArgs a = a_in;
+  if (a.dx_nchw != nullptr && g_isx_tail_n > 0 && g_isx_c64 < 2 && a.force_bn == 0 && a.halo_mode == 0 && a.persist == 0 &&
+      a.Cin == 64 && a.Cout == 16 && a.ntaps == 9)
+    return conv1_1_tail_n(a.in, a.weight, a.in_mask, a.mask_b, a.dx_nchw, a.xc, a.B, a.H, a.W, stream);
   if (g_isx_c64 > 0 && a.force_bn == 0 && a.halo_mode == 0 && a.persist == 0 && conv_c64_applicable(a) &&
       (g_isx_c64 >= 2 || (a.dx_nchw == nullptr && static_cast<long>(a.B) * ((a.H + 15) / 16) * ((a.W + 7) / 8) >= kNumSMs)))
     return conv_c64(a, stream);

@@ -35,6 +35,9 @@ struct ConvArgs {
 int conv_tc(const ConvArgs& a, cudaStream_t stream);
 bool conv_c64_applicable(const ConvArgs& a);
 int conv_c64(const ConvArgs& a, cudaStream_t stream);
+// image-gradient tail with the taps in N (conv1_1_tail.cu)
+int conv1_1_tail_n(const __nv_bfloat16* dy, const __nv_bfloat16* wd, const float* mask, int mask_b, float* dx, int xc,
+                   int B, int H, int W, cudaStream_t stream);
 // halo-patch kernel for the mid layers (conv_halo.cu)
 bool conv_halo_applicable(const ConvArgs& a);
 double conv_halo_efficiency(const ConvArgs& a);

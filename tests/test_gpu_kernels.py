@@ -218,6 +218,37 @@ def test_conv_halo_dgrad(isx, halo2_forced, shape, mode):
         test_conv3x3_dgrad(isx, shape, mode)
 
 
+@pytest.mark.parametrize("xc", [3, 1])
+@pytest.mark.parametrize("use_mask", [False, True])
+def test_conv1_1_generic_tail(isx, xc, use_mask):
+    """The 36-MMA image-gradient tail of the generic kernel (the default is the taps-in-N kernel, conv1_1_tail.cu)."""
+    lib = isx.load()
+    assert lib.isx_set_option(b"tail_n", 0) == 0
+    try:
+        test_conv1_1_fwd_dgrad(isx, xc, use_mask)
+    finally:
+        assert lib.isx_set_option(b"tail_n", 1) == 0
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 14, 14), (2, 15, 29), (3, 100, 57), (2, 200, 320)])
+@pytest.mark.parametrize("xc", [3, 1])
+def test_conv1_1_tail_shapes(isx, B, H, W, xc):
+    """Taps-in-N tail on exact, ragged and multi-patch-per-CTA shapes against autograd of the fp32 convolution."""
+    w = torch.randn(64, 3, 3, 3, device="cuda") * (2.0 / (9 * 64)) ** 0.5
+    mask = (torch.rand(B, 1, H, W, device="cuda") > 0.3).float()
+    dy = nhwc_bf16(B, H, W, 64, 7)
+    wd0 = torch.empty(9, 16, 64, device="cuda", dtype=torch.bfloat16)
+    isx.call("isx_pack_conv1_1_dgrad", w, wd0, isx.stream_ptr())
+    dx = torch.full((B, xc, H, W), float("nan"), device="cuda")
+    isx.call("isx_conv1_1_dgrad_tc", dy, wd0, mask, B, dx, xc, B, H, W, isx.stream_ptr())
+    torch.cuda.synchronize()
+    mean = torch.tensor([0.485, 0.456, 0.406], device="cuda").view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device="cuda").view(1, 3, 1, 1)
+    x = torch.rand(B, xc, H, W, device="cuda", requires_grad=True)
+    F.conv2d((x - mean) / std * mask, w.to(torch.bfloat16).float(), None, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    assert torch.allclose(dx, x.grad, rtol=1e-4, atol=1e-4 * x.grad.abs().max().item())
+
+
 def test_conv_c64_matches_generic_kernel(isx):
     """Same inputs through the generic tcgen05 kernel and through conv_c64: the MMAs run in the same order
     (tap-major, then the Gram block), so the bf16 results must be identical."""
