@@ -413,7 +413,9 @@ def test_masked_gram_eval_matches_oracle(mods):
     # and through the public API
     x, _, ch, sh = _run(mods, c, s, BN_loss=False, s_loss_weight=1e6, epochs=20, c_mask=mask, s_mask=torch.ones(2, 1, H, W),
                         x_hist_stride=0)
-    assert len(sh) == 20 and np.isfinite(sh).all()
+    # 20 evaluations, or up to 19 more when an optimizer.step exits early (lbfgs.py:370-374,463,511-526: this tiny job sits
+    # at the tolerance_grad / tolerance_change thresholds, so the count depends on summation order)
+    assert 20 <= len(sh) < 40 and np.isfinite(sh).all()
 
 
 def test_feature_extraction_matches_oracle(mods):
