@@ -359,7 +359,7 @@ def main():
     conv_n, conv_ms, conv_flops = prof[0], prof[1], prof[2]
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else None
     roofline = {
-        "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv fwd/dgrad/Gram-bwd)", "bound": "tensor",
+        "kernel": "conv family: conv_halo / conv_c64 / conv_tc / conv1_1 head+tail (tcgen05 implicit-GEMM conv fwd/dgrad/Gram-bwd)", "bound": "tensor",
         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if achieved else None,
         # algorithmic DRAM bytes of the 19 conv launches of one evaluation (bf16 NHWC in + out, ReLU-mask and Gram-operand
         # reads of the dgrads): 587 MB per 640x400 image
