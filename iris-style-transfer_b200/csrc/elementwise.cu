@@ -380,20 +380,33 @@ __global__ void __launch_bounds__(256)
 gram_finalize_kernel(const float* __restrict__ partial, int splits, int C, float inv_n, float* __restrict__ G_out,
                      const float* __restrict__ target, int target_b, double loss_scale, double* __restrict__ loss,
                      float grad_scale, __nv_bfloat16* __restrict__ D_out) {
+  // four consecutive Gram entries per thread (C*C is a multiple of 4), grid-stride over the image's C*C/4 quads:
+  // few blocks per image, so the per-image loss takes a handful of double atomics instead of C*C/256
   const int b = blockIdx.y;
   const long cc = static_cast<long>(C) * C;
-  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  const long quads = cc >> 2;
+  const float4* p4 = reinterpret_cast<const float4*>(partial + static_cast<long>(b) * splits * cc);
+  const float4* t4 = target ? reinterpret_cast<const float4*>(target + (target_b > 1 ? b : 0) * cc) : nullptr;
   float d2 = 0.f;
-  if (i < cc) {
-    float acc = 0.f;
-    const float* p = partial + static_cast<long>(b) * splits * cc + i;
-    for (int s = 0; s < splits; ++s) acc += p[s * cc];
-    const float g = acc * inv_n;
-    if (G_out) G_out[b * cc + i] = g;
-    if (target) {
-      const float d = g - target[(target_b > 1 ? b : 0) * cc + i];
-      d2 = d * d;
-      if (D_out) D_out[b * cc + i] = __float2bfloat16_rn(d * grad_scale);
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < quads;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    float4 acc = __ldg(p4 + i);
+    for (int s = 1; s < splits; ++s) {
+      const float4 v = __ldg(p4 + s * quads + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const float4 g = make_float4(acc.x * inv_n, acc.y * inv_n, acc.z * inv_n, acc.w * inv_n);
+    if (G_out) reinterpret_cast<float4*>(G_out + b * cc)[i] = g;
+    if (t4) {
+      const float4 t = __ldg(t4 + i);
+      const float dx = g.x - t.x, dy = g.y - t.y, dz = g.z - t.z, dw = g.w - t.w;
+      d2 = fmaf(dx, dx, d2); d2 = fmaf(dy, dy, d2); d2 = fmaf(dz, dz, d2); d2 = fmaf(dw, dw, d2);
+      if (D_out) {
+        uint2 o;
+        o.x = pack_bf16x2(dx * grad_scale, dy * grad_scale);
+        o.y = pack_bf16x2(dz * grad_scale, dw * grad_scale);
+        reinterpret_cast<uint2*>(D_out + b * cc)[i] = o;
+      }
     }
   }
   if (loss) {
@@ -412,7 +425,11 @@ gram_finalize_kernel(const float* __restrict__ partial, int splits, int C, float
 int gram_finalize(const float* partial, int B, int splits, int C, float inv_n, float* G_out, const float* target,
                   int target_b, double loss_scale, double* loss, float grad_scale, __nv_bfloat16* D_out,
                   cudaStream_t s) {
-  dim3 grid(static_cast<unsigned>((static_cast<long>(C) * C + 255) / 256), B);
+  ISX_REQUIRE(C % 2 == 0, "gram_finalize: C = %d must be even", C);
+  const long quads = static_cast<long>(C) * C / 4;
+  // one quad per thread up to 64 blocks per image, grid-stride beyond (C = 512: 4 quads per thread)
+  const unsigned bx = static_cast<unsigned>(std::max<long>(1, std::min<long>(64, (quads + 255) / 256)));
+  dim3 grid(bx, B);
   gram_finalize_kernel<<<grid, 256, 0, s>>>(partial, splits, C, inv_n, G_out, target, target_b, loss_scale,
                                             target ? loss : nullptr, grad_scale, D_out);
   ISX_LAUNCH_CHECK();
