@@ -249,6 +249,43 @@ def test_conv1_1_tail_shapes(isx, B, H, W, xc):
     assert torch.allclose(dx, x.grad, rtol=1e-4, atol=1e-4 * x.grad.abs().max().item())
 
 
+def test_persistent_conv_kernels_are_deterministic(isx):
+    """conv_halo / conv_c64 / conv1_1_tail with ~10 work items per CTA (every ring, TMEM set and staging slot wraps several
+    times): three runs must agree bit for bit -- a missed barrier shows up as run-to-run noise."""
+    B, H, W = 6, 200, 160
+    outs = []
+    x128 = nhwc_bf16(B, H, W, 128, 21, relu=True)
+    x64 = nhwc_bf16(B, H, W, 64, 22, relu=True)
+    dy = nhwc_bf16(B, H, W, 128, 23)
+    w = torch.randn(128, 128, 3, 3, device="cuda") * 0.03
+    wf, wd = pack(isx, w)
+    w64 = torch.randn(64, 64, 3, 3, device="cuda") * 0.04
+    wf64, wd64 = pack(isx, w64)
+    bias = torch.randn(128, device="cuda") * 0.1
+    D = (torch.randn(B, 128, 128, device="cuda") * 0.05).to(torch.bfloat16)
+    D64 = (torch.randn(B, 64, 64, device="cuda") * 0.05).to(torch.bfloat16)
+    w0 = torch.randn(64, 3, 3, 3, device="cuda") * 0.1
+    wd0 = torch.empty(9, 16, 64, device="cuda", dtype=torch.bfloat16)
+    isx.call("isx_pack_conv1_1_dgrad", w0, wd0, isx.stream_ptr())
+    for rep in range(3):
+        o1 = torch.empty(B, H, W, 128, device="cuda", dtype=torch.bfloat16)
+        p1 = torch.empty(B, H // 2, W // 2, 128, device="cuda", dtype=torch.bfloat16)
+        o2 = torch.empty_like(o1)
+        o3 = torch.empty(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
+        o4 = torch.empty_like(o3)
+        o5 = torch.empty(B, 3, H, W, device="cuda")
+        isx.call("isx_conv3x3_bias_relu_pool_fwd", x128, wf, bias, o1, p1, B, H, W, 128, 128, 0, isx.stream_ptr())
+        isx.call("isx_conv3x3_dgrad_gram", dy, wd, o2, B, H, W, 128, 128, x128, D, isx.stream_ptr())
+        isx.call("isx_conv3x3_bias_relu_fwd", x64, wf64, bias[:64].contiguous(), o3, B, H, W, 64, 64, 1, 0, isx.stream_ptr())
+        isx.call("isx_conv3x3_dgrad_gram", x64, wd64, o4, B, H, W, 64, 64, x64, D64, isx.stream_ptr())
+        isx.call("isx_conv1_1_dgrad_tc", x64, wd0, None, 0, o5, 3, B, H, W, isx.stream_ptr())
+        torch.cuda.synchronize()
+        outs.append((o1, p1, o2, o3, o4, o5))
+    for later in outs[1:]:
+        for a, b in zip(outs[0], later):
+            assert torch.equal(a, b)
+
+
 def test_conv_c64_matches_generic_kernel(isx):
     """Same inputs through the generic tcgen05 kernel and through conv_c64: the MMAs run in the same order
     (tap-major, then the Gram block), so the bf16 results must be identical."""
