@@ -236,8 +236,10 @@ int isx_composite(const float* new_iris, int src_c, int SH, int SW, float* frame
  * stream; after a device sync isx_prof_collect fills out[3*family + {0,1,2}] = {launches, total ms,
  * total algorithmic work (FLOPs for 0/1, bytes for 2)}. */
 unsigned long long isx_launch_count(void);
-/* tuning knobs: "halo_mode" (0 = one TMA box per tap, 1/2 = halo patch + shifted descriptor views for 3x3 convs),
- * "halo_max_cout" (widest Cout the halo variant is used for) */
+/* kernel-selection knobs (tests, experiments; defaults in parentheses): "c64" (1) resident-weight kernel for the 64->64
+ * layers, "halo2" (1) halo-patch pair kernel for the mid layers, "tail_n" (1) taps-in-N image-gradient tail -- 0 sends
+ * the call to the generic kernel, 2 ("c64", "halo2") forces the kernel on every applicable call; "c64_slots",
+ * "halo2_stages": ring depths (0 = as many as fit).  Unknown names return non-zero. */
 int isx_set_option(const char* name, int value);
 int isx_prof_enable(int on);
 int isx_prof_collect(double* out, int n_out);

@@ -11,14 +11,9 @@ static inline cudaStream_t S(isx_stream s) { return reinterpret_cast<cudaStream_
 static inline const bf16* P(const isx_bf16* p) { return reinterpret_cast<const bf16*>(p); }
 static inline bf16* P(isx_bf16* p) { return reinterpret_cast<bf16*>(p); }
 
-// tile_cfg (test / tuning hook): halo*1000000 + BN*100 + MT*10 + stages, 0 = heuristic (e.g. 25623 = BN 256, MT 2, 3 stages)
+// tile_cfg (test / tuning hook): BN*100 + MT*10 + stages forces that tile of the generic kernel (conv_tc.cu);
+// 0 = library heuristic (conv_c64 / conv_halo / generic).  E.g. 25623 = BN 256, MT 2, 3 stages.
 static void decode_tile_cfg(int cfg, ConvArgs* a) {
-  if (cfg >= 1000000) {  // 1, 2: halo variants; 3: persistent kernel; 4: force one tile per CTA
-    const int mode = cfg / 1000000;
-    if (mode <= 2) a->halo_mode = mode;
-    else a->persist = mode == 3 ? 1 : -1;
-    cfg %= 1000000;
-  }
   if (cfg > 0) {
     a->force_bn = cfg / 100;
     a->force_mt = (cfg % 100) / 10;
@@ -199,10 +194,6 @@ extern "C" int isx_tap_add_mask(const isx_bf16* g, const isx_bf16* add, const fl
 }
 
 namespace isx {
-extern int g_isx_halo_mode;
-extern int g_isx_halo_max_cout;
-extern int g_isx_persist;
-extern int g_isx_conv_dbg_skip;
 extern int g_isx_c64;
 extern int g_isx_c64_slots;
 extern int g_isx_halo2;
@@ -211,10 +202,6 @@ extern int g_isx_halo2_stages;
 }
 extern "C" int isx_set_option(const char* name, int value) {
   ISX_REQUIRE(name != nullptr, "isx_set_option: null name");
-  if (strcmp(name, "halo_mode") == 0) { isx::g_isx_halo_mode = value; return 0; }
-  if (strcmp(name, "halo_max_cout") == 0) { isx::g_isx_halo_max_cout = value; return 0; }
-  if (strcmp(name, "conv_dbg_skip") == 0) { isx::g_isx_conv_dbg_skip = value; return 0; }
-  if (strcmp(name, "persist") == 0) { isx::g_isx_persist = value; return 0; }
   if (strcmp(name, "c64") == 0) { isx::g_isx_c64 = value; return 0; }
   if (strcmp(name, "tail_n") == 0) { isx::g_isx_tail_n = value; return 0; }
   if (strcmp(name, "halo2") == 0) { isx::g_isx_halo2 = value; return 0; }

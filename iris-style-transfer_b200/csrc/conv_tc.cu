@@ -29,12 +29,8 @@ struct ConvParams {
   int tiles_x, tiles_y, tiles_b;
   int n_tiles;               // Cout / BN
   int w_rows_per_image;      // 0, or Cout when every image has its own [Cout x Cin] matrix (Gram bwd)
-  long total_items;          // persistent kernel: (pixel super-tiles) x (Cout tiles)
-  int a_stages;              // halo mode: number of halo slots (1 or 2)
-  int halo_base_offset;      // halo mode: put the swizzle phase (kx) into the descriptor's base-offset field
   int extra_kb;              // fused Gram backward: extra K blocks (C/64) of  act(centre tap) x D_b  after the taps
   int stages;
-  int dbg_skip;              // experiment only (isx_set_option("conv_dbg_skip")): 1 = no A loads, 2 = no B loads (results garbage)
   int relu;
   const float* bias;         // [Cout] or null
   const __nv_bfloat16* mask_act;  // [B,H,W,Cout] or null: out = act > 0 ? out : 0
@@ -49,21 +45,11 @@ struct ConvParams {
   int mask_b;
 };
 
-extern int g_isx_conv_dbg_skip;
-
 static constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
 
-static constexpr int kHaloBytes = 18 * 16 * 128;  // (16+2) rows x 16 pixel slots x 64 bf16: halo patch of an 8x16 tile
-
-// HALO = true -- EXPERIMENTAL, off by default (isx_set_option("halo_mode", 2)): correct (the UMMA swizzle is a pure
-// function of the shared-memory address, so shifted descriptor starts need no base-offset) but measured ~30 % slower
-// than one TMA box per tap because every tap waits on its own small weight slab.  (3x3 only, one 8 x 16 pixel tile per CTA): the input patch of a 64-channel chunk is loaded ONCE with
-// its halo ([18][16] pixel slots, pitch 2048 B) and the nine taps are nine shifted views of it -- the A descriptor
-// simply starts at row (ky*16 + kx) with SBO = 2048 B and swizzle phase kx -- so L2->SM traffic per chunk drops
-// from 9 x 16 KB to 36 KB; only the weight slabs stream per tap (their own smem ring).
 static constexpr int kConvThreads = 64 + 256;  // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant)
 
-template <int BN, int MT, int EPI, bool HALO = false>
+template <int BN, int MT, int EPI>
 __global__ void __launch_bounds__(kConvThreads, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmM,
@@ -74,16 +60,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int kTmemCols = (MT * BN) <= 32 ? 32 : (MT * BN) <= 64 ? 64 : (MT * BN) <= 128 ? 128 : (MT * BN) <= 256 ? 256 : 512;
   static_assert(MT * BN <= 512, "accumulators exceed TMEM");
 
-  static_assert(!HALO || MT == 1, "halo mode handles one M-tile per CTA");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int stages = p.stages;  // HALO: stages of the weight-slab ring; p.a_stages halo slots precede it
-  const int ring_bytes = HALO ? p.a_stages * kHaloBytes + stages * kBTileBytes : stages * kStageBytes;
+  const int stages = p.stages;
+  const int ring_bytes = stages * kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + ring_bytes);
   uint64_t* empty_bar = full_bar + stages;
-  uint64_t* a_full_bar = empty_bar + stages;   // [2] halo slots (HALO only)
-  uint64_t* a_empty_bar = a_full_bar + 2;      // [2]
-  uint64_t* tmem_full_bar = a_empty_bar + 2;
+  uint64_t* tmem_full_bar = empty_bar + stages;
   uint64_t* epi_bar = tmem_full_bar + 1;  // [2]: TMA loads of the ReLU-mask activation tile for the epilogue
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(epi_bar + 2);
 
@@ -121,10 +104,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(tmem_full_bar, 1);
     mbar_init(&epi_bar[0], 1);
     mbar_init(&epi_bar[1], 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&a_full_bar[s], 1);
-      mbar_init(&a_empty_bar[s], 1);
-    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr_smem);
@@ -137,72 +116,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_kb_conv = p.ntaps * cin_blocks;
   const int num_kb = num_kb_conv + p.extra_kb;
 
-  if (HALO && warp == 0) {
-    // ================================ TMA producer (halo mode) ===============================
-    if (lane == 0) {
-      uint8_t* bring = smem + p.a_stages * kHaloBytes;
-      int bk = 0;  // running weight-slab index
-      for (int c = 0; c < cin_blocks + p.extra_kb; ++c) {
-        const int as = c % p.a_stages;
-        const uint32_t aph = (c / p.a_stages) & 1;
-        mbar_wait(&a_empty_bar[as], aph ^ 1);
-        if (c < cin_blocks) {
-          mbar_arrive_expect_tx(&a_full_bar[as], kHaloBytes);
-          tma_load_4d(smem + as * kHaloBytes, &tmA, &a_full_bar[as], c * 64, x0[0] - 1, y0[0] - 1, b0[0]);
-        } else {  // fused Gram backward: a plain 128-row tile of the activation below (no halo)
-          mbar_arrive_expect_tx(&a_full_bar[as], kATileBytes);
-          tma_load_4d(smem + as * kHaloBytes, &tmA2, &a_full_bar[as], (c - cin_blocks) * 64, x0[0], y0[0], b0[0]);
-        }
-        const int ntap = c < cin_blocks ? 9 : 1;
-        for (int tap = 0; tap < ntap; ++tap, ++bk) {
-          const int s = bk % stages;
-          const uint32_t ph = (bk / stages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], kBTileBytes);
-          if (c < cin_blocks) tma_load_2d(bring + s * kBTileBytes, &tmB, &full_bar[s], c * 64, tap * p.Cout + n0);
-          else tma_load_2d(bring + s * kBTileBytes, &tmB2, &full_bar[s], (c - cin_blocks) * 64, b0[0] * p.Cout + n0);
-        }
-      }
-    }
-  } else if (HALO && warp == 1) {
-    // ================================ MMA issuer (halo mode) =================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, false, false);
-      const uint32_t bring = smem_u32(smem + p.a_stages * kHaloBytes);
-      int bk = 0;
-      uint32_t first = 1;
-      for (int c = 0; c < cin_blocks + p.extra_kb; ++c) {
-        const int as = c % p.a_stages;
-        mbar_wait(&a_full_bar[as], (c / p.a_stages) & 1);
-        const uint32_t a_base = smem_u32(smem + as * kHaloBytes);
-        const int ntap = c < cin_blocks ? 9 : 1;
-        for (int tap = 0; tap < ntap; ++tap, ++bk) {
-          const int s = bk % stages;
-          mbar_wait(&full_bar[s], (bk / stages) & 1);
-          tc_fence_after();
-          const uint32_t b_addr = bring + s * kBTileBytes;
-          uint32_t a_addr, sbo, phase;
-          if (c < cin_blocks) {
-            const int ky = tap / 3, kx = tap - ky * 3;
-            a_addr = a_base + (ky * 16 + kx) * 128;  // shifted view of the halo patch
-            sbo = 2048;
-            phase = p.halo_base_offset ? static_cast<uint32_t>(kx) : 0u;
-          } else {
-            a_addr = a_base; sbo = 1024; phase = 0;
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_bf16(tmem_base, umma_desc_sw128(a_addr + k * 32, 16, sbo, phase), umma_desc_sw128(b_addr + k * 32, 16, 1024),
-                      idesc, first ? 0u : 1u);
-            first = 0;
-          }
-          umma_commit(&empty_bar[s]);
-        }
-        umma_commit(&a_empty_bar[as]);
-      }
-      umma_commit(tmem_full_bar);
-    }
-  } else if (!HALO && warp == 0) {
+  if (warp == 0) {
     // ================================ TMA producer =========================================
     if (lane == 0) {
       const int wrow0 = (p.w_rows_per_image ? b0[0] * p.w_rows_per_image : 0) + n0;
@@ -212,16 +126,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = 0; kb < num_kb; ++kb) {
         const int sb = s;
         mbar_wait(&empty_bar[sb], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[sb], kStageBytes - ((p.dbg_skip & 1) ? MT * kATileBytes : 0) - ((p.dbg_skip & 2) ? kBTileBytes : 0));
+        mbar_arrive_expect_tx(&full_bar[sb], kStageBytes);
         uint8_t* st = smem + sb * kStageBytes;
         if (++s == stages) { s = 0; ph ^= 1; }
         if (kb < num_kb_conv) {
-          if (!(p.dbg_skip & 1)) {
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-              tma_load_4d(st + mt * kATileBytes, &tmA, &full_bar[sb], cb * 64, x0[mt] + kx - 1, y0[mt] + ky - 1, b0[mt]);
-          }
-          if (!(p.dbg_skip & 2)) tma_load_2d(st + MT * kATileBytes, &tmB, &full_bar[sb], cb * 64, tap * p.Cout + wrow0);
+          for (int mt = 0; mt < MT; ++mt)
+            tma_load_4d(st + mt * kATileBytes, &tmA, &full_bar[sb], cb * 64, x0[mt] + kx - 1, y0[mt] + ky - 1, b0[mt]);
+          tma_load_2d(st + MT * kATileBytes, &tmB, &full_bar[sb], cb * 64, tap * p.Cout + wrow0);
           if (++cb == cin_blocks) {
             cb = 0; ++tap;
             if (p.ntaps == 9 && ++kx == 3) { kx = 0; ++ky; }
@@ -236,7 +148,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (!HALO && warp == 1) {
+  } else if (warp == 1) {
     // ================================ MMA issuer ===========================================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, false, false);
@@ -444,314 +356,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-// =============================================================================================
-// EXPERIMENTAL (off by default, isx_set_option("persist", 1)): measured on B200 it is NOT faster than the
-// one-tile-per-CTA kernel above with two co-resident CTAs per SM (profiles/r01_README.md): the N = 64 layers are
-// bound by shared-memory bandwidth (TMA writes + UMMA operand reads), not by per-CTA prologue latency.
-// Persistent variant: one CTA per SM walks a static round-robin list of (pixel super-tile, Cout tile) work
-// items.  The TMA/MMA pipeline (stage ring + phases) runs straight through item boundaries and the fp32
-// accumulators are double-buffered in TMEM, so the producer prefetches the next item and the tensor core
-// starts on it while the four epilogue warps drain the previous one (TMEM -> bias/ReLU/mask -> bf16 ->
-// staging -> TMA store).  Per-CTA prologue cost (barrier init, TMEM alloc, descriptor fetch, first TMA round
-// trip) is paid once per SM instead of once per 128 x BN tile.
-// =============================================================================================
-template <int BN, int MT, int EPI>
-__global__ void __launch_bounds__(192, 1)
-conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmM,
-                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const ConvParams p) {
-  constexpr int kBTileBytes = BN * 128;
-  constexpr int kStageBytes = MT * kATileBytes + kBTileBytes;
-  constexpr int kAccCols = MT * BN < 32 ? 32 : MT * BN;  // columns of one accumulator set
-  constexpr int kTmemCols = 2 * kAccCols <= 32 ? 32 : 2 * kAccCols <= 64 ? 64 : 2 * kAccCols <= 128 ? 128 : 2 * kAccCols <= 256 ? 256 : 512;
-  static_assert(2 * kAccCols <= 512, "double-buffered accumulators exceed TMEM");
-  constexpr int NGT = MT * (BN / 64);  // 64-channel output groups per work item
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int stages = p.stages;
-  uint8_t* staging = smem + stages * kStageBytes;           // 2 x 16 KB output staging (EPI == 0)
-  uint8_t* scratch = staging + 2 * kATileBytes;             // 2 x 16 KB ReLU-mask tiles   (EPI == 0)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * kStageBytes + (EPI == 0 ? 4 * kATileBytes : 0));
-  uint64_t* empty_bar = full_bar + stages;
-  uint64_t* tmem_full_bar = empty_bar + stages;   // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint64_t* epi_bar = tmem_empty_bar + 2;         // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(epi_bar + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    if (EPI == 0) tma_prefetch_desc(&tmO);
-    if (EPI == 0 && p.mask_act != nullptr) tma_prefetch_desc(&tmM);
-    if (p.extra_kb > 0) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
-    for (int s = 0; s < stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4);  // one arrival per epilogue warp
-      mbar_init(&epi_bar[i], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr_smem);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-
-  const int cin_blocks = p.Cin >> 6;
-  const int num_kb_conv = p.ntaps * cin_blocks;
-  const int num_kb = num_kb_conv + p.extra_kb;
-  const long total_items = p.total_items;
-
-  // work item -> tile coordinates
-  auto coords = [&](long w, int& n0, int (&x0)[MT], int (&y0)[MT], int (&b0)[MT]) {
-    const int n_tile = static_cast<int>(w % p.n_tiles);
-    const long sp_super = w / p.n_tiles;
-    n0 = n_tile * BN;
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      const long t = sp_super * MT + mt;
-      const int tx = static_cast<int>(t % p.tiles_x);
-      const long r = t / p.tiles_x;
-      const int ty = static_cast<int>(r % p.tiles_y);
-      const int tb = static_cast<int>(r / p.tiles_y);
-      x0[mt] = tx * p.TW; y0[mt] = ty * p.TH; b0[mt] = tb * p.TB;
-    }
-  };
-
-  if (warp == 0) {
-    // ================================ TMA producer =========================================
-    if (lane == 0) {
-      uint32_t kbg = 0;
-      for (long w = blockIdx.x; w < total_items; w += gridDim.x) {
-        int n0, x0[MT], y0[MT], b0[MT];
-        coords(w, n0, x0, y0, b0);
-        const int wrow0 = (p.w_rows_per_image ? b0[0] * p.w_rows_per_image : 0) + n0;
-        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
-          const int s = kbg % stages;
-          const uint32_t ph = (kbg / stages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-          uint8_t* st = smem + s * kStageBytes;
-          if (kb < num_kb_conv) {
-            const int tap = kb / cin_blocks;
-            const int cb = kb - tap * cin_blocks;
-            const int ky = p.ntaps == 9 ? tap / 3 : 1;
-            const int kx = p.ntaps == 9 ? tap - ky * 3 : 1;
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-              tma_load_4d(st + mt * kATileBytes, &tmA, &full_bar[s], cb * 64, x0[mt] + kx - 1, y0[mt] + ky - 1, b0[mt]);
-            tma_load_2d(st + MT * kATileBytes, &tmB, &full_bar[s], cb * 64, tap * p.Cout + wrow0);
-          } else {
-            const int cb = kb - num_kb_conv;
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-              tma_load_4d(st + mt * kATileBytes, &tmA2, &full_bar[s], cb * 64, x0[mt], y0[mt], b0[mt]);
-            tma_load_2d(st + MT * kATileBytes, &tmB2, &full_bar[s], cb * 64, b0[0] * p.Cout + n0);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ===========================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, false, false);
-      uint32_t kbg = 0, it = 0;
-      for (long w = blockIdx.x; w < total_items; w += gridDim.x, ++it) {
-        const uint32_t acc = it & 1;
-        mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator set
-        tc_fence_after();
-        const uint32_t d_base = tmem_base + acc * kAccCols;
-        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
-          const int s = kbg % stages;
-          const uint32_t ph = (kbg / stages) & 1;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
-          const uint32_t b_addr = a_addr + MT * kATileBytes;
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t da = umma_desc_sw128(a_addr + mt * kATileBytes + k * 32, 16, 1024);
-              const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-              umma_bf16(d_base + mt * BN, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-            }
-          }
-          umma_commit(&empty_bar[s]);
-        }
-        umma_commit(&tmem_full_bar[acc]);
-      }
-    }
-  } else {
-    // ================================ epilogue =============================================
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int tw = row % p.TW;
-    const int th = (row / p.TW) % p.TH;
-    const int tb = row / (p.TW * p.TH);
-    const bool use_mask = EPI == 0 && p.mask_act != nullptr;
-    uint32_t it = 0, gc = 0;  // item counter, global 64-channel group counter (staging / mask rings)
-    for (long w = blockIdx.x; w < total_items; w += gridDim.x, ++it) {
-      int n0, x0[MT], y0[MT], b0[MT];
-      coords(w, n0, x0, y0, b0);
-      const uint32_t acc = it & 1;
-      const uint32_t d_base = tmem_base + acc * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
-      if constexpr (EPI == 1) {
-        mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
-        tc_fence_after();
-#pragma unroll 1
-        for (int mt = 0; mt < MT; ++mt) {
-          const int x = x0[mt] + tw, y = y0[mt] + th, b = b0[mt] + tb;
-          const bool valid = (x < p.W) && (y < p.H) && (b < p.B);
-          uint32_t v[16];
-          tmem_ld_32x16(d_base + mt * BN, v);
-          tmem_ld_wait();
-          if (valid) {
-            const size_t hw = static_cast<size_t>(p.H) * p.W;
-            const size_t off = static_cast<size_t>(y) * p.W + x;
-            float m = 1.f;
-            if (p.in_mask != nullptr) m = __ldg(p.in_mask + (p.mask_b > 1 ? b : 0) * hw + off);
-            const float a0 = __uint_as_float(v[0]) * m / 0.229f;
-            const float a1 = __uint_as_float(v[1]) * m / 0.224f;
-            const float a2 = __uint_as_float(v[2]) * m / 0.225f;
-            if (p.xc == 3) {
-              float* o = p.dx_nchw + static_cast<size_t>(b) * 3 * hw + off;
-              o[0] = a0; o[hw] = a1; o[2 * hw] = a2;
-            } else {
-              p.dx_nchw[static_cast<size_t>(b) * hw + off] = a0 + a1 + a2;
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-      } else {
-        const uint32_t gc0 = gc;  // group counter at the start of this item
-        auto issue_mask_load = [&](int gi) {  // gi: group index inside this item
-          const uint32_t slot = (gc0 + gi) & 1;
-          const int mt_ = gi / (BN / 64), g_ = gi % (BN / 64);
-          mbar_arrive_expect_tx(&epi_bar[slot], kATileBytes);
-          tma_load_4d(scratch + slot * kATileBytes, &tmM, &epi_bar[slot], n0 + g_ * 64, x0[mt_], y0[mt_], b0[mt_]);
-        };
-        if (use_mask && threadIdx.x == 64) {
-          issue_mask_load(0);
-          if (NGT > 1) issue_mask_load(1);
-        }
-        mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
-        tc_fence_after();
-#pragma unroll 1
-        for (int mt = 0; mt < MT; ++mt) {
-          const int x = x0[mt] + tw, y = y0[mt] + th, b = b0[mt] + tb;
-          const bool valid = (x < p.W) && (y < p.H) && (b < p.B);
-          const size_t pix = valid ? ((static_cast<size_t>(b) * p.H + y) * p.W + x) * p.Cout : 0;
-#pragma unroll 1
-          for (int g = 0; g < BN / 64; ++g, ++gc) {
-            const int gi = mt * (BN / 64) + g;
-            const uint32_t slot = gc & 1;
-            uint8_t* stg = staging + slot * kATileBytes;
-            const uint8_t* mrow = scratch + slot * kATileBytes + row * 128;
-            if (use_mask) mbar_wait(&epi_bar[slot], (gc >> 1) & 1);
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-              const int nloc = g * 64 + h * 32;
-              uint32_t v[32];
-              tmem_ld_32x32(d_base + mt * BN + nloc, v);
-              tmem_ld_wait();
-              float f[32];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-              const int n = n0 + nloc;
-              if (p.bias != nullptr) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
-                  f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
-                }
-              }
-              if (p.add_buf != nullptr && valid) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.add_buf + pix + n + i));
-                  float2 t;
-                  t = unpack_bf16x2(u.x); f[i] += t.x; f[i + 1] += t.y;
-                  t = unpack_bf16x2(u.y); f[i + 2] += t.x; f[i + 3] += t.y;
-                  t = unpack_bf16x2(u.z); f[i + 4] += t.x; f[i + 5] += t.y;
-                  t = unpack_bf16x2(u.w); f[i + 6] += t.x; f[i + 7] += t.y;
-                }
-              }
-              if (use_mask) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                  const int chunk = (h * 4 + (i >> 3)) ^ (row & 7);
-                  const uint4 u = *reinterpret_cast<const uint4*>(mrow + chunk * 16);
-                  float a[8];
-                  float2 t;
-                  t = unpack_bf16x2(u.x); a[0] = t.x; a[1] = t.y;
-                  t = unpack_bf16x2(u.y); a[2] = t.x; a[3] = t.y;
-                  t = unpack_bf16x2(u.z); a[4] = t.x; a[5] = t.y;
-                  t = unpack_bf16x2(u.w); a[6] = t.x; a[7] = t.y;
-                  if (p.aff_a != nullptr && valid) {
-                    const float* pa = p.aff_a + static_cast<size_t>(b) * p.Cout + n + i;
-                    const float* pb = p.aff_b + static_cast<size_t>(b) * p.Cout + n + i;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) f[i + j] += __ldg(pa + j) + __ldg(pb + j) * a[j];
-                  }
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[i + j] = a[j] > 0.f ? f[i + j] : 0.f;
-                }
-              }
-              if (p.relu) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-              }
-              uint8_t* rowp = stg + row * 128;
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                uint4 o;
-                o.x = pack_bf16x2(f[c * 8 + 0], f[c * 8 + 1]);
-                o.y = pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]);
-                o.z = pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]);
-                o.w = pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]);
-                const int chunk = (h * 4 + c) ^ (row & 7);
-                *reinterpret_cast<uint4*>(rowp + chunk * 16) = o;
-              }
-            }
-            if (gi == NGT - 1) {  // last TMEM read of this item: hand the accumulator set back to the MMA warp
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-            }
-            fence_proxy_async_smem();
-            // the other staging slot is re-used by the next group: its TMA store must have finished reading
-            if (threadIdx.x == 64) tma_store_wait_read<0>();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (threadIdx.x == 64) {
-              tma_store_4d(&tmO, stg, n0 + g * 64, x0[mt], y0[mt], b0[mt]);
-              tma_store_commit();
-              if (use_mask && gi + 2 < NGT) issue_mask_load(gi + 2);
-            }
-          }
-        }
-      }
-    }
-    if (EPI == 0 && threadIdx.x == 64) tma_store_wait_all<0>();
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
-  }
-}
-
 // Pick the 128-pixel patch shape (TW x TH x TB) with the least padding; ties -> wider rows.
 static void choose_patch(int B, int H, int W, bool one_image_per_tile, int* TW, int* TH, int* TB) {
   long best = -1;
@@ -769,15 +373,13 @@ static void choose_patch(int B, int H, int W, bool one_image_per_tile, int* TW, 
   }
 }
 
-template <int BN, int MT, int EPI = 0, bool HALO = false, bool PERSIST = false>
+template <int BN, int MT, int EPI = 0>
 static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stream) {
-  static_assert(!(HALO && PERSIST), "halo and persistent modes are separate kernels");
   ConvParams p;
   memset(&p, 0, sizeof(p));
   p.B = a.B; p.H = a.H; p.W = a.W; p.Cin = a.Cin; p.Cout = a.Cout; p.ntaps = a.ntaps;
   const bool per_image = a.per_image_weights || a.gram_act != nullptr;
-  if (HALO) { p.TW = 8; p.TH = 16; p.TB = 1; }
-  else choose_patch(a.B, a.H, a.W, per_image, &p.TW, &p.TH, &p.TB);
+  choose_patch(a.B, a.H, a.W, per_image, &p.TW, &p.TH, &p.TB);
   p.tiles_x = (a.W + p.TW - 1) / p.TW;
   p.tiles_y = (a.H + p.TH - 1) / p.TH;
   p.tiles_b = (a.B + p.TB - 1) / p.TB;
@@ -792,39 +394,18 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
 
   constexpr int kStageBytes = MT * kATileBytes + BN * 128;
   // epilogue staging (one 16 KB tile per 64-channel group) + 2 mask-tile slots alias the drained pipeline
-  const bool fuse_pool = !PERSIST && !HALO && EPI == 0 && a.pool_out != nullptr && p.TW % 2 == 0 && p.TH % 2 == 0 &&
+  const bool fuse_pool = EPI == 0 && a.pool_out != nullptr && p.TW % 2 == 0 && p.TH % 2 == 0 &&
                          a.H >= 2 && a.W >= 2;
   p.fuse_pool = fuse_pool ? 1 : 0;
   const int epi_bytes = (MT * (BN / 64) + (a.mask_act ? 2 : 0)) * kATileBytes + (fuse_pool ? MT * (BN / 64) * 4096 : 0);
   int stages;
   size_t ring_bytes;
-  if (PERSIST) {
-    // one CTA per SM: [stage ring][2 x 16 KB staging + 2 x 16 KB mask tiles (EPI 0)][barriers]
-    const int epi_fixed = EPI == 0 ? 4 * kATileBytes : 0;
-    const int avail = 227 * 1024 - 1024 - 512 - epi_fixed;
-    stages = stages_override > 0 ? stages_override : avail / kStageBytes;
-    if (stages > 8) stages = 8;
-    ISX_REQUIRE(stages >= 2, "conv_tc: persistent tile BN=%d MT=%d does not fit", BN, MT);
-    ring_bytes = static_cast<size_t>(stages) * kStageBytes + epi_fixed;
-  } else if (HALO) {
-    ISX_REQUIRE(a.ntaps == 9 && !a.per_image_weights, "conv_tc: halo mode is for 3x3 convolutions");
-    p.a_stages = (a.Cin / 64 + (a.gram_act ? a.Cout / 64 : 0)) > 1 ? 2 : 1;
-    p.halo_base_offset = a.halo_mode == 2 ? 0 : 1;
-    const int budget = 104 * 1024 - p.a_stages * kHaloBytes;  // two CTAs per SM
-    stages = stages_override > 0 ? stages_override : budget / (BN * 128);
-    if (stages > 8) stages = 8;
-    if (stages < 2) stages = 2;
-    while (p.a_stages * kHaloBytes + stages * BN * 128 < epi_bytes) ++stages;
-    ring_bytes = static_cast<size_t>(p.a_stages) * kHaloBytes + static_cast<size_t>(stages) * BN * 128;
-  } else {
-    stages = stages_override > 0 ? stages_override : (200 * 1024) / kStageBytes;
-    if (stages > 8) stages = 8;
-    if (stages < 2) stages = 2;
-    while (stages * kStageBytes < epi_bytes) ++stages;
-    ring_bytes = static_cast<size_t>(stages) * kStageBytes;
-  }
+  stages = stages_override > 0 ? stages_override : (200 * 1024) / kStageBytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  while (stages * kStageBytes < epi_bytes) ++stages;
+  ring_bytes = static_cast<size_t>(stages) * kStageBytes;
   p.stages = stages;
-  p.dbg_skip = g_isx_conv_dbg_skip;
   const size_t smem_bytes = 1024 + ring_bytes + 256;
   ISX_REQUIRE(smem_bytes <= 227 * 1024, "conv_tc: %zu B of shared memory exceed 227 KB", smem_bytes);
 
@@ -833,7 +414,6 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
     uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
     uint64_t str[3] = {(uint64_t)a.Cin * 2, (uint64_t)a.W * a.Cin * 2, (uint64_t)a.H * a.W * a.Cin * 2};
     uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
-    if (HALO) { box[1] = 16; box[2] = 18; }  // halo patch: 16 pixel slots (10 used) x 18 rows
     if (isx_make_tmap_bf16(&tmA, a.in, 4, dims, str, box, true)) return 3;
   }
   {
@@ -876,19 +456,7 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
   }
   const long sp_tiles = static_cast<long>(p.tiles_x) * p.tiles_y * p.tiles_b;
   long grid = ((sp_tiles + MT - 1) / MT) * p.n_tiles;
-  p.total_items = grid;
-  if constexpr (PERSIST) {
-    auto kernp = conv_tcp_kernel<BN, MT, EPI>;
-    ISX_CHECK_CUDA(cudaFuncSetAttribute(kernp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    if (grid > kNumSMs) grid = kNumSMs;
-    isx_prof_begin(ISX_PROF_CONV,
-                   2.0 * (a.ntaps * a.Cin + (a.gram_act ? a.Cout : 0)) * a.Cout * static_cast<double>(a.B) * a.H * a.W, stream);
-    kernp<<<(unsigned)grid, 192, smem_bytes, stream>>>(tmA, tmB, tmO, tmM, tmA2, tmB2, p);
-    isx_prof_end(ISX_PROF_CONV, stream);
-    ISX_LAUNCH_CHECK();
-    return 0;
-  } else {
-  auto kern = conv_tc_kernel<BN, MT, EPI, HALO>;
+  auto kern = conv_tc_kernel<BN, MT, EPI>;
   ISX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   isx_prof_begin(ISX_PROF_CONV,
                  2.0 * (a.ntaps * a.Cin + (a.gram_act ? a.Cout : 0)) * a.Cout * static_cast<double>(a.B) * a.H * a.W, stream);
@@ -898,14 +466,9 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
   if (a.pool_out != nullptr && !fuse_pool)  // patch shape not poolable in the epilogue: separate kernel
     return maxpool_fwd(a.out, a.pool_out, a.B, a.H, a.W, a.Cout, stream);
   return 0;
-  }
 }
 
-// tuning knobs (isx_set_option): default halo mode and the widest Cout it applies to
-int g_isx_halo_mode = 0;
-int g_isx_halo_max_cout = 64;
-int g_isx_conv_dbg_skip = 0;
-int g_isx_persist = 0;  // 1: persistent double-buffered kernel for every tensor-core conv
+// tuning knobs (isx_set_option)
 // Specialised Cin = 64 kernel (resident weights + halo patch, conv_c64.cu).  0: never; 1 (default): the 64 -> 64 layers
 // when there is at least one tile per SM; 2: every applicable call, including the N = 16 tail and tiny inputs (tests).
 int g_isx_c64 = 1;
@@ -918,25 +481,20 @@ extern int g_isx_tail_n;
 
 int conv_tc(const ConvArgs& a_in, cudaStream_t stream) {
   ConvArgs a = a_in;
-  if (a.dx_nchw != nullptr && g_isx_tail_n > 0 && g_isx_c64 < 2 && a.force_bn == 0 && a.halo_mode == 0 && a.persist == 0 &&
+  if (a.dx_nchw != nullptr && g_isx_tail_n > 0 && g_isx_c64 < 2 && a.force_bn == 0 &&
       a.Cin == 64 && a.Cout == 16 && a.ntaps == 9)
     return conv1_1_tail_n(a.in, a.weight, a.in_mask, a.mask_b, a.dx_nchw, a.xc, a.B, a.H, a.W, stream);
-  if (g_isx_c64 > 0 && a.force_bn == 0 && a.halo_mode == 0 && a.persist == 0 && conv_c64_applicable(a) &&
+  if (g_isx_c64 > 0 && a.force_bn == 0 && conv_c64_applicable(a) &&
       (g_isx_c64 >= 2 || (a.dx_nchw == nullptr && static_cast<long>(a.B) * ((a.H + 15) / 16) * ((a.W + 7) / 8) >= kNumSMs)))
     return conv_c64(a, stream);
-  if (g_isx_halo2 > 0 && a.force_bn == 0 && a.halo_mode == 0 && a.persist == 0 && conv_halo_applicable(a)) {
+  if (g_isx_halo2 > 0 && a.force_bn == 0 && conv_halo_applicable(a)) {
     const long items = static_cast<long>(a.B) * ((a.H + 15) / 16) * ((a.W + 15) / 16) * (a.Cout / (a.Cout % 128 == 0 ? 128 : 64));
     if (g_isx_halo2 >= 2 || (items >= 2 * kNumSMs && conv_halo_efficiency(a) >= 0.85)) return conv_halo(a, stream);
   }
-  if (a.halo_mode == 0 && a.force_bn == 0 && g_isx_halo_mode > 0 && a.ntaps == 9 && !a.per_image_weights &&
-      a.Cout <= g_isx_halo_max_cout && static_cast<long>(a.B) * ((a.H + 15) / 16) * ((a.W + 7) / 8) >= 2 * kNumSMs)
-    a.halo_mode = g_isx_halo_mode;
   if (a.dx_nchw != nullptr) {  // conv1_1 dgrad tail: N = 16 (3 real output channels), fp32 NCHW epilogue
     ISX_REQUIRE(a.Cin == 64 && a.Cout == 16 && a.ntaps == 9, "conv_tc: image-gradient mode needs Cin 64, Cout 16 (padded)");
     ISX_REQUIRE(a.xc == 1 || a.xc == 3, "conv_tc: xc must be 1 or 3");
     const long pix_tiles = (static_cast<long>(a.B) * a.H * a.W + 127) / 128;
-    if (a.halo_mode > 0) return launch_conv<16, 1, 1, true>(a, a.force_stages, stream);
-    if (a.persist > 0 || (a.persist == 0 && g_isx_persist > 0)) return launch_conv<16, 2, 1, false, true>(a, a.force_stages, stream);
     if (a.force_mt == 1 || pix_tiles < 4 * kNumSMs) return launch_conv<16, 1, 1>(a, a.force_stages ? a.force_stages : 3, stream);
     return launch_conv<16, 2, 1>(a, a.force_stages ? a.force_stages : 2, stream);
   }
@@ -968,22 +526,6 @@ int conv_tc(const ConvArgs& a_in, cudaStream_t stream) {
     }
   }
   if (mt == 0) mt = 1;
-  if (a.halo_mode > 0) {
-    if (bn == 64) return launch_conv<64, 1, 0, true>(a, st == 2 && a.force_bn == 0 ? 0 : st, stream);
-    if (bn == 128) return launch_conv<128, 1, 0, true>(a, st == 2 && a.force_bn == 0 ? 0 : st, stream);
-    if (bn == 256) return launch_conv<256, 1, 0, true>(a, st == 2 && a.force_bn == 0 ? 0 : st, stream);
-  }
-  if (a.persist > 0 || (a.persist == 0 && g_isx_persist > 0)) {
-    const int pst = a.force_bn ? a.force_stages : 0;
-    if (a.per_image_weights || (a.gram_act != nullptr && mt == 1)) {
-      if (bn == 64) return launch_conv<64, 1, 0, false, true>(a, pst, stream);
-      if (bn == 128) return launch_conv<128, 1, 0, false, true>(a, pst, stream);
-      return launch_conv<256, 1, 0, false, true>(a, pst, stream);
-    }
-    if (bn == 64) return mt == 2 ? launch_conv<64, 2, 0, false, true>(a, pst, stream) : launch_conv<64, 1, 0, false, true>(a, pst, stream);
-    if (bn == 128) return mt == 2 ? launch_conv<128, 2, 0, false, true>(a, pst, stream) : launch_conv<128, 1, 0, false, true>(a, pst, stream);
-    if (bn == 256) return launch_conv<256, 1, 0, false, true>(a, pst, stream);
-  }
 #define ISX_CONV_CASE(BN_, MT_) \
   if (bn == BN_ && mt == MT_) return launch_conv<BN_, MT_>(a, st, stream);
   ISX_CONV_CASE(64, 1) ISX_CONV_CASE(64, 2) ISX_CONV_CASE(128, 1) ISX_CONV_CASE(128, 2)

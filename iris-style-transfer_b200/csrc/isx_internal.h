@@ -21,8 +21,6 @@ struct ConvArgs {
   const float* aff_a = nullptr;
   const float* aff_b = nullptr;
   int force_bn = 0, force_mt = 0, force_stages = 0;  // tuning / test hooks (0 = heuristic)
-  int persist = 0;    // 0: library default (isx_set_option "persist"), 1: persistent kernel, -1: one tile per CTA
-  int halo_mode = 0;  // 0: one TMA box per tap; 1: halo patch + shifted views (swizzle phase in the descriptor); 2: same, phase 0
   // fused Gram backward: out += gram_act . gram_D[b]   (gram_act [B,H,W,Cout], gram_D bf16 [B,Cout,Cout])
   const __nv_bfloat16* gram_act = nullptr;
   const __nv_bfloat16* gram_D = nullptr;
