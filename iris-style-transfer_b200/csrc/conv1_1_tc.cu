@@ -36,8 +36,12 @@ struct C11Params {
 };
 
 
+// TW (power of two, TH = 128 / TW) is a template parameter: the patch index arithmetic (i % PW, i / (PW*PH), tid % TW)
+// then compiles to multiply-shift instead of ~15 integer divisions per thread and tile.
+template <int TW>
 __global__ void __launch_bounds__(128)
 conv1_1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const C11Params p) {
+  constexpr int TH = 128 / TW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                 // 128 rows x 128 B
@@ -47,7 +51,7 @@ conv1_1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   uint64_t* mma_bar = w_bar + 1;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mma_bar + 1);
   __shared__ float s_bias[64];
-  __shared__ uint32_t s_patch[3 * 3 * 130];  // worst case TW = 128, TH = 1
+  __shared__ uint32_t s_patch[3 * (TW + 2) * (TH + 2)];
   const int tid = threadIdx.x, warp = tid >> 5;
   const float mean[3] = {0.485f, 0.456f, 0.406f};
   const float stdv[3] = {0.229f, 0.224f, 0.225f};
@@ -73,33 +77,59 @@ conv1_1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   constexpr uint32_t idesc = umma_idesc_bf16(128, 64, false, false);
   uint32_t phase = 0;
   bool w_ready = false;
-  const int PW = p.TW + 2, PH = p.TH + 2;
-  const int npatch = 3 * PH * PW;
-  const int tw = tid % p.TW, th = tid / p.TW;
+  constexpr int PW = TW + 2, PH = TH + 2;
+  constexpr int npatch = 3 * PH * PW;
+  const int tw = tid % TW, th = tid / TW;
+  // The raw patch values of the NEXT tile are fetched into registers before this tile's MMA + epilogue (their global /
+  // L2 latency is the longest link of the per-tile chain) and normalised into shared memory at the top of the next round.
+  constexpr int kMaxPerThread = (npatch + 127) / 128;  // patch words per thread
+  float raw[kMaxPerThread], rawm[kMaxPerThread];
+  auto fetch = [&](int tile) {
+    const int tx = tile % p.tiles_x;
+    const int ty = (tile / p.tiles_x) % p.tiles_y;
+    const int b = tile / (p.tiles_x * p.tiles_y);
+    const int x0 = tx * TW, y0 = ty * TH;
+#pragma unroll
+    for (int j = 0; j < kMaxPerThread; ++j) {
+      const int i = tid + j * 128;
+      raw[j] = 0.f; rawm[j] = 0.f;  // rawm = 0 marks zero padding of the NORMALISED image
+      if (i < npatch) {
+        const int px = i % PW;
+        const int py = (i / PW) % PH;
+        const int c = i / (PW * PH);
+        const int y = y0 + py - 1, xq = x0 + px - 1;
+        if (y >= 0 && y < p.H && xq >= 0 && xq < p.W) {
+          const float* xp = p.x + (static_cast<long>(b) * p.xc + (p.xc == 3 ? c : 0)) * hw;
+          raw[j] = __ldg(xp + static_cast<long>(y) * p.W + xq);
+          rawm[j] = p.mask ? __ldg(p.mask + (static_cast<long>(p.mask_b > 1 ? b : 0) * p.H + y) * p.W + xq) : 1.f;
+        }
+      }
+    }
+  };
+  if (static_cast<int>(blockIdx.x) < p.n_tiles) fetch(blockIdx.x);
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const int tx = tile % p.tiles_x;
     const int ty = (tile / p.tiles_x) % p.tiles_y;
     const int b = tile / (p.tiles_x * p.tiles_y);
-    const int x0 = tx * p.TW, y0 = ty * p.TH;
-    // ---- normalise + split the input patch once (zero padding applies to the NORMALISED image) ----
-    for (int i = tid; i < npatch; i += 128) {
-      const int px = i % PW;
-      const int py = (i / PW) % PH;
-      const int c = i / (PW * PH);
-      const int y = y0 + py - 1, xq = x0 + px - 1;
-      float t = 0.f;
-      if (y >= 0 && y < p.H && xq >= 0 && xq < p.W) {
-        const float* xp = p.x + (static_cast<long>(b) * p.xc + (p.xc == 3 ? c : 0)) * hw;
-        t = (__ldg(xp + static_cast<long>(y) * p.W + xq) - mean[c]) / stdv[c];
-        if (p.mask) t *= __ldg(p.mask + (static_cast<long>(p.mask_b > 1 ? b : 0) * p.H + y) * p.W + xq);
+    const int x0 = tx * TW, y0 = ty * TH;
+    // ---- normalise + split the prefetched patch (zero padding applies to the NORMALISED image) ----
+#pragma unroll
+    for (int j = 0; j < kMaxPerThread; ++j) {
+      const int i = tid + j * 128;
+      if (i < npatch) {
+        const int c = i / (PW * PH);
+        // same expression as the oracle: ((x - mean) / std) * mask; padding stays exactly 0
+        float t = (raw[j] - mean[c]) / stdv[c];
+        t = rawm[j] == 0.f ? 0.f : (p.mask ? t * rawm[j] : t);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(t);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(t - __bfloat162float(hi));
+        __nv_bfloat162 w2;
+        w2.x = hi;
+        w2.y = lo;
+        s_patch[i] = *reinterpret_cast<uint32_t*>(&w2);
       }
-      const __nv_bfloat16 hi = __float2bfloat16_rn(t);
-      const __nv_bfloat16 lo = __float2bfloat16_rn(t - __bfloat162float(hi));
-      __nv_bfloat162 w2;
-      w2.x = hi;
-      w2.y = lo;
-      s_patch[i] = *reinterpret_cast<uint32_t*>(&w2);
     }
+    if (tile + static_cast<int>(gridDim.x) < p.n_tiles) fetch(tile + gridDim.x);
     if (tid == 0) tma_store_wait_read<0>();  // previous tile's TMA store has finished reading sA (== staging)
     __syncthreads();
     // ---- this thread's pixel: 27 (hi, lo) words -> one swizzled 128-byte row ----
@@ -198,9 +228,22 @@ int conv1_1_fwd_tc(const float* x, int xc, const float* mask, int mask_b, const 
     if (isx_make_tmap_bf16(&tmO, out, 4, dims, str, box, true)) return 3;
   }
   const size_t smem_bytes = 1024 + 16384 + 8192 + 64;
-  ISX_CHECK_CUDA(cudaFuncSetAttribute(conv1_1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  const int grid = std::min(p.n_tiles, kNumSMs * 7);
-  conv1_1_tc_kernel<<<grid, 128, smem_bytes, s>>>(tmW, tmO, p);
+  // Latency-bound kernel (per tile: patch -> smem, row build, MMA round trip, TMEM read, TMA store): ~5 CTAs are resident
+  // per SM (90 registers x 128 threads, 64 TMEM columns each).  Measured grid sweep at 640x400 (us/image): 148 x 5 12.0,
+  // x 6 15.4 (partial second wave), x 10 11.9, x 32 11.8 -> many short CTAs make the static tile split insensitive to
+  // wave quantisation.
+  const int grid = std::min(p.n_tiles, kNumSMs * 32);
+#define ISX_C11_CASE(TW_)                                                                                                   \
+  case TW_:                                                                                                                 \
+    ISX_CHECK_CUDA(cudaFuncSetAttribute(conv1_1_tc_kernel<TW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); \
+    conv1_1_tc_kernel<TW_><<<grid, 128, smem_bytes, s>>>(tmW, tmO, p);                                                      \
+    break;
+  switch (p.TW) {
+    ISX_C11_CASE(128) ISX_C11_CASE(64) ISX_C11_CASE(32) ISX_C11_CASE(16) ISX_C11_CASE(8) ISX_C11_CASE(4) ISX_C11_CASE(2)
+    ISX_C11_CASE(1)
+    default: ISX_REQUIRE(false, "conv1_1: bad tile width %d", p.TW);
+  }
+#undef ISX_C11_CASE
   ISX_LAUNCH_CHECK();
   return 0;
 }
