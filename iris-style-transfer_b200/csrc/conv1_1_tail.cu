@@ -6,8 +6,9 @@
 //     E[q][(tap, c)] = sum_o dY[q][o] * wd[tap][c][o]          (M = pixels, N = 27 -> 32, K = 64: 4 MMAs per 128 pixels)
 // and the 3x3 gather  dX[y][x][c] = sum_tap E[(y + ky - 1, x + kx - 1)][(tap, c)]  happens in the epilogue through
 // shared memory.  A work item is a 16 x 16 pixel patch (one TMA box, two 128-row M tiles) whose 14 x 14 interior is
-// written; patches overlap by one pixel on every side (1.31x re-read, mostly from L2).  Persistent CTAs, a ring of
-// patch slots, two TMEM accumulator sets, two E buffers: load, MMA and gather of consecutive patches overlap.
+// written; patches overlap by one pixel on every side (1.31x re-read, mostly from L2).  Persistent CTAs, two per SM (the
+// per-patch chain TMEM read -> E -> gather -> store is latency-bound: a second CTA fills its bubbles), each with a ring
+// of two patch slots and two TMEM accumulator sets.
 // HBM-bound by design: 128 B/pixel of dY read + 12 B/pixel of dX written.
 #include <algorithm>
 
@@ -19,7 +20,7 @@ namespace isx {
 
 static constexpr int kTailThreads = 64 + 256;
 static constexpr int kTailPatch = 256 * 128;   // 16 x 16 pixels x 64 bf16
-static constexpr int kTailSlots = 4;
+static constexpr int kTailSlots = 2;        // per CTA; two CTAs share an SM
 static constexpr int kTailInner = 14;          // interior of a patch
 static constexpr int kTailE = 27 * 256 * 4;    // E^T[27][256] fp32
 static constexpr int kTailEPad = ((kTailE + 1023) / 1024) * 1024;
@@ -35,14 +36,14 @@ struct TailParams {
   int mask_b;
 };
 
-__global__ void __launch_bounds__(kTailThreads, 1)
+__global__ void __launch_bounds__(kTailThreads, 2)
 conv1_1_tail_kernel(const __grid_constant__ CUtensorMap tmA, const TailParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_patch = smem;                                  // kTailSlots x 32 KB
   uint8_t* s_w = smem + kTailSlots * kTailPatch;            // 32 rows x 128 B, SWIZZLE_128B
-  float* s_e = reinterpret_cast<float*>(s_w + 4096);        // 2 x E^T[27][256]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + 4096 + 2 * kTailEPad);
+  float* s_e = reinterpret_cast<float*>(s_w + 4096);        // E^T[27][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + 4096 + kTailEPad);
   uint64_t* full = bars;             // [4]
   uint64_t* empty = bars + 4;        // [4]
   uint64_t* tmem_full = bars + 8;    // [2]
@@ -137,7 +138,7 @@ conv1_1_tail_kernel(const __grid_constant__ CUtensorMap tmA, const TailParams p)
     uint32_t acc = 0, aph = 0;
     for (int i = 0; i < n_my; ++i) {
       const int x0 = (r % p.tiles_x) * kTailInner, y0 = (r / p.tiles_x) * kTailInner;
-      float* e = s_e + acc * (kTailEPad / 4);
+      float* e = s_e;
       mbar_wait(&tmem_full[acc], aph);
       tc_fence_after();
       uint32_t v[32];
@@ -175,8 +176,7 @@ conv1_1_tail_kernel(const __grid_constant__ CUtensorMap tmA, const TailParams p)
           }
         }
       }
-      // E buffer `acc` is rewritten two items later; every thread passes the next item's bar.sync (after finishing this
-      // gather) before any thread gets there.
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // every gather of this item is done before E is rewritten
       acc ^= 1;
       if (acc == 0) aph ^= 1;
       r += gridDim.x;
@@ -212,9 +212,9 @@ int conv1_1_tail_n(const __nv_bfloat16* dy, const __nv_bfloat16* wd, const float
     uint32_t box[4] = {64, 16, 16, 1};
     if (isx_make_tmap_bf16(&tmA, dy, 4, dims, str, box, true)) return 3;
   }
-  const size_t smem_bytes = 1024 + kTailSlots * kTailPatch + 4096 + 2 * kTailEPad + 256;
+  const size_t smem_bytes = 1024 + kTailSlots * kTailPatch + 4096 + kTailEPad + 256;  // ~98 KB: two CTAs per SM
   ISX_CHECK_CUDA(cudaFuncSetAttribute(conv1_1_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  const int grid = std::min<int>(p.total_items, kNumSMs);
+  const int grid = std::min<int>(p.total_items, 2 * kNumSMs);
   isx_prof_begin(ISX_PROF_CONV, 2.0 * 27 * 64 * static_cast<double>(B) * H * W, stream);
   conv1_1_tail_kernel<<<(unsigned)grid, kTailThreads, smem_bytes, stream>>>(tmA, p);
   isx_prof_end(ISX_PROF_CONV, stream);
