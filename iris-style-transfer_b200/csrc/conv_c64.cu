@@ -158,6 +158,14 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ================================ MMA issuer ===========================================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, false, false);
+      // One CTA per SM owns the whole TMEM, so the allocation starts at column 0.  Using that constant (instead of the
+      // value read back from shared memory) lets the accumulator address live in a uniform register: ptxas otherwise wraps
+      // every tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (5 extra instructions per MMA on the
+      // issue-bound thread).
+      if (tmem_base != 0) {
+        printf("isx: unexpected TMEM base %u (block %d)\n", tmem_base, blockIdx.x);
+        __trap();
+      }
       mbar_wait(w_full, 0);
       const uint64_t dw0 = umma_desc_sw128(smem_u32(smem + L.w), 16, 1024);
       const uint64_t da0 = umma_desc_sw128(smem_u32(smem + L.halo), 16, 2048);
@@ -174,7 +182,7 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (!t_ready) mbar_wait(&tmem_empty[acc], aph ^ 1);
         if (!h_ready) mbar_wait(&halo_full[hs], hph);
         tc_fence_after();
-        const uint32_t d_tm = tmem_base + acc * kAccCols;
+        const uint32_t d_tm = acc * kAccCols;  // TMEM base is 0 (checked above): keeps the address in a uniform register
         {
           const uint32_t hs_n = hs + 1 == static_cast<uint32_t>(HS) ? 0 : hs + 1;
           const uint32_t hph_n = hs_n == 0 ? hph ^ 1 : hph;

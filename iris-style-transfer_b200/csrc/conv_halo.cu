@@ -168,6 +168,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ================================ MMA issuer ===========================================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, false, false);
+      // One CTA per SM owns the whole TMEM, so the allocation starts at column 0.  Using that constant (instead of the
+      // value read back from shared memory) lets the accumulator address live in a uniform register: ptxas otherwise wraps
+      // every tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (5 extra instructions per MMA on the
+      // issue-bound thread).
+      if (tmem_base != 0) {
+        printf("isx: unexpected TMEM base %u (block %d)\n", tmem_base, blockIdx.x);
+        __trap();
+      }
       const uint64_t dh = umma_desc_sw128(smem_u32(smem + L.halo), 16, kPitch * 128);  // shifted views of the patch
       const uint64_t dp = umma_desc_sw128(smem_u32(smem + L.halo), 16, 1024);          // plain 128-row tiles / weight slabs
       const uint64_t dw = umma_desc_sw128(smem_u32(smem + L.w), 16, 1024);
@@ -185,7 +193,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int i = 0; i < n_my; ++i) {
         mbar_wait(&tmem_empty[acc], aph ^ 1);
         tc_fence_after();
-        const uint32_t d_tm = tmem_base + acc * kAccCols;
+        const uint32_t d_tm = acc * kAccCols;  // TMEM base is 0 (checked above): keeps the address in a uniform register
         for (int c = 0; c < p.cin_blocks; ++c) {
           if (!h_ready) mbar_wait(&halo_full[hs], hph);
           h_ready = false;
