@@ -70,36 +70,47 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const GramParams p) {
 
   if (warp == 0) {
     if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (kb / stages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
         uint8_t* st = smem + s * kStageBytes;
 #pragma unroll
         for (int cb = 0; cb < NB; ++cb)  // cb*64 >= C only happens for C == 64: zero-filled box
           tma_load_3d(st + cb * kBlkBytes, &tmF, &full_bar[s], cb * 64, p_begin + kb * KP, b);
+        if (++s == stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      // Same issue-thread rules as the conv kernels (profiles/r01_umma_issue_probe.txt): descriptor built once and advanced
+      // by immediates, running ring counters, the next stage's mbarrier probed before this stage's MMAs.
       const uint32_t idesc = umma_idesc_bf16(128, p.C == 64 ? 64 : kN, true, true);
+      const uint64_t d0 = umma_desc_sw128(smem_u32(smem), kBlkBytes, 1024);
+      const uint32_t d_hi = static_cast<uint32_t>(d0 >> 32);
+      const uint32_t lo0 = static_cast<uint32_t>(d0);
+      const uint32_t a_off = static_cast<uint32_t>((2 * mblk) * kBlkBytes) >> 4;
+      uint32_t lo = lo0;
+      int s = 0;
+      uint32_t ph = 0;
+      bool ready = false;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (kb / stages) & 1;
-        mbar_wait(&full_bar[s], ph);
+        if (!ready) mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t base = smem_u32(smem + s * kStageBytes);
+        const uint32_t cur = lo;
+        const int s_cur = s;
+        lo += kStageBytes >> 4;
+        if (++s == stages) { s = 0; ph ^= 1; lo = lo0; }
+        ready = (kb + 1 < num_kb) && mbar_try_wait(&full_bar[s], ph);
 #pragma unroll
         for (int k = 0; k < KP / 16; ++k) {
-          const uint64_t da = umma_desc_sw128(base + (2 * mblk) * kBlkBytes + k * 2048, kBlkBytes, 1024);
 #pragma unroll
-          for (int nh = 0; nh < kNHalves; ++nh) {
-            const uint64_t db = umma_desc_sw128(base + (nh * 4) * kBlkBytes + k * 2048, kBlkBytes, 1024);
-            umma_bf16(tmem_base + nh * 256, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int nh = 0; nh < kNHalves; ++nh)
+            umma_bf16_lohi(tmem_base + nh * 256, cur + a_off + ((k * 2048) >> 4), d_hi,
+                           cur + (((nh * 4) * kBlkBytes + k * 2048) >> 4), d_hi, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit(&empty_bar[s_cur]);
       }
       umma_commit(tmem_full_bar);
     }
