@@ -1,14 +1,17 @@
-// 3x3 convolutions with Cin = 64 (conv1_2 forward, conv1_2 dgrad, the 64->3 image-gradient tail): the layers whose
-// N = 64 / 16 tiles are bound by SHARED-MEMORY bandwidth in the generic kernel (per 128x64x16 MMA the tensor core reads
-// 6 KB of operands while TMA writes the next A tiles into the same shared memory -- nine times per pixel tile, once per
-// tap).  This variant removes most of that traffic:
+// 3x3 convolutions with Cin = Cout = 64 (conv1_2 forward and dgrad; with option c64 = 2 also the 64 -> 3 image-gradient
+// tail as an N = 16 tile, kept for tests -- the default tail is conv1_1_tail.cu).  In the generic kernel these layers
+// re-load a 16 KB A tile and an 8 KB weight slab for every tap; here:
 //   * the nine weight slabs (9 x BN x 64 bf16 = 72 KB for BN = 64) stay RESIDENT in shared memory for the life of the CTA;
 //   * the input patch of a tile is loaded ONCE with its halo ([18 rows][16 pixel slots] x 64 ch, 36 KB) and the nine
 //     taps are nine shifted UMMA-descriptor views of it (start = patch + (ky*16 + kx)*128 B, SBO = 2048 B; the 128-byte
 //     swizzle is a pure function of the shared-memory address, so no descriptor base-offset is needed -- verified in
-//     profiles/r01_halo_variant_test.txt);
+//     profiles/r01_halo_variant_test.txt): DRAM traffic is exactly algorithmic (73 / 98 MB per 640x400 image);
 //   * persistent CTAs (one per SM) with a ring of halo slots and double-buffered TMEM accumulators: the producer
 //     prefetches the next tiles while the tensor core works and the eight epilogue warps drain the previous tile.
+// What bounds it now is MMA ISSUE: an M = 128 tcgen05.mma cannot be issued faster than one per ~49 cycles whatever N is
+// (profiles/r01_umma_issue_probe.txt; cta_group::2 has the same per-instruction floor), and an N = 64 MMA is only 32
+// cycles of tensor work -- so the issuing thread runs from precomputed descriptor words, running counters, probes of the
+// next tile's barriers issued before the current MMAs, and a uniform-register accumulator address.
 // Optional extras of the dgrad: the ReLU-mask activation tile of the layer below is TMA-loaded once per tile and used
 // both as the A operand of the fused Gram-backward block (x D_b) and as the epilogue mask.
 #include <algorithm>
