@@ -295,12 +295,19 @@ def main():
         base = torch.from_numpy(base).pin_memory()
 
         class Tiled:
+            """n_total eyes = the 16 synthetic frames repeated; a slice is served from pinned memory (cached per phase)."""
+            def __init__(self):
+                self.cache = {}
+
             def __len__(self):
                 return n_total
 
             def __getitem__(self, sl):
-                idx = torch.arange(sl.start, sl.stop) % base.shape[0]
-                return base[idx]
+                key = (sl.start % base.shape[0], sl.stop - sl.start)
+                if key not in self.cache:
+                    idx = torch.arange(sl.start, sl.stop) % base.shape[0]
+                    self.cache[key] = base[idx].pin_memory()
+                return self.cache[key]
 
         imgs = Tiled()
         vgg_feat = iris_b200.VGG19(content_layers=[], weights=vgg.host_weights)  # forward stops at relu4_1

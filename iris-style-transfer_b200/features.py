@@ -55,14 +55,46 @@ def extract_features_sharded(vgg: VGG19, images, batch: int = 32, gram: bool = T
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
 
     def work(lo: int, hi: int) -> torch.Tensor:
-        rows = []
-        for i in range(lo, hi, batch):
-            xb = images[i:min(hi, i + batch)]
-            xb = torch.as_tensor(xb).to(dev, torch.float32, non_blocking=True)
-            rows.append(style_features_batch(vgg, xb, gram=gram, stats=stats))
-        if not rows:
+        # Host -> device copies run on a side stream, one batch ahead of the kernels (two pinned staging buffers when the
+        # source is pageable), so the PCIe transfer of batch i+1 overlaps the forward pass of batch i.
+        starts = list(range(lo, hi, batch))
+        if not starts:
             chans = [vgg.packed(dev).bias[c].numel() for c in vgg.style_convs]
             return torch.empty(0, feature_dim(chans, gram, stats), device=dev)
+        main = torch.cuda.current_stream(dev)
+        copy = torch.cuda.Stream(dev)
+        staging = [None, None]
+
+        def fetch(k: int):
+            i = starts[k]
+            xb = torch.as_tensor(images[i:min(hi, i + batch)])
+            if xb.device.type == "cuda":
+                return xb.to(dev, torch.float32), None
+            xb = xb.to(torch.float32)
+            if not xb.is_pinned():
+                buf = staging[k & 1]
+                if buf is None or buf.shape != xb.shape:
+                    buf = staging[k & 1] = torch.empty(xb.shape, dtype=torch.float32).pin_memory()
+                buf.copy_(xb)
+                xb = buf
+            with torch.cuda.stream(copy):
+                xd = xb.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return xd, ev
+
+        rows = []
+        nxt = fetch(0)
+        for k in range(len(starts)):
+            xd, ev = nxt
+            if ev is not None:
+                main.wait_event(ev)
+                xd.record_stream(main)
+            if k + 1 < len(starts):
+                if ev is not None and staging[(k + 1) & 1] is not None:
+                    ev.synchronize()  # pageable source: staging buffer (k+1) & 1 was last read by the copy of batch k-1 (<= ev)
+                nxt = fetch(k + 1)
+            rows.append(style_features_batch(vgg, xd, gram=gram, stats=stats))
         return torch.cat(rows, dim=0)
 
     return sharded_map(n, work)

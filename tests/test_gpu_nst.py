@@ -418,6 +418,22 @@ def test_masked_gram_eval_matches_oracle(mods):
     assert 20 <= len(sh) < 40 and np.isfinite(sh).all()
 
 
+def test_feature_extraction_overlapped_copies(mods):
+    """extract_features_sharded copies batch i+1 host->device on a side stream while batch i runs: pageable and pinned
+    sources, a ragged last batch, and a device-resident source must all give the rows of a plain per-batch call."""
+    from iris_b200 import features, synthetic
+    import iris_b200
+
+    dev = torch.device("cuda:0")
+    net = iris_b200.VGG19(content_layers=[], weights=mods["weights"])
+    fr, _ = synthetic.synthetic_batch(list(range(11)), 48, 40)
+    host = torch.from_numpy(fr)                               # pageable
+    ref = torch.cat([features.style_features_batch(net, host[i:i + 4].to(dev)) for i in range(0, 11, 4)])
+    for src in (host, host.pin_memory(), host.to(dev)):
+        got = features.extract_features_sharded(net, src, batch=4, device=dev)
+        assert got.shape == ref.shape and torch.equal(got, ref)
+
+
 def test_feature_extraction_matches_oracle(mods):
     """classifiers.py:71 style features (mean | unbiased std per channel -> 1920 floats) + Gram upper triangles."""
     from iris_b200 import features, synthetic
