@@ -8,10 +8,11 @@
 //     profiles/r01_halo_variant_test.txt): DRAM traffic is exactly algorithmic (73 / 98 MB per 640x400 image);
 //   * persistent CTAs (one per SM) with a ring of halo slots and double-buffered TMEM accumulators: the producer
 //     prefetches the next tiles while the tensor core works and the eight epilogue warps drain the previous tile.
-// What bounds it now is MMA ISSUE: an M = 128 tcgen05.mma cannot be issued faster than one per ~49 cycles whatever N is
-// (profiles/r01_umma_issue_probe.txt; cta_group::2 has the same per-instruction floor), and an N = 64 MMA is only 32
-// cycles of tensor work -- so the issuing thread runs from precomputed descriptor words, running counters, probes of the
-// next tile's barriers issued before the current MMAs, and a uniform-register accumulator address.
+// What bounds it now is the MMA's own operand traffic: an SS-mode M = 128 x N = 64 x K = 16 MMA reads 4 KB (A) + 2 KB (B) from
+// shared memory at 128 B/clk = 48 cycles for 32 cycles of tensor work (profiles/r01_umma_issue_probe.txt: same floor with
+// two issuing warps and with cta_group::2), i.e. <= 67 % of the tensor peak.  To sit AT that bound the issuing thread runs
+// from precomputed descriptor words, running counters, probes of the next tile's barriers issued before the current MMAs,
+// and a uniform-register accumulator address (9 instructions per MMA).
 // Optional extras of the dgrad: the ReLU-mask activation tile of the layer below is TMA-loaded once per tile and used
 // both as the A operand of the fused Gram-backward block (x D_b) and as the epilogue mask.
 #include <algorithm>
