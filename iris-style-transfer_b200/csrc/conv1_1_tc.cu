@@ -202,12 +202,14 @@ int conv1_1_fwd_tc(const float* x, int xc, const float* mask, int mask_b, const 
   ISX_REQUIRE(xc == 1 || xc == 3, "conv1_1: image must have 1 or 3 channels, got %d", xc);
   C11Params p;
   p.x = x; p.mask = mask; p.bias = bias; p.xc = xc; p.mask_b = mask_b; p.B = B; p.H = H; p.W = W;
-  // 128-pixel patch with the least padding (wide rows first: coalesced image reads)
-  long best = -1;
+  // 128-pixel tile TW x TH with the least work: padded pixels x the halo overhead of its (TW+2) x (TH+2) input patch
+  // (16 x 8 reads 180 patch words per 128 pixels, 128 x 1 reads 390); ties go to the wider tile (coalesced image reads).
+  double best = -1.0;
   for (int twc = 128; twc >= 1; twc >>= 1) {
     const int thc = 128 / twc;
-    const long padded = static_cast<long>((W + twc - 1) / twc * twc) * ((H + thc - 1) / thc * thc);
-    if (best < 0 || padded < best) { best = padded; p.TW = twc; p.TH = thc; }
+    const double padded = static_cast<double>((W + twc - 1) / twc * twc) * ((H + thc - 1) / thc * thc);
+    const double cost = padded * ((twc + 2) * (thc + 2));
+    if (best < 0 || cost < best) { best = cost; p.TW = twc; p.TH = thc; }
   }
   p.tiles_x = (W + p.TW - 1) / p.TW;
   p.tiles_y = (H + p.TH - 1) / p.TH;
