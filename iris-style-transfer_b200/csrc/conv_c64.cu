@@ -402,7 +402,9 @@ static int launch_c64(const ConvArgs& a, cudaStream_t stream) {
   while (hs > 2 && 1024 + L.total > 227 * 1024) { --hs; L = c64_layout<BN, EPI>(hs, p.use_mask, p.use_gram, p.fuse_pool); }
   ISX_REQUIRE(1024 + L.total <= 227 * 1024, "conv_c64: %d B of shared memory exceed 227 KB", 1024 + L.total);
   p.halo_slots = hs;
-  const size_t smem_bytes = 1024 + L.total;
+  // At least 204 KB, so that no other TMEM-using CTA of this library (the conv1_1 head needs 29 KB, everything else more)
+  // can share the SM when jobs run on several streams: the MMA thread relies on owning TMEM from column 0.
+  const size_t smem_bytes = std::max<size_t>(1024 + L.total, 204 * 1024);
 
   CUtensorMap tmA, tmW, tmO, tmM, tmD, tmP;
   {
