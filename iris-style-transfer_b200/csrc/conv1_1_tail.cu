@@ -131,8 +131,10 @@ conv1_1_tail_kernel(const __grid_constant__ CUtensorMap tmA, const TailParams p)
     const int q = warp & 3;            // TMEM lane quadrant
     const int mt = (warp - 2) >> 2;    // which 128-row half of the patch this warp reads
     const int prow = mt * 128 + q * 32 + lane;  // patch pixel index: (py, px) = (prow / 16, prow % 16)
-    const int t = threadIdx.x - 64;    // gather role: interior pixel t of 196
-    const int ly = t / kTailInner, lx = t - ly * kTailInner;
+    // gather role: 16 threads per patch row (14 active) -- a warp then reads words [r*16 + 0..13] and [(r+1)*16 + 0..13] of an
+    // E row: 28 distinct banks (14 threads per row would wrap a third row onto the first one's banks: 29 % conflict cycles)
+    const int t = threadIdx.x - 64;
+    const int ly = t >> 4, lx = t & 15;
     const size_t hw = static_cast<size_t>(p.H) * p.W;
     int b = static_cast<int>(blockIdx.x) / per_img, r = static_cast<int>(blockIdx.x) % per_img;
     uint32_t acc = 0, aph = 0;
@@ -150,7 +152,7 @@ conv1_1_tail_kernel(const __grid_constant__ CUtensorMap tmA, const TailParams p)
 #pragma unroll
       for (int j = 0; j < 27; ++j) e[j * 256 + prow] = __uint_as_float(v[j]);
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (t < kTailInner * kTailInner) {
+      if (lx < kTailInner && ly < kTailInner) {
         const int x = x0 + lx, y = y0 + ly;
         if (x < p.W && y < p.H) {
           float a0 = 0.f, a1 = 0.f, a2 = 0.f;
