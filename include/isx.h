@@ -154,6 +154,9 @@ int isx_lbfgs_tick(float* x, const float* grad, float* grad_prev, void* S, void*
 /* done_out[p] (device int32) <- number of closure evaluations problem p performed once it has finished its
  * pipelines.py:79 loop, 0 while it is still running */
 int isx_lbfgs_done_flags(const void* state, int P, int32_t* done_out, isx_stream stream);
+/* count_out[p] (device int32) <- number of (y, s) pairs problem p currently holds in its history ring (len(old_dirs),
+ * lbfgs.py:409-417): what the two history passes of the next tick will stream */
+int isx_lbfgs_history_counts(const void* state, int P, int32_t* count_out, isx_stream stream);
 int isx_clamp01(float* x, int64_t n, isx_stream stream);
 
 /* ---- fused driver: one closure evaluation of pipelines.py:80-91 ------------------------------- */
@@ -174,7 +177,8 @@ typedef struct {
   int32_t coupled;                      /* 1: batch is ONE problem -> content loss is a mean over the batch too */
   int32_t mask_b;                       /* 0: no input mask, else 1 or B */
   int32_t style_mask_b;                 /* 0: plain Gram; 1 or B: mask-weighted Gram (row G'), see style_mask */
-  int32_t reserved_;
+  int32_t pred_unbatched;               /* 1: the content image was passed UNBATCHED (3,H,W): utils.GramMatrix then divides the
+                                           prediction's Gram by H*W instead of C*H*W (utils.py:253-254, n = x[0].numel()) */
   double c_weight, s_weight;            /* alpha, beta */
 } isx_nst_config;
 

@@ -322,7 +322,7 @@ extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, c
       const double w = c->style_w[st];
       if (c->style_mode == 0) {  // StyleLoss_Gram (utils.py:317-322); GramMatrix n = C*H*W (utils.py:254)
         ISX_REQUIRE(b->gram_target[st], "nst: Gram target %d missing", st);
-        const double inv_n = 1.0 / (static_cast<double>(C) * HW);
+        const double inv_n = 1.0 / ((c->pred_unbatched ? 1.0 : static_cast<double>(C)) * HW);
         const bf16* gin = at(b, L.act[i]);
         if (c->style_mask_b > 0) {  // row G': Gram of F * m_l
           ISX_REQUIRE(b->style_mask[st], "nst: style mask %d missing", st);
@@ -435,6 +435,16 @@ __global__ void done_flags_kernel(const LbfgsState* st, int P, int32_t* out) {
 extern "C" int isx_lbfgs_done_flags(const void* state, int P, int32_t* done_out, isx_stream stream) {
   ISX_REQUIRE(state && done_out, "isx_lbfgs_done_flags: null pointer");
   done_flags_kernel<<<(P + 127) / 128, 128, 0, S(stream)>>>(static_cast<const LbfgsState*>(state), P, done_out);
+  ISX_LAUNCH_CHECK();
+  return 0;
+}
+__global__ void history_counts_kernel(const LbfgsState* st, int P, int32_t* out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P) out[p] = st[p].hist_count;
+}
+extern "C" int isx_lbfgs_history_counts(const void* state, int P, int32_t* count_out, isx_stream stream) {
+  ISX_REQUIRE(state && count_out, "isx_lbfgs_history_counts: null pointer");
+  history_counts_kernel<<<(P + 127) / 128, 128, 0, S(stream)>>>(static_cast<const LbfgsState*>(state), P, count_out);
   ISX_LAUNCH_CHECK();
   return 0;
 }

@@ -47,7 +47,7 @@ class NstConfig(ctypes.Structure):
         ("content_w", ctypes.c_float * MAX_TAPS),
         ("style_target_b", ctypes.c_int32), ("content_target_b", ctypes.c_int32),
         ("coupled", ctypes.c_int32), ("mask_b", ctypes.c_int32),
-        ("style_mask_b", ctypes.c_int32), ("reserved_", ctypes.c_int32),
+        ("style_mask_b", ctypes.c_int32), ("pred_unbatched", ctypes.c_int32),
         ("c_weight", ctypes.c_double), ("s_weight", ctypes.c_double),
     ]
 
@@ -114,7 +114,8 @@ class NstEngine:
     def __init__(self, packed: PackedVGG, B: int, H: int, W: int, xc: int, content_convs: Sequence[int],
                  style_convs: Sequence[int], style_mode: int = 0, content_w: Optional[Sequence[float]] = None,
                  style_w: Optional[Sequence[float]] = None, c_weight: float = 1.0, s_weight: float = 1.0,
-                 coupled: bool = False, n_conv: Optional[int] = None, style_mask_b: int = 0):
+                 coupled: bool = False, n_conv: Optional[int] = None, style_mask_b: int = 0,
+                 pred_unbatched: bool = False):
         self.packed = packed
         self.device = packed.device
         cfg = NstConfig()
@@ -137,6 +138,7 @@ class NstEngine:
         cfg.coupled = int(coupled)
         cfg.mask_b = 0
         cfg.style_mask_b = int(style_mask_b)
+        cfg.pred_unbatched = int(pred_unbatched)
         cfg.c_weight, cfg.s_weight = float(c_weight), float(s_weight)
         self.cfg = cfg
         nbytes = _lib.call_i64("isx_nst_workspace_bytes", ctypes.byref(cfg))

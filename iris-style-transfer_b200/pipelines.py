@@ -25,6 +25,24 @@ def _prep_images(img: torch.Tensor, device) -> Tuple[torch.Tensor, bool]:
     return img.detach().to(device, torch.float32).contiguous(), unbatched
 
 
+def _norm_mask(mask: torch.Tensor, B: int, H: int, W: int, name: str, dev) -> torch.Tensor:
+    """Mask argument -> [Bm,H,W] on the device with Bm in {1, B}; anything else is a ValueError (never a silent
+    broadcast).  Accepted: (H,W), (Bm,H,W), (Bm,1,H,W)."""
+    m = mask.to(dev)
+    if m.dim() == 2:
+        m = m[None]
+    elif m.dim() == 4:
+        if m.shape[1] != 1:
+            raise ValueError("%s must have one channel, got shape %s" % (name, tuple(mask.shape)))
+        m = m[:, 0]
+    elif m.dim() != 3:
+        raise ValueError("%s must be (H,W), (B,H,W) or (B,1,H,W), got shape %s" % (name, tuple(mask.shape)))
+    if m.shape[0] not in (1, B) or tuple(m.shape[-2:]) != (H, W):
+        raise ValueError("%s of shape %s does not match a batch of %d %dx%d images (batch must be 1 or %d)"
+                         % (name, tuple(mask.shape), B, H, W, B))
+    return m
+
+
 class NstJob:
     """Device-resident state of one nst() call: targets, L-BFGS buffers, the evaluation engine.
     `tick()` = one closure evaluation (pipelines.py:80-101) + one L-BFGS iteration for the whole batch."""
@@ -32,8 +50,9 @@ class NstJob:
     def __init__(self, c_img, s_img, vgg, dev, clone_content=True, BN_loss=True, c_loss_weight=1.0,
                  s_loss_weight=1.0, lr=1.0, epochs=200, independent=False, history_size=100, x_init=None,
                  history_dtype=torch.float32, c_mask=None, s_mask=None):
-        c_img, _ = _prep_images(c_img, dev)
+        c_img, c_unbatched = _prep_images(c_img, dev)
         s_img, s_unbatched = _prep_images(s_img, dev)
+        self.c_unbatched = c_unbatched
         if clone_content:
             x = c_img.clone()
         elif x_init is not None:
@@ -53,12 +72,13 @@ class NstJob:
         levels = [CONV_LEVEL[i] for i in sc]
         cmask_b = 0
         if c_mask is not None:
-            c_mask = c_mask.to(dev)
-            cmask_b = c_mask.shape[0] if c_mask.dim() >= 3 and c_mask.shape[0] in (1, B) else 1
-            if c_mask.dim() == 2:
-                c_mask = c_mask[None]
+            c_mask = _norm_mask(c_mask, B, H, W, "c_mask", dev)
+            cmask_b = c_mask.shape[0]
+        # an UNBATCHED content image (the notebook's call) makes utils.GramMatrix divide the prediction's Gram by H*W
+        # only (utils.py:253-254); the target keeps its own normaliser (s_unbatched below), exactly like the reference
         eng = NstEngine(packed, B, H, W, xc, cc, sc, style_mode=1 if BN_loss else 0, c_weight=c_loss_weight,
-                        s_weight=s_loss_weight, coupled=not independent, style_mask_b=cmask_b)
+                        s_weight=s_loss_weight, coupled=not independent, style_mask_b=cmask_b,
+                        pred_unbatched=c_unbatched)
         if cmask_b:
             eng.set_style_masks(mask_pyramid(c_mask, levels))
         eng.forward(c_img)
@@ -79,9 +99,7 @@ class NstJob:
             eng.set_bn_targets([m for m, _ in st], [s for _, s in st])
         else:
             if s_mask is not None:  # row G': targets are Gram matrices of the style features weighted by the style's mask
-                s_mask = s_mask.to(dev)
-                if s_mask.dim() == 2:
-                    s_mask = s_mask[None]
+                s_mask = _norm_mask(s_mask, Bs, Hs, Ws, "s_mask", dev)
                 s_feats = [masked_features(f, m) for f, m in zip(s_feats, mask_pyramid(s_mask, levels))]
             # unbatched style image (…2020.py:103-104): GramMatrix divides by H*W only (SURVEY note N3)
             eng.set_gram_targets([gram_of(f, 1.0 / (f.shape[1] * f.shape[2]) if s_unbatched else None) for f in s_feats])
@@ -148,6 +166,12 @@ class NstJob:
         _lib.call("isx_lbfgs_done_flags", self.state, self.P, self.done, _lib.stream_ptr())
         return self.done.cpu()
 
+    def history_counts(self):
+        """Per-problem number of (y, s) pairs currently in the L-BFGS ring (one small D2H read)."""
+        out = torch.zeros(self.P, device=self.x.device, dtype=torch.int32)
+        _lib.call("isx_lbfgs_history_counts", self.state, self.P, out, _lib.stream_ptr())
+        return out.cpu()
+
     def finish(self):
         evals = self.evals_done()
         n_evals = int(evals.max().item()) if bool((evals > 0).all().item()) else self.ticks
@@ -177,13 +201,22 @@ class NstJobGroup:
         self.streams = [torch.cuda.Stream(dev) for _ in range(n)]
         self.jobs: List[NstJob] = []
         x_init = kw.pop("x_init", None)
+        c_mask, s_mask = kw.pop("c_mask", None), kw.pop("s_mask", None)
+        s_batched = s_img.dim() == 4 and s_img.shape[0] == B and B > 1
+
+        def part(m, lo, hi, batched):  # per-image masks follow their images into the sub-batch
+            if m is None or m.dim() < 3 or m.shape[0] == 1 or not batched:
+                return m
+            return m[lo:hi]
+
         for i, st in enumerate(self.streams):
             lo, hi = bounds[i], bounds[i + 1]
             st.wait_stream(main)
             with torch.cuda.stream(st):
-                si = s_img if (s_img.dim() == 3 or s_img.shape[0] == 1) else s_img[lo:hi]
+                si = s_img[lo:hi] if s_batched else s_img
                 xi = x_init[lo:hi] if x_init is not None else None
-                self.jobs.append(NstJob(c_img[lo:hi], si, vgg, dev, x_init=xi, **kw))
+                self.jobs.append(NstJob(c_img[lo:hi], si, vgg, dev, x_init=xi, c_mask=part(c_mask, lo, hi, True),
+                                        s_mask=part(s_mask, lo, hi, s_batched), **kw))
         self.max_ticks = self.jobs[0].max_ticks
         self.epochs = self.jobs[0].epochs
         self.P = B
@@ -227,6 +260,107 @@ class NstJobGroup:
         self.join(dev)
         return (torch.cat(xs), n_evals, torch.cat(evs), torch.cat([pad(h) for h in hcs], dim=1),
                 torch.cat([pad(h) for h in hss], dim=1))
+
+
+class _HistoryWriter:
+    """x_hist without stalling the optimisation loop (the reference does a blocking
+    `x.detach().cpu()` per evaluation, pipelines.py:93).  Per kept evaluation: a device-to-device snapshot of x on
+    the compute stream (x is overwritten by the L-BFGS update of the same tick), then a device-to-host copy on a
+    side stream, ordered by events only -- the host never synchronises inside the loop.
+      * small histories (<= ISX_XHIST_PINNED_GB, default 8 GiB in total): every entry is its own pinned host tensor
+        (torch's caching host allocator recycles the blocks across calls) and is the D2H destination;
+      * larger ones: a ring of pinned slots drained into ordinary (pageable) tensors by a worker thread.
+    `finish()` is the only synchronisation point."""
+
+    SLOTS = 3
+
+    def __init__(self, shape, n_entries, dev):
+        import os
+        import threading
+
+        self.dev, self.shape = dev, tuple(shape)
+        nbytes = 4
+        for d in self.shape:
+            nbytes *= d
+        limit = float(os.environ.get("ISX_XHIST_PINNED_GB", "8")) * (1 << 30)
+        self.direct = nbytes * max(1, n_entries) <= limit
+        self.copy_stream = torch.cuda.Stream(dev)
+        self.dslots = [torch.empty(self.shape, device=dev, dtype=torch.float32) for _ in range(self.SLOTS)]
+        self.d2h_done = [None] * self.SLOTS          # event on copy_stream: device slot j may be overwritten
+        self.entries = []
+        self.k = 0
+        if not self.direct:
+            self.pslots = [torch.empty(self.shape, dtype=torch.float32).pin_memory() for _ in range(self.SLOTS)]
+            self.free = [threading.Event() for _ in range(self.SLOTS)]
+            for f in self.free:
+                f.set()
+            self.queue = []
+            self.cv = threading.Condition()
+            self.closed = False
+            self.error = None
+            self.worker = threading.Thread(target=self._drain, daemon=True)
+            self.worker.start()
+
+    def _drain(self):
+        try:
+            while True:
+                with self.cv:
+                    while not self.queue and not self.closed:
+                        self.cv.wait()
+                    if not self.queue:
+                        return
+                    j, ev, dst = self.queue.pop(0)
+                ev.synchronize()
+                dst.copy_(self.pslots[j])
+                self.free[j].set()
+        except Exception as e:  # surfaced by finish()
+            self.error = e
+            for f in self.free:
+                f.set()
+
+    def snapshot(self, x: torch.Tensor):
+        """Record the current x (called on the compute stream right before the evaluation that consumes it)."""
+        j = self.k % self.SLOTS
+        self.k += 1
+        main = torch.cuda.current_stream(self.dev)
+        if self.d2h_done[j] is not None:
+            main.wait_event(self.d2h_done[j])
+        self.dslots[j].copy_(x.view(self.shape), non_blocking=True)
+        snap = torch.cuda.Event()
+        snap.record(main)
+        if self.direct:
+            dst = torch.empty(self.shape, dtype=torch.float32, pin_memory=True)
+        else:
+            self.free[j].wait()       # back-pressure only when the host drains slower than the GPU produces
+            if self.error is not None:
+                raise self.error
+            self.free[j].clear()
+            dst = self.pslots[j]
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(snap)
+            dst.copy_(self.dslots[j], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self.d2h_done[j] = ev
+        if self.direct:
+            self.entries.append(dst)
+        else:
+            out = torch.empty(self.shape, dtype=torch.float32)
+            self.entries.append(out)
+            with self.cv:
+                self.queue.append((j, ev, out))
+                self.cv.notify()
+
+    def finish(self, keep: int):
+        self.copy_stream.synchronize()
+        if not self.direct:
+            with self.cv:
+                self.closed = True
+                self.cv.notify()
+            self.worker.join()
+            if self.error is not None:
+                raise self.error
+        return self.entries[:keep]
 
 
 def nst(c_img: torch.Tensor,
@@ -291,24 +425,33 @@ def nst(c_img: torch.Tensor,
             job = NstJobGroup(c_dev, s_dev, vgg, dev, streams=streams, **kw)
         else:
             job = NstJob(c_img, s_img, vgg, dev, **kw)
-            if cuda_graph:
-                if x_hist_stride:
-                    x_hist_first = job.x.detach().to('cpu')
-                job.enable_graph()
-        x_hist: List[torch.Tensor] = []
-        if getattr(job, "_graph", None) is not None and x_hist_stride:
-            x_hist.append(x_hist_first)  # image of the eager first evaluation
+        B_all = c_img.shape[0] if c_img.dim() == 4 else 1
+        hist = None
+        if x_hist_stride:
+            n_keep = (job.max_ticks + x_hist_stride - 1) // x_hist_stride
+            shape = tuple(c_img.shape[-3:]) if c_img.dim() == 3 else (B_all,) + tuple(c_img.shape[-3:])
+            hist = _HistoryWriter(shape, n_keep, dev)
+        group = isinstance(job, NstJobGroup)
+
+        def snapshot():
+            if group:     # sub-batches live on their own streams: gather their images on the caller's stream
+                job.join(dev)
+                hist.snapshot(torch.cat([j.x for j in job.jobs]))
+                job.fork(dev)
+            else:
+                hist.snapshot(job.x)
+
+        if cuda_graph and not group:
+            if hist is not None:
+                snapshot()            # image of the eager first evaluation
+            job.enable_graph()
         pbar = None
         if use_tqdm:
             import tqdm
             pbar = tqdm.tqdm(total=epochs)
         while job.ticks < job.max_ticks:
-            if x_hist_stride and job.ticks % x_hist_stride == 0:
-                if isinstance(job, NstJobGroup):
-                    job.join(dev)
-                    x_hist.append(torch.cat([j.x.detach().to('cpu') for j in job.jobs]))
-                else:
-                    x_hist.append(job.x.detach().to('cpu'))  # pipelines.py:93
+            if hist is not None and job.ticks % x_hist_stride == 0:
+                snapshot()            # pipelines.py:93, without the host synchronisation
             job.tick()
             if pbar is not None:
                 pbar.update(1)
@@ -321,8 +464,11 @@ def nst(c_img: torch.Tensor,
         if pbar is not None:
             pbar.close()
         x, n_evals, evals, hc, hs = job.finish()
-        if x_hist_stride:
-            x_hist = x_hist[:(n_evals + x_hist_stride - 1) // x_hist_stride]
+        x_hist: List[torch.Tensor] = []
+        if hist is not None:
+            x_hist = hist.finish((n_evals + x_hist_stride - 1) // x_hist_stride)
+        if c_img.dim() == 3:          # unbatched content image: the reference returns (3,H,W) (pipelines.py:52,110)
+            x = x[0]
         c_loss_hist = (hc.mean(dim=1) if independent else hc[:, 0]).tolist()
         s_loss_hist = (hs.sum(dim=1) if independent else hs[:, 0]).tolist()
         last_info.clear()
@@ -378,7 +524,9 @@ def crop_resize_irises(frames: torch.Tensor, masks: torch.Tensor, bboxes: torch.
     for the whole batch at once.  frames [B,1,H,W] fp32, masks uint8 [B,1,H,W], bboxes int32 [B,4]."""
     B, _, H, W = frames.shape
     xm = (frames * masks).contiguous()  # masking multiply: plumbing-level elementwise on the caller's tensors
-    out = torch.empty(B, 3, size[0], size[1], device=frames.device, dtype=torch.float32)
+    # zero-initialised: a frame WITHOUT iris pixels (bbox sentinel row_max = -1) yields an all-zero crop, never
+    # uninitialised memory; callers that must skip such frames test `bboxes[:, 2] < 0` (mask_and_crop_iris raises)
+    out = torch.zeros(B, 3, size[0], size[1], device=frames.device, dtype=torch.float32)
     with torch.cuda.device(frames.device):
         _lib.call("isx_resize_bilinear_aa", xm, 1, H, W, bboxes.contiguous(), out, 3, size[0], size[1], B,
                   _lib.stream_ptr())

@@ -71,6 +71,18 @@ def random_vgg19_weights(seed: int = 0) -> List[Tuple[torch.Tensor, torch.Tensor
     return out
 
 
+class _RoundSTE(torch.autograd.Function):
+    """Round to a narrower storage type in the forward pass, identity in the backward pass."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        return x.to(dtype).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
 def vgg19_forward(
     x: torch.Tensor,
     weights: Sequence[Tuple[torch.Tensor, torch.Tensor]],
@@ -78,6 +90,7 @@ def vgg19_forward(
     style_layers: Sequence[str] = DEFAULT_STYLE,
     mask: Optional[torch.Tensor] = None,
     full: bool = True,
+    operand_dtype: Optional[torch.dtype] = None,
 ):
     """VGG19.forward (models/vgg/vgg.py:69-92): Normalize(mean,std) -> optional `* mask` ->
     vgg19.features; returns (last activation, [content feats], [style feats]).
@@ -85,7 +98,13 @@ def vgg19_forward(
     torchvision's ReLUs are inplace, so a `conv*` tap aliases the following ReLU's output
     (SURVEY.md note N2): every tap is the post-ReLU tensor.  `full=False` stops after the
     deepest tap (what the product computes inside nst(); the reference always runs to pool5,
-    vgg.py:87, but nothing on the NST path reads that output)."""
+    vgg.py:87, but nothing on the NST path reads that output).
+
+    `operand_dtype` (None = the reference's fp32): EMULATION of the precision BASELINE.json's north star prescribes
+    for the accelerated path -- conv operands stored in that type (torch.bfloat16), fp32 accumulation: the weights
+    of conv1_2.. and every post-ReLU activation are rounded to it (straight-through in the backward pass).  Used by
+    the tests to measure how far the REFERENCE ALGORITHM itself moves under that rounding (the calibration of the
+    trajectory bounds); never by the product."""
     unbatched = x.dim() == 3
     mean = torch.tensor(IMAGENET_MEAN, dtype=x.dtype).view(-1, 1, 1)
     std = torch.tensor(IMAGENET_STD, dtype=x.dtype).view(-1, 1, 1)
@@ -107,7 +126,11 @@ def vgg19_forward(
         else:
             w, b = weights[ci]
             ci += 1
+            if operand_dtype is not None:
+                w = w.to(operand_dtype).to(torch.float32)
             h = F.relu(F.conv2d(h, w, b, padding=1))
+            if operand_dtype is not None:
+                h = _RoundSTE.apply(h, operand_dtype)
             feats[idx] = h  # conv index aliases post-ReLU
             feats[idx + 1] = h
             idx += 2
@@ -313,10 +336,15 @@ def nst(
     x0: Optional[torch.Tensor] = None,
     keep_hist: bool = True,
     full_forward: bool = False,
+    operand_dtype: Optional[torch.dtype] = None,
+    grad_noise: float = 0.0,
+    noise_seed: int = 0,
 ):
     """pipelines.py:8-110 restated on CPU fp32.  A batch is ONE L-BFGS problem exactly as in the
     reference; call with B=1 for the per-image semantics the product shards on.
-    `x0` replaces torch.rand (pipelines.py:54) when clone_content is False so the test controls it."""
+    `x0` replaces torch.rand (pipelines.py:54) when clone_content is False so the test controls it.
+    `operand_dtype` (see vgg19_forward) and `grad_noise` (multiply every gradient element by 1 + grad_noise * N(0,1))
+    are SENSITIVITY PROBES of the reference algorithm for the tests' calibrated trajectory bounds; both default off."""
     c_img = c_img.to(torch.float32)
     s_img = s_img.to(torch.float32)
     if clone_content:
@@ -325,8 +353,10 @@ def nst(
         x = x0.clone() if x0 is not None else torch.rand(c_img.shape)
     x = x.contiguous()
     with torch.no_grad():
-        _, c_feats, _ = vgg19_forward(c_img, weights, content_layers, style_layers, full=full_forward)
-        _, _, s_feats = vgg19_forward(s_img, weights, content_layers, style_layers, full=full_forward)
+        _, c_feats, _ = vgg19_forward(c_img, weights, content_layers, style_layers, full=full_forward,
+                                      operand_dtype=operand_dtype)
+        _, _, s_feats = vgg19_forward(s_img, weights, content_layers, style_layers, full=full_forward,
+                                      operand_dtype=operand_dtype)
         if BN_loss:
             t_mean = [t.mean(dim=(-2, -1)) for t in s_feats]
             t_std = [t.std(dim=(-2, -1)) for t in s_feats]
@@ -337,17 +367,21 @@ def nst(
     c_hist: List[float] = []
     s_hist: List[float] = []
     n_evals = [0]
+    gen = torch.Generator().manual_seed(noise_seed)
 
     def closure():
         with torch.no_grad():
             x.clamp_(0, 1)  # pipelines.py:81-82
         xv = x.detach().requires_grad_(True)
         with torch.enable_grad():
-            _, x_c, x_s = vgg19_forward(xv, weights, content_layers, style_layers, full=full_forward)
+            _, x_c, x_s = vgg19_forward(xv, weights, content_layers, style_layers, full=full_forward,
+                                        operand_dtype=operand_dtype)
             c_loss = content_loss_l2(x_c, c_feats)
             s_loss = style_loss_bn(x_s, t_mean, t_std) if BN_loss else style_loss_gram(x_s, t_gram)
             loss = c_loss * c_loss_weight + s_loss * s_loss_weight
             (g,) = torch.autograd.grad(loss, xv)
+        if grad_noise > 0.0:
+            g = g * (1.0 + grad_noise * torch.randn(g.shape, generator=gen))
         if keep_hist:
             x_hist.append(x.detach().clone())
         c_hist.append(float(c_loss))

