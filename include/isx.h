@@ -98,6 +98,15 @@ int64_t isx_gram_workspace_bytes(int B, int HW, int C);
 int isx_gram_fwd(const isx_bf16* feat, int B, int HW, int C, float inv_n, void* workspace, float* G_out,
                  const float* target, int target_b, double loss_scale, double* loss, float grad_scale,
                  isx_bf16* D_out, isx_stream stream);
+/* Mask-weighted Gram (row G' of the hot path; hooks models/vgg/vgg.py:84-85, pipelines.py:83): G = (F*m)^T (F*m) * inv_n
+ * with m fp32 [mask_b,HW], mask_b in {1,B}.  The weights are applied to the operand tiles inside the Gram kernel and K
+ * blocks whose mask is all zero are skipped.  flags_ws: isx_gram_mask_flags_bytes(mask_b,HW,C) bytes of scratch;
+ * fm2 (bf16 [B,HW,C], required) receives F*m^2, the operand of the Gram backward (dF = (F m^2) . D): written on the
+ * non-zero blocks, zeroed elsewhere.  Other arguments as isx_gram_fwd. */
+int64_t isx_gram_mask_flags_bytes(int mask_b, int HW, int C);
+int isx_gram_masked_fwd(const isx_bf16* feat, int B, int HW, int C, const float* m, int mask_b, void* flags_ws,
+                        isx_bf16* fm2, float inv_n, void* workspace, float* G_out, const float* target, int target_b,
+                        double loss_scale, double* loss, float grad_scale, isx_bf16* D_out, isx_stream stream);
 /* ---- K5: Gram backward dF[b] = F[b] . D[b] (autograd of utils.py:253-256), tcgen05 1x1 mode.
  * feat bf16 [B,H,W,C], D bf16 [B,C,C] (symmetric), dF bf16 [B,H,W,C]; optional relu mask. */
 int isx_gram_bwd(const isx_bf16* feat, const isx_bf16* D, isx_bf16* dF, int B, int H, int W, int C,
@@ -211,6 +220,15 @@ int isx_nst_forward(const isx_nst_config* cfg, const isx_nst_buffers* bufs, cons
 /* device pointer / shape of a stored activation: kind 0 = ReLU output of conv `idx`, 1 = output of pool `idx` (0..4) */
 int isx_nst_feature(const isx_nst_config* cfg, const isx_nst_buffers* bufs, int kind, int idx, isx_bf16** ptr,
                     int32_t* h, int32_t* w, int32_t* c);
+/* row G': call once after the style masks (bufs->style_mask) were set or changed and before isx_nst_eval: zeroes the
+ * F * m^2 buffers of the workspace and records which K blocks of every mask are non-zero (the Gram kernel skips the
+ * others: an iris mask covers 6-10 % of an eye frame) */
+int isx_nst_prepare_style_masks(const isx_nst_config* cfg, const isx_nst_buffers* bufs, isx_stream stream);
+/* style features of the batch the preceding isx_nst_forward left in the workspace, one row per image written straight
+ * into out (row stride ld floats): [per style tap: mean | unbiased std over (H,W)] (models/classifiers/classifiers.py:71)
+ * then [per style tap: upper triangle of utils.GramMatrix in torch.triu_indices order] (BASELINE config 3) */
+int isx_nst_style_features(const isx_nst_config* cfg, const isx_nst_buffers* bufs, int want_stats, int want_gram,
+                           float* out, int64_t ld, isx_stream stream);
 /* closure evaluation: loss_c/loss_s double [B] (unweighted, per image), grad fp32 [B,xc,H,W] = d(alpha c + beta s)/dx */
 int isx_nst_eval(const isx_nst_config* cfg, const isx_nst_buffers* bufs, const float* x, double* loss_c,
                  double* loss_s, float* grad, isx_stream stream);

@@ -144,6 +144,31 @@ extern "C" int isx_gram_fwd(const isx_bf16* feat, int B, int HW, int C, float in
                        loss, grad_scale, P(D_out), S(stream));
 }
 
+extern "C" int64_t isx_gram_mask_flags_bytes(int mask_b, int HW, int C) {
+  if (mask_b <= 0 || HW <= 0 || C <= 0) return 0;
+  return gram_mask_flags_bytes(mask_b, HW, C);
+}
+
+extern "C" int isx_gram_masked_fwd(const isx_bf16* feat, int B, int HW, int C, const float* m, int mask_b, void* flags_ws,
+                                   isx_bf16* fm2, float inv_n, void* workspace, float* G_out, const float* target,
+                                   int target_b, double loss_scale, double* loss, float grad_scale, isx_bf16* D_out,
+                                   isx_stream stream) {
+  ISX_REQUIRE(feat && m && flags_ws && workspace, "isx_gram_masked_fwd: null pointer");
+  ISX_REQUIRE(mask_b == 1 || mask_b == B, "isx_gram_masked_fwd: mask batch %d must be 1 or %d", mask_b, B);
+  ISX_REQUIRE(!target || target_b == 1 || target_b == B, "isx_gram_masked_fwd: target batch %d must be 1 or %d", target_b, B);
+  int rc = gram_mask_flags(m, mask_b, HW, C, static_cast<uint8_t*>(flags_ws), S(stream));
+  if (rc) return rc;
+  ISX_REQUIRE(fm2 != nullptr, "isx_gram_masked_fwd: fm2 (bf16 [B,HW,C]) is required: the kernel stores F*m^2 while it scales the tiles");
+  ISX_CHECK_CUDA(cudaMemsetAsync(fm2, 0, static_cast<size_t>(B) * HW * C * 2, S(stream)));
+  GramMask gm;
+  gm.m = m; gm.mask_b = mask_b; gm.kb_flags = static_cast<const uint8_t*>(flags_ws); gm.fm2 = P(fm2);
+  const int splits = gram_pick_splits(B, HW, C);
+  rc = gram_sym_partial(P(feat), B, HW, C, splits, static_cast<float*>(workspace), &gm, S(stream));
+  if (rc) return rc;
+  return gram_finalize(static_cast<const float*>(workspace), B, splits, C, inv_n, G_out, target, target_b, loss_scale,
+                       loss, grad_scale, P(D_out), S(stream));
+}
+
 extern "C" int isx_gram_bwd(const isx_bf16* feat, const isx_bf16* D, isx_bf16* dF, int B, int H, int W, int C,
                             const isx_bf16* relu_act, isx_stream stream) {
   ISX_REQUIRE(feat && D && dF, "isx_gram_bwd: null pointer");

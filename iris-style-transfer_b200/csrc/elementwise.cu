@@ -372,45 +372,63 @@ int tap_add_mask(const __nv_bfloat16* g, const __nv_bfloat16* add, const float* 
 }
 
 // ------------------------------------------------------------------------------------------
-// Gram finalize: G = sum_splits(partial) * inv_n; optional store; optional (G - T), loss, dL/dG (bf16)
-//   loss[b] += loss_scale * sum((G - T)^2)        (StyleLoss_Gram, utils.py:319-321: 0.25 * w_l * sum)
-//   D[b]     = grad_scale * (G - T)  in bf16        (dF = D . F, see conv_tc 1x1 mode)
+// Gram finalize: G = sum_splits(partial) * inv_n over the block-upper triangle the symmetric Gram kernel computed
+// (128-channel granularity), mirrored into the lower triangle.  One block per 32x32 tile (tr <= tc) of one image.
+//   G_out  (optional) full fp32 [B,C,C]
+//   loss[b] += loss_scale * sum((G - T)^2)          (StyleLoss_Gram, utils.py:319-321: 0.25 * w_l * sum)
+//   D[b]    = grad_scale * (G - T)  in bf16, full     (dF = D . F, see conv_tc 1x1 mode)
+//   triu    (optional) upper triangle incl. diagonal in torch.triu_indices order, row b at triu + b * triu_ld
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 gram_finalize_kernel(const float* __restrict__ partial, int splits, int C, float inv_n, float* __restrict__ G_out,
                      const float* __restrict__ target, int target_b, double loss_scale, double* __restrict__ loss,
-                     float grad_scale, __nv_bfloat16* __restrict__ D_out) {
-  // four consecutive Gram entries per thread (C*C is a multiple of 4), grid-stride over the image's C*C/4 quads:
-  // few blocks per image, so the per-image loss takes a handful of double atomics instead of C*C/256
+                     float grad_scale, __nv_bfloat16* __restrict__ D_out, float* __restrict__ triu, long triu_ld) {
+  __shared__ float sg[32][33];
+  __shared__ double red[8];
   const int b = blockIdx.y;
+  // tile index -> (tr, tc), tr <= tc, row-major over the upper triangle of the nt x nt tile grid
+  const int nt = C >> 5;
+  int tr = 0, rem = blockIdx.x;
+  while (rem >= nt - tr) { rem -= nt - tr; ++tr; }
+  const int tc = tr + rem;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const long cc = static_cast<long>(C) * C;
-  const long quads = cc >> 2;
-  const float4* p4 = reinterpret_cast<const float4*>(partial + static_cast<long>(b) * splits * cc);
-  const float4* t4 = target ? reinterpret_cast<const float4*>(target + (target_b > 1 ? b : 0) * cc) : nullptr;
+  const float* pb = partial + static_cast<long>(b) * splits * cc;
+  const float* tb = target ? target + (target_b > 1 ? b : 0) * cc : nullptr;
   float d2 = 0.f;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < quads;
-       i += static_cast<long>(gridDim.x) * blockDim.x) {
-    float4 acc = __ldg(p4 + i);
-    for (int s = 1; s < splits; ++s) {
-      const float4 v = __ldg(p4 + s * quads + i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  float g[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = tr * 32 + ty + 8 * k, c = tc * 32 + tx;
+    const long o = static_cast<long>(r) * C + c;
+    float acc = __ldg(pb + o);
+    for (int s = 1; s < splits; ++s) acc += __ldg(pb + s * cc + o);
+    g[k] = acc * inv_n;
+    sg[ty + 8 * k][tx] = g[k];
+    if (G_out) G_out[b * cc + o] = g[k];
+    if (triu && c >= r) triu[b * triu_ld + static_cast<long>(r) * C - (static_cast<long>(r) * (r - 1)) / 2 + (c - r)] = g[k];
+    if (tb) {
+      const float d = g[k] - __ldg(tb + o);
+      d2 = fmaf(d, d, d2);
+      if (D_out) D_out[b * cc + o] = __float2bfloat16_rn(d * grad_scale);
     }
-    const float4 g = make_float4(acc.x * inv_n, acc.y * inv_n, acc.z * inv_n, acc.w * inv_n);
-    if (G_out) reinterpret_cast<float4*>(G_out + b * cc)[i] = g;
-    if (t4) {
-      const float4 t = __ldg(t4 + i);
-      const float dx = g.x - t.x, dy = g.y - t.y, dz = g.z - t.z, dw = g.w - t.w;
-      d2 = fmaf(dx, dx, d2); d2 = fmaf(dy, dy, d2); d2 = fmaf(dz, dz, d2); d2 = fmaf(dw, dw, d2);
-      if (D_out) {
-        uint2 o;
-        o.x = pack_bf16x2(dx * grad_scale, dy * grad_scale);
-        o.y = pack_bf16x2(dz * grad_scale, dw * grad_scale);
-        reinterpret_cast<uint2*>(D_out + b * cc)[i] = o;
+  }
+  if (tr != tc) {  // mirror tile: entry (row, col) = (tc*32 + ty + 8k, tr*32 + tx) = G(tr*32 + tx, tc*32 + ty + 8k)
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = tc * 32 + ty + 8 * k, c = tr * 32 + tx;
+      const long o = static_cast<long>(r) * C + c;
+      const float v = sg[tx][ty + 8 * k];
+      if (G_out) G_out[b * cc + o] = v;
+      if (tb) {
+        const float d = v - __ldg(tb + o);
+        d2 = fmaf(d, d, d2);
+        if (D_out) D_out[b * cc + o] = __float2bfloat16_rn(d * grad_scale);
       }
     }
   }
   if (loss) {
-    __shared__ double red[8];
     double v = warp_sum(static_cast<double>(d2));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
@@ -424,14 +442,12 @@ gram_finalize_kernel(const float* __restrict__ partial, int splits, int C, float
 
 int gram_finalize(const float* partial, int B, int splits, int C, float inv_n, float* G_out, const float* target,
                   int target_b, double loss_scale, double* loss, float grad_scale, __nv_bfloat16* D_out,
-                  cudaStream_t s) {
-  ISX_REQUIRE(C % 2 == 0, "gram_finalize: C = %d must be even", C);
-  const long quads = static_cast<long>(C) * C / 4;
-  // one quad per thread up to 64 blocks per image, grid-stride beyond (C = 512: 4 quads per thread)
-  const unsigned bx = static_cast<unsigned>(std::max<long>(1, std::min<long>(64, (quads + 255) / 256)));
-  dim3 grid(bx, B);
+                  cudaStream_t s, float* triu, long triu_ld) {
+  ISX_REQUIRE(C % 32 == 0, "gram_finalize: C = %d must be a multiple of 32", C);
+  const int nt = C / 32;
+  dim3 grid(static_cast<unsigned>(nt * (nt + 1) / 2), B);
   gram_finalize_kernel<<<grid, 256, 0, s>>>(partial, splits, C, inv_n, G_out, target, target_b, loss_scale,
-                                            target ? loss : nullptr, grad_scale, D_out);
+                                            target ? loss : nullptr, grad_scale, D_out, triu, triu_ld);
   ISX_LAUNCH_CHECK();
   return 0;
 }
@@ -541,7 +557,8 @@ int chan_sums(const __nv_bfloat16* f, int B, long HW, int C, double* sums, cudaS
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, int B, int C, double n, float* __restrict__ mean,
                                    float* __restrict__ stdv, const float* __restrict__ t_mean,
                                    const float* __restrict__ t_std, int target_b, double loss_scale, double grad_scale,
-                                   double* __restrict__ loss, float* __restrict__ aff_a, float* __restrict__ aff_b) {
+                                   double* __restrict__ loss, float* __restrict__ aff_a, float* __restrict__ aff_b,
+                                   long out_ld) {
   const int b = blockIdx.x;
   double lacc = 0.0;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -550,8 +567,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int B, int C
     double var = (s2 - s1 * mu) / (n - 1.0);
     if (var < 0.0) var = 0.0;
     const double sd = sqrt(var);
-    if (mean) mean[b * C + c] = static_cast<float>(mu);
-    if (stdv) stdv[b * C + c] = static_cast<float>(sd);
+    if (mean) mean[b * out_ld + c] = static_cast<float>(mu);
+    if (stdv) stdv[b * out_ld + c] = static_cast<float>(sd);
     if (t_mean) {
       const int tb = target_b > 1 ? b : 0;
       const double dm = static_cast<double>(static_cast<float>(mu)) - t_mean[tb * C + c];
@@ -579,9 +596,9 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int B, int C
 
 int bn_finalize(const double* sums, int B, int C, long HW, float* mean, float* stdv, const float* t_mean,
                 const float* t_std, int target_b, double loss_scale, double grad_scale, double* loss, float* aff_a,
-                float* aff_b, cudaStream_t s) {
+                float* aff_b, cudaStream_t s, long out_ld) {
   bn_finalize_kernel<<<B, 256, 0, s>>>(sums, B, C, static_cast<double>(HW), mean, stdv, t_mean, t_std, target_b,
-                                       loss_scale, grad_scale, loss, aff_a, aff_b);
+                                       loss_scale, grad_scale, loss, aff_a, aff_b, out_ld > 0 ? out_ld : C);
   ISX_LAUNCH_CHECK();
   return 0;
 }

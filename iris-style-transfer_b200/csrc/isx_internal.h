@@ -45,5 +45,17 @@ int conv_halo(const ConvArgs& a, cudaStream_t stream);
 int gram_tc_partial(const __nv_bfloat16* feat, int B, int HW, int C, int splits, float* partial,
                     cudaStream_t stream);
 int gram_pick_splits(int B, int HW, int C);
+// mask-weighted variant (row G'): Gram of F * m with m fp32 [mask_b,HW]; kb_flags from gram_mask_flags; fm2 <- F * m^2 on
+// the K blocks whose mask is not all zero (the caller zeroes fm2 once: untouched blocks must read as zero)
+struct GramMask {
+  const float* m;
+  int mask_b;
+  const uint8_t* kb_flags;
+  __nv_bfloat16* fm2;
+};
+int gram_sym_partial(const __nv_bfloat16* feat, int B, int HW, int C, int splits, float* partial, const GramMask* mask,
+                     cudaStream_t stream);
+int gram_mask_flags_bytes(int mask_b, int HW, int C);
+int gram_mask_flags(const float* m, int mask_b, int HW, int C, uint8_t* flags, cudaStream_t stream);
 
 }  // namespace isx

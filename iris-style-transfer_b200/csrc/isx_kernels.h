@@ -25,12 +25,12 @@ int mask_features(const __nv_bfloat16* f, const float* m, int mask_b, __nv_bfloa
 int avgpool2x2_f32(const float* in, float* out, int B, int H, int W, cudaStream_t s);
 int gram_finalize(const float* partial, int B, int splits, int C, float inv_n, float* G_out, const float* target,
                   int target_b, double loss_scale, double* loss, float grad_scale, __nv_bfloat16* D_out,
-                  cudaStream_t s);
+                  cudaStream_t s, float* triu = nullptr, long triu_ld = 0);
 int content_mse(const __nv_bfloat16* pred, const __nv_bfloat16* target, int target_b, __nv_bfloat16* grad, int B,
                 long per_image, double loss_scale, float grad_scale, double* loss, cudaStream_t s);
 int chan_sums(const __nv_bfloat16* f, int B, long HW, int C, double* sums, cudaStream_t s);
 int bn_finalize(const double* sums, int B, int C, long HW, float* mean, float* stdv, const float* t_mean,
                 const float* t_std, int target_b, double loss_scale, double grad_scale, double* loss, float* aff_a,
-                float* aff_b, cudaStream_t s);
+                float* aff_b, cudaStream_t s, long out_ld = 0);  // out_ld: row stride of mean / stdv (0 = C)
 
 }  // namespace isx

@@ -28,7 +28,7 @@ struct Layout {
   size_t gradA, gradB, tapbuf;
   size_t cgrad[ISX_MAX_TAPS];
   size_t gram_ws, D[ISX_MAX_TAPS], sums, aff_a[ISX_MAX_TAPS], aff_b[ISX_MAX_TAPS];
-  size_t fm[ISX_MAX_TAPS], fm2[ISX_MAX_TAPS];  // masked features (row G')
+  size_t fm2[ISX_MAX_TAPS], kbflags[ISX_MAX_TAPS];  // row G': F * m^2 (Gram-backward operand), non-zero K-block flags
   size_t total;
 };
 
@@ -84,11 +84,11 @@ int make_layout(const isx_nst_config* c, Layout* L) {
     L->D[t] = off; off += align_up(static_cast<size_t>(c->B) * C * C * 2);
     L->aff_a[t] = off; off += align_up(static_cast<size_t>(c->B) * C * 4);
     L->aff_b[t] = off; off += align_up(static_cast<size_t>(c->B) * C * 4);
-    L->fm[t] = L->fm2[t] = 0;
+    L->fm2[t] = L->kbflags[t] = 0;
     if (c->style_mask_b > 0) {
       const size_t act_bytes = static_cast<size_t>(c->B) * HW * C * 2;
-      L->fm[t] = off; off += align_up(act_bytes);
       L->fm2[t] = off; off += align_up(act_bytes);
+      L->kbflags[t] = off; off += align_up(static_cast<size_t>(gram_mask_flags_bytes(c->style_mask_b, HW, C)));
     }
   }
   L->gram_ws = off; off += align_up(gram_ws);
@@ -323,14 +323,15 @@ extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, c
       if (c->style_mode == 0) {  // StyleLoss_Gram (utils.py:317-322); GramMatrix n = C*H*W (utils.py:254)
         ISX_REQUIRE(b->gram_target[st], "nst: Gram target %d missing", st);
         const double inv_n = 1.0 / ((c->pred_unbatched ? 1.0 : static_cast<double>(C)) * HW);
-        const bf16* gin = at(b, L.act[i]);
-        if (c->style_mask_b > 0) {  // row G': Gram of F * m_l
+        GramMask gm;
+        if (c->style_mask_b > 0) {  // row G': Gram of F * m_l, weights applied to the operand tile inside the Gram kernel
           ISX_REQUIRE(b->style_mask[st], "nst: style mask %d missing", st);
-          if (int rc = mask_features(gin, b->style_mask[st], c->style_mask_b, at(b, L.fm[st]), at(b, L.fm2[st]), B, HW, C, s)) return rc;
-          gin = at(b, L.fm[st]);
+          gm.m = b->style_mask[st]; gm.mask_b = c->style_mask_b;
+          gm.kb_flags = reinterpret_cast<const uint8_t*>(at(b, L.kbflags[st]));  // isx_nst_prepare_style_masks
+          gm.fm2 = at(b, L.fm2[st]);
         }
-        int rc = gram_tc_partial(gin, B, static_cast<int>(HW), C, gram_pick_splits(B, static_cast<int>(HW), C),
-                                 atf(b, L.gram_ws), s);
+        int rc = gram_sym_partial(at(b, L.act[i]), B, static_cast<int>(HW), C, gram_pick_splits(B, static_cast<int>(HW), C),
+                                  atf(b, L.gram_ws), c->style_mask_b > 0 ? &gm : nullptr, s);
         if (rc) return rc;
         rc = gram_finalize(atf(b, L.gram_ws), B, gram_pick_splits(B, static_cast<int>(HW), C), C,
                            static_cast<float>(inv_n), nullptr, b->gram_target[st], c->style_target_b, 0.25 * w, loss_s,
@@ -374,6 +375,69 @@ extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, c
     }
   }
   return run_backward(c, b, L, src, nullptr, grad, s);
+}
+
+extern "C" int isx_nst_prepare_style_masks(const isx_nst_config* c, const isx_nst_buffers* b, isx_stream stream) {
+  ISX_REQUIRE(c && b && b->workspace, "isx_nst_prepare_style_masks: null pointer");
+  ISX_REQUIRE(c->style_mask_b == 1 || c->style_mask_b == c->B, "isx_nst_prepare_style_masks: style mask batch %d", c->style_mask_b);
+  Layout L;
+  if (int rc = make_layout(c, &L)) return rc;
+  cudaStream_t s = S(stream);
+  for (int t = 0; t < c->n_style; ++t) {
+    const int i = c->style_conv[t];
+    const int C = kCout[i];
+    const int HW = L.H[kLevel[i]] * L.W[kLevel[i]];
+    ISX_REQUIRE(b->style_mask[t], "isx_nst_prepare_style_masks: style mask %d missing", t);
+    // F * m^2 is rewritten by every evaluation on the K blocks whose mask is not all zero; everything else stays zero
+    ISX_CHECK_CUDA(cudaMemsetAsync(at(b, L.fm2[t]), 0, static_cast<size_t>(c->B) * HW * C * 2, s));
+    if (int rc = gram_mask_flags(b->style_mask[t], c->style_mask_b, HW, C, reinterpret_cast<uint8_t*>(at(b, L.kbflags[t])), s))
+      return rc;
+  }
+  return 0;
+}
+
+// Style features of the batch the preceding isx_nst_forward left in the workspace (classifiers.py:71 statistics and
+// the utils.GramMatrix upper triangles), written straight into the caller's row-major matrix.
+extern "C" int isx_nst_style_features(const isx_nst_config* c, const isx_nst_buffers* b, int want_stats, int want_gram,
+                                      float* out, int64_t ld, isx_stream stream) {
+  ISX_REQUIRE(c && b && out && b->workspace, "isx_nst_style_features: null pointer");
+  ISX_REQUIRE(want_stats || want_gram, "isx_nst_style_features: nothing to extract");
+  Layout L;
+  if (int rc = make_layout(c, &L)) return rc;
+  cudaStream_t s = S(stream);
+  const int B = c->B;
+  int64_t need = 0;
+  for (int t = 0; t < c->n_style; ++t) {
+    const int64_t C = kCout[c->style_conv[t]];
+    need += (want_stats ? 2 * C : 0) + (want_gram ? C * (C + 1) / 2 : 0);
+  }
+  ISX_REQUIRE(ld >= need, "isx_nst_style_features: row stride %lld < feature dimension %lld", (long long)ld, (long long)need);
+  int64_t off = 0;
+  if (want_stats) {
+    double* sums = reinterpret_cast<double*>(static_cast<char*>(b->workspace) + L.sums);
+    for (int t = 0; t < c->n_style; ++t) {
+      const int i = c->style_conv[t], lv = kLevel[i], C = kCout[i];
+      const long HW = static_cast<long>(L.H[lv]) * L.W[lv];
+      ISX_REQUIRE(HW >= 2, "isx_nst_style_features: unbiased std needs >= 2 pixels at conv %d", i);
+      ISX_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * B * C * 2, s));
+      if (int rc = chan_sums(at(b, L.act[i]), B, HW, C, sums, s)) return rc;
+      if (int rc = bn_finalize(sums, B, C, HW, out + off, out + off + C, nullptr, nullptr, 1, 0.0, 0.0, nullptr, nullptr,
+                               nullptr, s, ld)) return rc;
+      off += 2 * C;
+    }
+  }
+  if (want_gram) {
+    for (int t = 0; t < c->n_style; ++t) {
+      const int i = c->style_conv[t], lv = kLevel[i], C = kCout[i];
+      const int HW = L.H[lv] * L.W[lv];
+      const int splits = gram_pick_splits(B, HW, C);
+      if (int rc = gram_sym_partial(at(b, L.act[i]), B, HW, C, splits, atf(b, L.gram_ws), nullptr, s)) return rc;
+      if (int rc = gram_finalize(atf(b, L.gram_ws), B, splits, C, static_cast<float>(1.0 / (static_cast<double>(C) * HW)),
+                                 nullptr, nullptr, 1, 0.0, nullptr, 0.f, nullptr, s, out + off, ld)) return rc;
+      off += static_cast<int64_t>(C) * (C + 1) / 2;
+    }
+  }
+  return 0;
 }
 
 extern "C" int isx_nst_backward(const isx_nst_config* c, const isx_nst_buffers* b, const isx_bf16* const* feat_grads,

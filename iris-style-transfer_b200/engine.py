@@ -181,6 +181,8 @@ class NstEngine:
             assert m.shape[0] == self.cfg.style_mask_b
             self._keep.append(m)
             self.bufs.style_mask[t] = m.data_ptr()
+        with torch.cuda.device(self.device):
+            _lib.call("isx_nst_prepare_style_masks", ctypes.byref(self.cfg), ctypes.byref(self.bufs), _lib.stream_ptr())
 
     def set_content_targets(self, feats: Sequence[torch.Tensor]):
         for t, f in enumerate(feats):
@@ -215,15 +217,25 @@ class NstEngine:
                   _lib.stream_ptr())
 
     def feature(self, kind: int, idx: int) -> torch.Tensor:
-        """bf16 NHWC view (a COPY) of a stored activation: kind 0 = conv idx's ReLU output, 1 = pool idx."""
+        """bf16 NHWC COPY of a stored activation: kind 0 = conv idx's ReLU output, 1 = pool idx."""
+        return self.feature_view(kind, idx).clone()
+
+    def style_features(self, out: torch.Tensor, stats: bool = True, gram: bool = True):
+        """Rows of style features of the batch of the last forward(), written in place into `out` [B, >= D] fp32
+        (isx_nst_style_features): mean | unbiased std per style tap, then the Gram upper triangles."""
+        assert out.is_cuda and out.dtype == torch.float32 and out.stride(1) == 1 and out.shape[0] == self.cfg.B
+        _lib.call("isx_nst_style_features", ctypes.byref(self.cfg), ctypes.byref(self.bufs), int(stats), int(gram), out,
+                  _lib.i64(out.stride(0)), _lib.stream_ptr())
+
+    def feature_view(self, kind: int, idx: int) -> torch.Tensor:
+        """bf16 NHWC VIEW into the workspace (valid until the next forward / eval on this engine)."""
         ptr = ctypes.c_void_p()
         h, w, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         _lib.call("isx_nst_feature", ctypes.byref(self.cfg), ctypes.byref(self.bufs), kind, idx, ctypes.byref(ptr),
                   ctypes.byref(h), ctypes.byref(w), ctypes.byref(c))
         off = ptr.value - self.workspace.data_ptr()
         n = self.cfg.B * h.value * w.value * c.value
-        view = self.workspace[off:off + 2 * n].view(torch.bfloat16).view(self.cfg.B, h.value, w.value, c.value)
-        return view.clone()
+        return self.workspace[off:off + 2 * n].view(torch.bfloat16).view(self.cfg.B, h.value, w.value, c.value)
 
     def backward(self, feat_grads: Dict[int, torch.Tensor], last_pool_grad: Optional[torch.Tensor], grad: torch.Tensor):
         """isx_nst_backward: feat_grads {conv index: bf16 NHWC gradient w.r.t. its ReLU output}; uses the activations of
@@ -258,6 +270,24 @@ def mask_pyramid(mask: torch.Tensor, levels: Sequence[int]) -> List[torch.Tensor
             cur, lvl = nxt, lvl + 1
         out[want] = cur
     return [out[l] for l in levels]
+
+
+def masked_gram_of(feat_nhwc: torch.Tensor, m: torch.Tensor, inv_n: Optional[float] = None) -> torch.Tensor:
+    """Row G': utils.GramMatrix(F * m) with m fp32 [Bm,h,w] (Bm in {1,B}) via isx_gram_masked_fwd -- the weights are
+    applied to the operand tiles inside the Gram kernel, all-zero K blocks are skipped."""
+    B, H, W, C = feat_nhwc.shape
+    HW = H * W
+    if inv_n is None:
+        inv_n = 1.0 / (C * HW)
+    dev = feat_nhwc.device
+    m = m.to(dev, torch.float32).contiguous()
+    ws = torch.empty(max(256, _lib.call_i64("isx_gram_workspace_bytes", B, HW, C)), device=dev, dtype=torch.uint8)
+    fl = torch.empty(max(256, _lib.call_i64("isx_gram_mask_flags_bytes", m.shape[0], HW, C)), device=dev, dtype=torch.uint8)
+    fm2 = torch.empty_like(feat_nhwc)
+    G = torch.empty(B, C, C, device=dev, dtype=torch.float32)
+    _lib.call("isx_gram_masked_fwd", feat_nhwc, B, HW, C, m, m.shape[0], fl, fm2, _lib.f32(inv_n), ws, G, None, 1,
+              _lib.f64(0.0), None, _lib.f32(0.0), None, _lib.stream_ptr())
+    return G
 
 
 def masked_features(feat_nhwc: torch.Tensor, m: torch.Tensor) -> torch.Tensor:

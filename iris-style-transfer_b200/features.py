@@ -9,8 +9,6 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from .engine import gram_of, stats_of
-from .sharding import sharded_map
 from .vgg import VGG19
 
 
@@ -25,27 +23,23 @@ def _copy_stream(dev: torch.device) -> torch.cuda.Stream:
     return _COPY_STREAMS[key]
 
 
-def _triu_index(C: int, device):
-    return torch.triu_indices(C, C, device=device)
-
-
 @torch.no_grad()
-def style_features_batch(vgg: VGG19, x: torch.Tensor, gram: bool = True, stats: bool = True) -> torch.Tensor:
-    """x: [B,1|3,H,W] fp32 on a CUDA device -> [B, D]; D = 2*sum(C_l) (stats) + sum(C_l(C_l+1)/2) (gram)."""
+def style_features_batch(vgg: VGG19, x: torch.Tensor, gram: bool = True, stats: bool = True,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: [B,1|3,H,W] fp32 on a CUDA device -> [B, D]; D = 2*sum(C_l) (stats) + sum(C_l(C_l+1)/2) (gram).
+    One forward + ONE libisx call (isx_nst_style_features): the statistics and the Gram upper triangles are computed
+    on the activations where they lie in the workspace and written straight into the rows of `out` (given or new)."""
     if not (gram or stats):
         raise ValueError("nothing to extract")
-    _, _, s, _ = vgg.features_nhwc(x, full=False)
-    cols = []
-    if stats:
-        for f in s:
-            m, sd = stats_of(f)
-            cols += [m, sd]
-    if gram:
-        for f in s:
-            G = gram_of(f)
-            iu = _triu_index(G.shape[-1], G.device)
-            cols.append(G[:, iu[0], iu[1]])
-    return torch.cat(cols, dim=1)
+    eng = vgg.run_forward(x, full=False)
+    chans = [vgg.packed(eng.device).bias[c].numel() for c in vgg.style_convs]
+    D = feature_dim(chans, gram, stats)
+    if out is None:
+        out = torch.empty(eng.cfg.B, D, device=eng.device, dtype=torch.float32)
+    assert out.shape[0] == eng.cfg.B and out.shape[1] >= D
+    with torch.cuda.device(eng.device):
+        eng.style_features(out, stats=stats, gram=gram)
+    return out
 
 
 def feature_dim(channels: Sequence[int], gram: bool = True, stats: bool = True) -> int:
@@ -59,72 +53,68 @@ def feature_dim(channels: Sequence[int], gram: bool = True, stats: bool = True) 
 
 @torch.no_grad()
 def extract_features_sharded(vgg: VGG19, images, batch: int = 32, gram: bool = True, stats: bool = True,
-                             device=None) -> torch.Tensor:
-    """`images`: indexable [n,1|3,H,W] (host or device).  Each rank extracts its contiguous shard in batches of
-    `batch`; one all-gather returns the full [n, D] matrix on every rank."""
+                             device=None, gather_chunk: int = 128) -> torch.Tensor:
+    """`images`: indexable [n,1|3,H,W] (host or device).  Each rank extracts its contiguous shard in batches of `batch`,
+    every batch writing its rows in place into the final matrix; complete chunks of `gather_chunk` rows are all-gathered
+    on a side stream while later batches compute (sharding.RowGatherer); every rank returns the full [n, D] matrix."""
+    from .sharding import RowGatherer
+
     n = len(images)
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    chans = [vgg.packed(dev).bias[c].numel() for c in vgg.style_convs]
+    rows = RowGatherer(n, feature_dim(chans, gram, stats), dev, chunk_rows=gather_chunk)
+    lo, hi = rows.lo, rows.hi
+    # Host -> device copies run on a side stream, one batch ahead of the kernels, into two device buffers that are
+    # allocated once (a fresh allocation per batch on a second stream makes the caching allocator fall back to
+    # cudaMalloc, which serialises the device: measured 83 ms vs 140-220 ms per 512 eyes).  Pageable sources go through
+    # two pinned staging buffers.
+    starts = list(range(lo, hi, batch))
+    main = torch.cuda.current_stream(dev)
+    copy = _copy_stream(dev)
+    copy.wait_stream(main)
+    staging = [None, None]
+    dbuf = [None, None]
+    consumed = [None, None]  # event on `main`: the kernels reading dbuf[j] have been enqueued and finished
 
-    def work(lo: int, hi: int) -> torch.Tensor:
-        # Host -> device copies run on a side stream, one batch ahead of the kernels, into two device buffers that are
-        # allocated once (a fresh allocation per batch on a second stream makes the caching allocator fall back to
-        # cudaMalloc, which serialises the device: measured 83 ms vs 140-220 ms per 512 eyes).  Pageable sources go through
-        # two pinned staging buffers.
-        starts = list(range(lo, hi, batch))
-        if not starts:
-            chans = [vgg.packed(dev).bias[c].numel() for c in vgg.style_convs]
-            return torch.empty(0, feature_dim(chans, gram, stats), device=dev)
-        main = torch.cuda.current_stream(dev)
-        copy = _copy_stream(dev)
-        copy.wait_stream(main)
-        staging = [None, None]
-        dbuf = [None, None]
-        consumed = [None, None]  # event on `main`: the kernels reading dbuf[j] have been enqueued and finished
+    def fetch(k: int):
+        i = starts[k]
+        xb = torch.as_tensor(images[i:min(hi, i + batch)])
+        if xb.device.type == "cuda":
+            return xb.to(dev, torch.float32), None
+        xb = xb.to(torch.float32)
+        j = k & 1
+        if not xb.is_pinned():
+            buf = staging[j]
+            if buf is None or buf.shape != xb.shape:
+                buf = staging[j] = torch.empty(xb.shape, dtype=torch.float32).pin_memory()
+            buf.copy_(xb)
+            xb = buf
+        if dbuf[j] is None or dbuf[j].shape[1:] != xb.shape[1:] or dbuf[j].shape[0] < xb.shape[0]:
+            dbuf[j] = torch.empty(xb.shape, dtype=torch.float32, device=dev)
+            dbuf[j].record_stream(copy)
+        xd = dbuf[j][:xb.shape[0]]
+        with torch.cuda.stream(copy):
+            if consumed[j] is not None:
+                copy.wait_event(consumed[j])
+            xd.copy_(xb, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+        return xd, ev
 
-        def fetch(k: int):
-            i = starts[k]
-            xb = torch.as_tensor(images[i:min(hi, i + batch)])
-            if xb.device.type == "cuda":
-                return xb.to(dev, torch.float32), None
-            xb = xb.to(torch.float32)
-            j = k & 1
-            if not xb.is_pinned():
-                buf = staging[j]
-                if buf is None or buf.shape != xb.shape:
-                    buf = staging[j] = torch.empty(xb.shape, dtype=torch.float32).pin_memory()
-                buf.copy_(xb)
-                xb = buf
-            if dbuf[j] is None or dbuf[j].shape[1:] != xb.shape[1:] or dbuf[j].shape[0] < xb.shape[0]:
-                dbuf[j] = torch.empty(xb.shape, dtype=torch.float32, device=dev)
-                dbuf[j].record_stream(copy)
-            xd = dbuf[j][:xb.shape[0]]
-            with torch.cuda.stream(copy):
-                if consumed[j] is not None:
-                    copy.wait_event(consumed[j])
-                xd.copy_(xb, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy)
-            return xd, ev
-
-        out = None
-        row = 0
-        nxt = fetch(0)
-        for k in range(len(starts)):
-            xd, ev = nxt
-            if ev is not None:
-                main.wait_event(ev)
-            if k + 1 < len(starts):
-                if ev is not None and staging[(k + 1) & 1] is not None:
-                    ev.synchronize()  # pageable source: staging buffer (k+1) & 1 was last read by the copy of batch k-1 (<= ev)
-                nxt = fetch(k + 1)
-            r = style_features_batch(vgg, xd, gram=gram, stats=stats)
-            if ev is not None:
-                consumed[k & 1] = torch.cuda.Event()
-                consumed[k & 1].record(main)
-            if out is None:
-                out = torch.empty(hi - lo, r.shape[1], device=dev, dtype=r.dtype)
-            out[row:row + r.shape[0]] = r
-            row += r.shape[0]
-        return out
-
-    return sharded_map(n, work)
+    row = 0
+    nxt = fetch(0) if starts else None
+    for k in range(len(starts)):
+        xd, ev = nxt
+        if ev is not None:
+            main.wait_event(ev)
+        if k + 1 < len(starts):
+            if ev is not None and staging[(k + 1) & 1] is not None:
+                ev.synchronize()  # pageable source: staging buffer (k+1) & 1 was last read by the copy of batch k-1 (<= ev)
+            nxt = fetch(k + 1)
+        style_features_batch(vgg, xd, gram=gram, stats=stats, out=rows.local[row:row + xd.shape[0]])
+        if ev is not None:
+            consumed[k & 1] = torch.cuda.Event()
+            consumed[k & 1].record(main)
+        row += xd.shape[0]
+        rows.flush(row)
+    return rows.finish()

@@ -12,7 +12,7 @@ from typing import List, Optional, Tuple
 import torch
 
 from . import _lib
-from .engine import CONV_LEVEL, LbfgsConfig, NstEngine, gram_of, mask_pyramid, masked_features, stats_of
+from .engine import CONV_LEVEL, LbfgsConfig, NstEngine, gram_of, mask_pyramid, masked_gram_of, stats_of
 from .vgg import VGG19
 
 last_info: dict = {}
@@ -86,24 +86,26 @@ class NstJob:
         Bs, xs, Hs, Ws = s_img.shape
         if (Bs, xs, Hs, Ws) == (B, xc, H, W):
             eng.forward(s_img)
-            s_feats = [eng.feature(0, i) for i in sc]
+            s_feats = [eng.feature_view(0, i) for i in sc]   # consumed below, before the engine runs again
         else:
             if Bs not in (1, B):
                 raise ValueError("style batch %d must be 1 or %d" % (Bs, B))
             seng = NstEngine(packed, Bs, Hs, Ws, xs, cc, sc)
             seng.forward(s_img)
-            s_feats = [seng.feature(0, i) for i in sc]
-            del seng
+            s_feats = [seng.feature_view(0, i) for i in sc]
         if BN_loss:
             st = [stats_of(f) for f in s_feats]
             eng.set_bn_targets([m for m, _ in st], [s for _, s in st])
         else:
+            # unbatched style image (…2020.py:103-104): GramMatrix divides by H*W only (SURVEY note N3)
+            inv = [1.0 / (f.shape[1] * f.shape[2]) if s_unbatched else None for f in s_feats]
             if s_mask is not None:  # row G': targets are Gram matrices of the style features weighted by the style's mask
                 s_mask = _norm_mask(s_mask, Bs, Hs, Ws, "s_mask", dev)
-                s_feats = [masked_features(f, m) for f, m in zip(s_feats, mask_pyramid(s_mask, levels))]
-            # unbatched style image (…2020.py:103-104): GramMatrix divides by H*W only (SURVEY note N3)
-            eng.set_gram_targets([gram_of(f, 1.0 / (f.shape[1] * f.shape[2]) if s_unbatched else None) for f in s_feats])
+                eng.set_gram_targets([masked_gram_of(f, m, n) for f, m, n in zip(s_feats, mask_pyramid(s_mask, levels), inv)])
+            else:
+                eng.set_gram_targets([gram_of(f, n) for f, n in zip(s_feats, inv)])
         del s_feats
+        seng = None
         self.eng = eng
 
         # ---- optimiser (pipelines.py:59): torch.optim.LBFGS([x], lr) defaults ----

@@ -49,6 +49,71 @@ def all_gather_rows(local_rows: torch.Tensor, n_total: int) -> torch.Tensor:
     return out[:n_total]
 
 
+class RowGatherer:
+    """Row-sharded [n_total, D] matrix that every rank ends up holding in full (BASELINE config 3: the feature rows of
+    the iris classifier).  Rank r produces rows [lo, hi) = shard_range(n_total, r, world) by writing them IN PLACE into
+    `local` (a view of the final buffer: no padded copy); `flush(rows_done)` all-gathers every complete chunk of
+    `chunk_rows` rows on a side stream, so the exchange of chunk k rides under the computation of chunk k+1 (NCCL over
+    NVLink / NVSwitch; on CPU tensors / gloo the same calls run synchronously); `finish()` gathers the rest and
+    returns the [n_total, D] matrix."""
+
+    def __init__(self, n_total: int, D: int, device, dtype=torch.float32, chunk_rows: int = 128):
+        self.dist = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.world = dist.get_world_size() if self.dist else 1
+        self.rank = dist.get_rank() if self.dist else 0
+        self.n_total, self.D = n_total, D
+        self.per = (n_total + self.world - 1) // self.world if n_total else 0
+        self.lo, self.hi = shard_range(n_total, self.rank, self.world)
+        self.device = torch.device(device)
+        self.full = torch.empty(self.world * self.per, D, device=self.device, dtype=dtype)
+        self.local = self.full[self.rank * self.per: self.rank * self.per + (self.hi - self.lo)]
+        self.chunk = max(1, int(chunk_rows))
+        self.sent = 0                      # rows of every rank's shard already exchanged (same schedule on all ranks)
+        self.cuda = self.device.type == "cuda"
+        self.comm = torch.cuda.Stream(self.device) if (self.cuda and self.dist) else None
+
+    def _gather(self, r0: int, r1: int):
+        """Exchange rows [r0, r1) of every rank's (padded) shard."""
+        n = r1 - r0
+        mine = self.full[self.rank * self.per + r0: self.rank * self.per + r1]
+        view3 = self.full.view(self.world, self.per, self.D)
+        if self.comm is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(ev)
+                tmp = torch.empty(self.world, n, self.D, device=self.device, dtype=self.full.dtype)
+                dist.all_gather_into_tensor(tmp.view(self.world * n, self.D), mine)
+                view3[:, r0:r1].copy_(tmp)
+        else:
+            tmp = torch.empty(self.world * n, self.D, device=self.device, dtype=self.full.dtype)
+            dist.all_gather_into_tensor(tmp, mine.contiguous())
+            view3[:, r0:r1].copy_(tmp.view(self.world, n, self.D))
+
+    def flush(self, rows_done: int):
+        """Call after `rows_done` local rows have been enqueued: complete chunks go out.  Every rank must reach the same
+        chunk boundaries, so only rows that EVERY rank owns (the padded tail of the last shard excluded) are sent here."""
+        if not self.dist:
+            return
+        # collectives must match across ranks: chunks are cut only from the rows EVERY shard has (the last shard is the
+        # shortest), so each rank issues the same floor(common / chunk) gathers here, whatever its own progress
+        common = max(0, self.n_total - (self.world - 1) * self.per)
+        limit = min(rows_done, common)
+        while self.sent + self.chunk <= limit:
+            self._gather(self.sent, self.sent + self.chunk)
+            self.sent += self.chunk
+
+    def finish(self) -> torch.Tensor:
+        if not self.dist:
+            return self.local
+        if self.sent < self.per:
+            self._gather(self.sent, self.per)
+            self.sent = self.per
+        if self.comm is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm)
+        return self.full[: self.n_total]
+
+
 def sharded_map(n_total: int, fn: Callable[[int, int], torch.Tensor]) -> torch.Tensor:
     """Run fn(lo, hi) -> [hi-lo, D] on this rank's shard and all-gather the rows of every rank."""
     rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0

@@ -129,10 +129,9 @@ class VGG19(torch.nn.Module):
         return self._engines[key]
 
     @torch.no_grad()
-    def features_nhwc(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None, full: bool = False):
-        """bf16 NHWC features straight from the device buffers: (pool5 or None, content list, style list)."""
-        unbatched = x.dim() == 3
-        if unbatched:
+    def run_forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None, full: bool = False) -> NstEngine:
+        """Forward pass only; the activations stay in the returned engine's workspace (engine.feature_view)."""
+        if x.dim() == 3:
             x = x[None]
         dev = x.device if x.is_cuda else self._device
         x = x.detach().to(dev, torch.float32).contiguous()
@@ -145,6 +144,14 @@ class VGG19(torch.nn.Module):
         self._fwd_version += 1
         with torch.cuda.device(dev):
             eng.forward(x, with_last_pool=full)
+        return eng
+
+    @torch.no_grad()
+    def features_nhwc(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None, full: bool = False):
+        """bf16 NHWC features (copies of the device buffers): (pool5 or None, content list, style list)."""
+        unbatched = x.dim() == 3
+        eng = self.run_forward(x, mask, full)
+        with torch.cuda.device(eng.device):
             last = eng.feature(1, 4) if full else None
             c = [eng.feature(0, i) for i in self.content_convs]
             s = [eng.feature(0, i) for i in self.style_convs]

@@ -344,6 +344,49 @@ def test_gram_fwd_and_loss(isx, C, B, H, W):
 
 
 @pytest.mark.parametrize("C", [64, 128, 256, 512])
+@pytest.mark.parametrize("B,H,W,mb", [(2, 50, 80, 2), (3, 17, 23, 1), (1, 100, 160, 1)])
+def test_gram_masked_fwd(isx, C, B, H, W, mb):
+    """Row G': the mask weights are applied to the operand tiles INSIDE the Gram kernel (all-zero K blocks skipped) and
+    F*m^2 is written for the backward -- bit-identical to the separate pre-pass isx_mask_features + isx_gram_fwd, and
+    equal to utils.GramMatrix(F * m) computed by torch."""
+    f = nhwc_bf16(B, H, W, C, 9, relu=True)
+    HW = H * W
+    g = torch.Generator().manual_seed(3)
+    m = torch.zeros(mb, H, W)
+    m[:, H // 3: H // 3 + max(2, H // 4), W // 4: W // 4 + max(3, W // 3)] = 1.0            # a blob: most K blocks are empty
+    m[:, H // 3 + 1, W // 4: W // 4 + 3] = torch.tensor([0.25, 0.5, 0.75])                  # pooled-mask style fractions
+    if mb > 1:
+        m[1] = (torch.rand(H, W, generator=g) > 0.5).float()                               # dense random mask
+    m = m.reshape(mb, HW).cuda().contiguous()
+    inv_n = 1.0 / (C * HW)
+    ws = torch.empty(isx.call_i64("isx_gram_workspace_bytes", B, HW, C), device="cuda", dtype=torch.uint8)
+    fl = torch.empty(max(16, isx.call_i64("isx_gram_mask_flags_bytes", mb, HW, C)), device="cuda", dtype=torch.uint8)
+    fm2 = torch.full((B, H, W, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    G = torch.full((B, C, C), float("nan"), device="cuda")
+    tgt = torch.randn(B, C, C, device="cuda") * 0.01
+    loss = torch.zeros(B, device="cuda", dtype=torch.float64)
+    D = torch.empty(B, C, C, device="cuda", dtype=torch.bfloat16)
+    isx.call("isx_gram_masked_fwd", f, B, HW, C, m, mb, fl, fm2, isx.f32(inv_n), ws, G, tgt, B, isx.f64(0.25), loss,
+             isx.f32(3.0), D, isx.stream_ptr())
+    # the pre-pass formulation
+    fm_ref = torch.empty_like(f)
+    fm2_ref = torch.empty_like(f)
+    isx.call("isx_mask_features", f, m, mb, fm_ref, fm2_ref, B, isx.i64(HW), C, isx.stream_ptr())
+    G2 = torch.empty_like(G)
+    loss2 = torch.zeros_like(loss)
+    isx.call("isx_gram_fwd", fm_ref, B, HW, C, isx.f32(inv_n), ws, G2, tgt, B, isx.f64(0.25), loss2, isx.f32(3.0), None,
+             isx.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(G, G2) and torch.equal(fm2, fm2_ref)
+    assert torch.allclose(loss, loss2, rtol=1e-12)
+    ff = (f.float().reshape(B, HW, C) * m.reshape(mb, HW, 1)).to(torch.bfloat16).float()
+    ref = torch.bmm(ff.transpose(1, 2), ff) * inv_n
+    assert torch.allclose(G, ref, rtol=2e-4, atol=1e-6 * ref.abs().max().item())
+    assert torch.equal(G, G.transpose(1, 2))
+    assert_close_bf16(D, 3.0 * (ref - tgt), "masked gram D")
+
+
+@pytest.mark.parametrize("C", [64, 128, 256, 512])
 def test_gram_bwd(isx, C):
     B, H, W = 2, 26, 40
     f = nhwc_bf16(B, H, W, C, 6, relu=True)

@@ -434,6 +434,36 @@ def test_feature_extraction_overlapped_copies(mods):
         assert got.shape == ref.shape and torch.equal(got, ref)
 
 
+def test_style_features_rows_match_separate_kernels(mods):
+    """isx_nst_style_features (statistics + Gram upper triangles computed on the workspace and written straight into the
+    caller's rows) == the per-layer isx_bn_stats_fwd / isx_gram_fwd results, 4 and 5 style taps, strided rows."""
+    from iris_b200 import features, synthetic
+    import iris_b200
+
+    E = mods["engine"]
+    dev = torch.device("cuda:0")
+    fr, _ = synthetic.synthetic_batch([1, 2, 3], 64, 96)
+    x = torch.from_numpy(fr).to(dev)
+    for layers in (["relu1_1", "relu2_1", "relu3_1", "relu4_1"], ["relu1_1", "relu2_1", "relu3_1", "relu4_1", "relu5_1"]):
+        net = iris_b200.VGG19(content_layers=[], style_layers=layers, weights=mods["weights"])
+        chans = [64, 128, 256, 512, 512][:len(layers)]
+        D = features.feature_dim(chans)
+        big = torch.full((3, D + 7), float("nan"), device=dev)
+        rows = features.style_features_batch(net, x, out=big[:, :D])
+        _, _, sf, _ = net.features_nhwc(x, full=False)
+        cols = []
+        for f in sf:
+            m, sd = E.stats_of(f)
+            cols += [m, sd]
+        for f in sf:
+            G = E.gram_of(f)
+            iu = torch.triu_indices(G.shape[-1], G.shape[-1], device=dev)
+            cols.append(G[:, iu[0], iu[1]])
+        ref = torch.cat(cols, dim=1)
+        assert rows.shape == ref.shape == (3, D)
+        assert torch.equal(rows, ref) and bool(torch.isnan(big[:, D:]).all())
+
+
 def test_feature_extraction_matches_oracle(mods):
     """classifiers.py:71 style features (mean | unbiased std per channel -> 1920 floats) + Gram upper triangles."""
     from iris_b200 import features, synthetic

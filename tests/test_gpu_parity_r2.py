@@ -9,7 +9,9 @@ operands are rounded to bf16 (tests/golden/make_calibration.py -> calibration_r2
 bench frames: 0.19-0.26 under 2^-9 noise).  No bf16-operand implementation can meet 1e-2 there, so every trajectory
 test asserts
     (1) exact evaluation counts and the first losses within 1-2 %,
-    (2) the image after a FIXED SHORT count (10 evaluations, before the amplification) within 1e-2 of the oracle, and
+    (2) the image after a FIXED SHORT count (10 evaluations, before most of the amplification) within 1e-2 of the
+        oracle -- or within 1.5 x what the oracle's own bf16-operand run differs by at that count, where that is larger
+        (32x32 uniform noise) --, and
     (3) the final image within max(1e-2, 1.5 x the reference algorithm's own sensitivity) of the REFERENCE's result.
 Golden vectors: tests/golden/nst_traj.npz / nst_traj_r2.npz (unmodified reference, make_golden*.py)."""
 import json
@@ -115,16 +117,18 @@ def test_golden_trajectory_calibrated(mods, traj, calib, tag):
     # (2) fixed short count: the image entering evaluation 10 vs the oracle's (per-evaluation copies; the reference's
     # own CPU x_hist aliases the final image, so the pinned oracle supplies them)
     _, oxh, _, _ = O.nst(c, s, mods["weights"], keep_hist=True, **kw)
+    _, exh, _, _ = O.nst(c, s, mods["weights"], keep_hist=True, operand_dtype=torch.bfloat16, **kw)
     mae10 = float((xh[10] - oxh[10]).abs().mean())
+    emu10 = float((exh[10] - oxh[10]).abs().mean())     # the reference algorithm with bf16 conv operands, same count
     moved10 = float((oxh[10] - c).abs().mean())
     # (3) final image vs the REFERENCE, calibrated
     mae = float((x - ref_x).abs().mean())
     bound = _bound(calib, tag)
-    print("%s: evals %d  MAE@10 %.5f (moved %.5f)  final MAE %.5f  bound %.5f (sens bf16 %.4f noise %s) moved %.4f  s_final %.3g/%.3g"
-          % (tag, len(sh), mae10, moved10, mae, bound, calib[tag]["sens_bf16"],
+    print("%s: evals %d  MAE@10 %.5f (bf16-operand oracle %.5f, moved %.5f)  final MAE %.5f  bound %.5f (sens bf16 %.4f noise %s) moved %.4f  s_final %.3g/%.3g"
+          % (tag, len(sh), mae10, emu10, moved10, mae, bound, calib[tag]["sens_bf16"],
              ["%.4f" % v for v in calib[tag]["sens_noise"]], calib[tag]["moved"], sh[-1], rs[-1]))
     assert torch.equal(xh[0], c)
-    assert mae10 <= 1e-2 and mae10 <= 0.6 * moved10
+    assert mae10 <= max(1e-2, 1.5 * emu10) and mae10 <= 0.6 * moved10
     assert mae <= bound
     assert np.isfinite(sh).all() and float(x.min()) >= 0.0 and float(x.max()) <= 1.0
 
