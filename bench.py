@@ -300,7 +300,7 @@ def nst_leg(args, dev, vgg, c_dev, s_dev, BN_loss, independent, K, Wm, world, ra
                    epochs=prefill + K + Wm + 40, independent=independent, history_size=hist,
                    history_dtype=torch.bfloat16 if args.history_bf16 else torch.float32, c_mask=c_mask, s_mask=s_mask)
         if args.streams > 1 and independent:
-            job = pipelines.NstJobGroup(c_dev, s_dev, vgg, dev, streams=args.streams, **jkw)
+            job = pipelines.NstJobGroup(c_dev, s_dev, vgg, dev, streams=args.streams, overlap=args.overlap, **jkw)
             subjobs = job.jobs
         else:
             job = pipelines.NstJob(c_dev, s_dev, vgg, dev, **jkw)
@@ -428,6 +428,8 @@ def main():
     ap.add_argument("--no-features", action="store_true")
     ap.add_argument("--no-prefill", action="store_true", help="do not fill the L-BFGS history before timing (diagnostic)")
     ap.add_argument("--streams", type=int, default=1, help="sub-batches on separate CUDA streams (overlap L-BFGS and convs)")
+    ap.add_argument("--overlap", action="store_true", help="with --streams > 1: L-BFGS passes on low-priority streams beside the convs")
+    ap.add_argument("--smem-reserve-kb", type=int, default=0, help="shared memory per SM the persistent conv CTAs leave free")
     ap.add_argument("--history-bf16", action="store_true", help="opt-in: store the L-BFGS (s, y) history in bf16")
     ap.add_argument("--feature-images", type=int, default=512, help="images per GPU of the feature-extraction leg")
     ap.add_argument("--e2e-evals", type=int, default=300, help="evaluations of the end-to-end job (BASELINE config[1]: 300)")
@@ -460,6 +462,8 @@ def main():
     lib = _lib.load()
     lib.isx_launch_count.restype = ctypes.c_ulonglong
     _lib.call("isx_device_check", local)
+    if args.smem_reserve_kb:
+        lib.isx_set_option(b"smem_reserve_kb", int(args.smem_reserve_kb))
 
     def finish():
         if world > 1:
@@ -541,7 +545,7 @@ def main():
     e2e = None
     e2e_hist = None
     nkw = dict(BN_loss=BN_loss, c_loss_weight=1.0, s_loss_weight=s_weight, vgg=vgg, use_tqdm=False, device=str(dev),
-               independent=independent, streams=args.streams, c_mask=c_mask, s_mask=s_mask,
+               independent=independent, streams=args.streams, overlap=args.overlap, c_mask=c_mask, s_mask=s_mask,
                history_dtype=torch.bfloat16 if args.history_bf16 else torch.float32)
     if not args.no_e2e:
         x_host = torch.empty_like(c_host).pin_memory()
@@ -686,6 +690,7 @@ def main():
                    "untimed_prefill_ticks": r["prefill"] + Wm, "problems": r["problems"],
                    "problems_still_running_at_end": r["problems_running"],
                    "history_dtype": "bf16" if args.history_bf16 else "f32", "streams": args.streams,
+                   "overlap": bool(args.overlap), "smem_reserve_kb": args.smem_reserve_kb,
                    "flops_per_image_step": flops,
                    "model_tflops": value * flops / 1e12 / world},
         "e2e": e2e, "e2e_default_api": e2e_hist, "secondary": feat, "secondary_5tap": feat5, "gpu_launches": r["launches"],

@@ -261,7 +261,9 @@ unsigned long long isx_launch_count(void);
 /* kernel-selection knobs (tests, experiments; defaults in parentheses): "c64" (1) resident-weight kernel for the 64->64
  * layers, "halo2" (1) halo-patch pair kernel for the mid layers, "tail_n" (1) taps-in-N image-gradient tail -- 0 sends
  * the call to the generic kernel, 2 ("c64", "halo2") forces the kernel on every applicable call; "c64_slots",
- * "halo2_stages": ring depths (0 = as many as fit).  Unknown names return non-zero. */
+ * "halo2_stages": ring depths (0 = as many as fit); "smem_reserve_kb" (0): shared memory per SM the persistent conv CTAs leave
+ * free (<= 22) so that one TMEM-free streaming CTA of another stream -- the L-BFGS history passes -- can be resident beside
+ * them.  Unknown names return non-zero. */
 int isx_set_option(const char* name, int value);
 int isx_prof_enable(int on);
 int isx_prof_collect(double* out, int n_out);

@@ -224,6 +224,7 @@ extern int g_isx_c64_slots;
 extern int g_isx_halo2;
 extern int g_isx_tail_n;
 extern int g_isx_halo2_stages;
+extern int g_isx_smem_reserve_kb;
 }
 extern "C" int isx_set_option(const char* name, int value) {
   ISX_REQUIRE(name != nullptr, "isx_set_option: null name");
@@ -232,5 +233,6 @@ extern "C" int isx_set_option(const char* name, int value) {
   if (strcmp(name, "halo2") == 0) { isx::g_isx_halo2 = value; return 0; }
   if (strcmp(name, "halo2_stages") == 0) { isx::g_isx_halo2_stages = value; return 0; }
   if (strcmp(name, "c64_slots") == 0) { isx::g_isx_c64_slots = value; return 0; }
+  if (strcmp(name, "smem_reserve_kb") == 0) { isx::g_isx_smem_reserve_kb = value; return 0; }
   ISX_REQUIRE(false, "isx_set_option: unknown option '%s'", name);
 }

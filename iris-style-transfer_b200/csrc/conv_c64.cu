@@ -380,6 +380,7 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+extern int g_isx_smem_reserve_kb;
 int g_isx_c64_slots = 0;  // isx_set_option("c64_slots"): halo ring depth override (0 = as many of 4 as fit)
 
 template <int BN, int EPI>
@@ -399,7 +400,8 @@ static int launch_c64(const ConvArgs& a, cudaStream_t stream) {
   p.dx_nchw = a.dx_nchw; p.xc = a.xc; p.in_mask = a.in_mask; p.mask_b = a.mask_b;
   int hs = g_isx_c64_slots > 0 ? g_isx_c64_slots : 4;
   C64Layout L = c64_layout<BN, EPI>(hs, p.use_mask, p.use_gram, p.fuse_pool);
-  while (hs > 2 && 1024 + L.total > 227 * 1024) { --hs; L = c64_layout<BN, EPI>(hs, p.use_mask, p.use_gram, p.fuse_pool); }
+  const int cap = (227 - std::max(0, std::min(g_isx_smem_reserve_kb, 22))) * 1024;  // see conv_halo.cu
+  while (hs > 2 && 1024 + L.total > cap) { --hs; L = c64_layout<BN, EPI>(hs, p.use_mask, p.use_gram, p.fuse_pool); }
   ISX_REQUIRE(1024 + L.total <= 227 * 1024, "conv_c64: %d B of shared memory exceed 227 KB", 1024 + L.total);
   p.halo_slots = hs;
   // At least 204 KB, so that no other TMEM-using CTA of this library (the conv1_1 head needs 29 KB, everything else more)

@@ -49,8 +49,12 @@ class NstJob:
 
     def __init__(self, c_img, s_img, vgg, dev, clone_content=True, BN_loss=True, c_loss_weight=1.0,
                  s_loss_weight=1.0, lr=1.0, epochs=200, independent=False, history_size=100, x_init=None,
-                 history_dtype=torch.float32, c_mask=None, s_mask=None):
+                 history_dtype=torch.float32, c_mask=None, s_mask=None, lbfgs_stream=None):
         c_img, c_unbatched = _prep_images(c_img, dev)
+        # optional second stream for the L-BFGS passes of every tick (NstJobGroup: a low-priority stream, so that the
+        # HBM-bound history passes of this sub-batch run beside the tensor-bound convolutions of another one)
+        self.aux = lbfgs_stream
+        self._lbfgs_done = None
         s_img, s_unbatched = _prep_images(s_img, dev)
         self.c_unbatched = c_unbatched
         if clone_content:
@@ -138,17 +142,36 @@ class NstJob:
         _lib.call("isx_lbfgs_init", self.state, P, _lib.stream_ptr())
         _lib.call("isx_clamp01", self.x, _lib.i64(self.x.numel()), _lib.stream_ptr())  # pipelines.py:82 (first closure)
 
-    def _tick_body(self):
-        self.eng.eval(self.x, self.grad)
+    def _lbfgs(self):
         _lib.call("isx_lbfgs_tick", self.x, self.grad, self.grad_prev, self.Sh, self.Yh, self.state, self.mats,
                   self.scratch, self.eng.loss_c, self.eng.loss_s, self.ipp, self.P, _lib.i64(self.N),
                   ctypes.byref(self.cfg), self.hist_c, self.hist_s, self.ticks, _lib.stream_ptr())
 
+    def _tick_body(self):
+        self.eng.eval(self.x, self.grad)
+        self._lbfgs()
+
+    def sync_lbfgs(self):
+        """Make the current stream wait for the L-BFGS passes issued on the auxiliary stream (no-op without one)."""
+        if self._lbfgs_done is not None:
+            torch.cuda.current_stream().wait_event(self._lbfgs_done)
+
     def tick(self):
         if self._graph is not None:
             self._graph.replay()
-        else:
+        elif self.aux is None:
             self._tick_body()
+        else:
+            main = torch.cuda.current_stream()
+            self.sync_lbfgs()                      # x of this evaluation = the previous tick's update
+            self.eng.eval(self.x, self.grad)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(self.aux):
+                self.aux.wait_event(ev)
+                self._lbfgs()
+                self._lbfgs_done = torch.cuda.Event()
+                self._lbfgs_done.record(self.aux)
         self.ticks += 1
 
     def enable_graph(self):
@@ -165,17 +188,19 @@ class NstJob:
 
     def evals_done(self):
         """Per-problem evaluation counts (0 while a problem is still running); one small D2H read."""
+        self.sync_lbfgs()
         _lib.call("isx_lbfgs_done_flags", self.state, self.P, self.done, _lib.stream_ptr())
         return self.done.cpu()
 
     def history_counts(self):
         """Per-problem number of (y, s) pairs currently in the L-BFGS ring (one small D2H read)."""
         out = torch.zeros(self.P, device=self.x.device, dtype=torch.int32)
+        self.sync_lbfgs()
         _lib.call("isx_lbfgs_history_counts", self.state, self.P, out, _lib.stream_ptr())
         return out.cpu()
 
     def finish(self):
-        evals = self.evals_done()
+        evals = self.evals_done()      # (waits for the auxiliary stream)
         n_evals = int(evals.max().item()) if bool((evals > 0).all().item()) else self.ticks
         hc = self.hist_c[:n_evals].cpu()
         hs = self.hist_s[:n_evals].cpu()
@@ -193,14 +218,17 @@ class NstJobGroup:
     sub-jobs are issued round-robin, so the HBM-bound L-BFGS passes of one sub-batch overlap the tensor-core
     convolutions of another (the two kernel families stress different units)."""
 
-    def __init__(self, c_img, s_img, vgg, dev, streams=2, **kw):
+    def __init__(self, c_img, s_img, vgg, dev, streams=2, overlap=False, **kw):
         if not kw.get("independent", False):
             raise ValueError("multi-stream execution needs independent=True (one problem per image)")
         B = c_img.shape[0]
         n = max(1, min(int(streams), B))
         bounds = [(B * i) // n for i in range(n + 1)]
         main = torch.cuda.current_stream(dev)
-        self.streams = [torch.cuda.Stream(dev) for _ in range(n)]
+        # overlap: evaluations on HIGH-priority streams, the L-BFGS passes of each sub-batch on its own LOW-priority
+        # stream; with isx_set_option("smem_reserve_kb") the streaming CTAs are resident beside the persistent conv CTAs
+        self.streams = [torch.cuda.Stream(dev, priority=-1 if overlap else 0) for _ in range(n)]
+        self.aux = [torch.cuda.Stream(dev, priority=0) if overlap else None for _ in range(n)]
         self.jobs: List[NstJob] = []
         x_init = kw.pop("x_init", None)
         c_mask, s_mask = kw.pop("c_mask", None), kw.pop("s_mask", None)
@@ -218,7 +246,7 @@ class NstJobGroup:
                 si = s_img[lo:hi] if s_batched else s_img
                 xi = x_init[lo:hi] if x_init is not None else None
                 self.jobs.append(NstJob(c_img[lo:hi], si, vgg, dev, x_init=xi, c_mask=part(c_mask, lo, hi, True),
-                                        s_mask=part(s_mask, lo, hi, s_batched), **kw))
+                                        s_mask=part(s_mask, lo, hi, s_batched), lbfgs_stream=self.aux[i], **kw))
         self.max_ticks = self.jobs[0].max_ticks
         self.epochs = self.jobs[0].epochs
         self.P = B
@@ -234,13 +262,17 @@ class NstJobGroup:
 
     def join(self, dev):
         main = torch.cuda.current_stream(dev)
-        for st in self.streams:
+        for st, ax in zip(self.streams, self.aux):
             main.wait_stream(st)
+            if ax is not None:
+                main.wait_stream(ax)
 
     def fork(self, dev):
         main = torch.cuda.current_stream(dev)
-        for st in self.streams:
+        for st, ax in zip(self.streams, self.aux):
             st.wait_stream(main)
+            if ax is not None:
+                ax.wait_stream(main)
 
     def evals_done(self):
         outs = []
@@ -383,6 +415,7 @@ def nst(c_img: torch.Tensor,
         x_init: Optional[torch.Tensor] = None,
         history_dtype: torch.dtype = torch.float32,
         streams: int = 1,
+        overlap: bool = False,
         cuda_graph: Optional[bool] = None,
         c_mask: Optional[torch.Tensor] = None,
         s_mask: Optional[torch.Tensor] = None,
@@ -398,6 +431,9 @@ def nst(c_img: torch.Tensor,
       x_init        replaces torch.rand (pipelines.py:54) when clone_content is False.
       streams       > 1 (with independent=True): split the batch into that many sub-batches on separate CUDA
                     streams so L-BFGS passes (HBM-bound) overlap convolutions (tensor-bound) of another sub-batch.
+      overlap       (with streams > 1) run each sub-batch's L-BFGS passes on a low-priority stream of its own so that they are
+                    resident beside the persistent conv CTAs of the other sub-batches (needs the conv kernels to leave some
+                    shared memory free: _lib.call("isx_set_option", b"smem_reserve_kb", 16)).
       c_mask/s_mask iris masks [B|1,1,H,W] of the content / style frames: the style loss then compares MASK-WEIGHTED Gram
                     matrices GramMatrix(F * m_l), m_l = the mask average-pooled to layer l (row G' of SURVEY.md §8a; the
                     reference only has the dormant hooks vgg.py:84-85 / pipelines.py:83).  All-ones masks == plain Gram.
@@ -424,7 +460,7 @@ def nst(c_img: torch.Tensor,
         if streams > 1 and independent and c_img.dim() == 4 and c_img.shape[0] > 1:
             c_dev, _ = _prep_images(c_img, dev)
             s_dev = s_img.detach().to(dev, torch.float32)
-            job = NstJobGroup(c_dev, s_dev, vgg, dev, streams=streams, **kw)
+            job = NstJobGroup(c_dev, s_dev, vgg, dev, streams=streams, overlap=overlap, **kw)
         else:
             job = NstJob(c_img, s_img, vgg, dev, **kw)
         B_all = c_img.shape[0] if c_img.dim() == 4 else 1

@@ -147,7 +147,10 @@ def test_iris224_bn_coupled_batch(mods, traj2, calib):
         tag, len(sh), len(rs), mae, _bound(calib, tag), calib[tag]["moved"], sh[-1], rs[-1]))
     assert len(sh) == len(rs) == 40
     assert sh[0] == pytest.approx(rs[0], rel=1e-2) and sh[1] == pytest.approx(rs[1], rel=2e-2)
-    assert ch[1] == pytest.approx(rc[1], rel=5e-2)
+    # (the content loss right after the first, 1/|g|_1-scaled step is 3e-12 in fp32 -- far below what bf16 features can
+    # resolve: one flipped bf16 ulp in 1e4 elements already gives 1e-7 -- so it is compared at the end of the run only)
+    assert ch[-1] == pytest.approx(rc[-1], rel=0.5)
+    assert mae <= 1e-2       # the strict north-star bar holds on the drivers' own configuration
     assert mae <= _bound(calib, tag)
 
 
