@@ -246,11 +246,34 @@ int isx_mask_bbox(const float* x, const int64_t* seg, int label, int use_thresho
  * (rgb_to_grayscale, …2019.py:112); the single result channel is replicated dst_c times (…2019.py:79). */
 int isx_resize_bilinear_aa(const float* src, int src_c, int SH, int SW, const int32_t* src_bbox, float* dst, int dst_c,
                            int DH, int DW, int B, isx_stream stream);
+/* …2019.py:64-79 / …2020.py:78-100 for a whole batch in one launch: (frame * mask)[bbox] -> Resize((DH,DW)) bilinear
+ * antialiased -> replicated to dst_c channels.  frames fp32 [B,1,H,W], mask uint8 [B,1,H,W], bbox int32 [B,4] (ragged);
+ * dst fp32 [B,dst_c,DH,DW] must be zero-initialised by the caller: a frame whose bbox is empty is left untouched. */
+int isx_crop_resize_masked(const float* frames, const uint8_t* mask, const int32_t* bbox, float* dst, int dst_c, int DH,
+                           int DW, int B, int H, int W, isx_stream stream);
 /* ---- K9: composite (…2019.py:111-130, …2020.py:121-139): gray(new_iris) -> Resize(bbox shape) -> * mask ->
  * frames[bbox] = frames[bbox] * ~mask + new, in place.  new_iris fp32 [B,src_c,SH,SW], frames fp32 [B,1,H,W],
  * mask uint8 [B,1,H,W], bbox int32 [B,4]. */
 int isx_composite(const float* new_iris, int src_c, int SH, int SW, float* frames, const uint8_t* mask,
                   const int32_t* bbox, int B, int H, int W, isx_stream stream);
+
+/* ---- mask producer: RITnet (models/ritnet/ritnet.py:8-223; call sites iris_style_transfer_openeds2019.py:155,
+ * data_preprocessing.py:165, pipelines.py:133-141) for a batch of frames in one call --------------------------------
+ * x fp32 [B,1,H,W] in [0,1] (H, W multiples of 16) -> labels int64 [B,H,W] in {0,1,2,3} (2 = iris), optionally the logits
+ * fp32 [B,4,H,W].  RITnet_transform (ritnet.py:79-98) runs on the device, bit-exact with the reference's OpenCV round trip:
+ * gamma_lut = the 256 uint8 values np.uint8(255 * linspace(0,1,256)**0.8) (ritnet.py:72,93-94), norm_lut = the 256 floats
+ * ToDtype(scale)/Normalize(0.5,0.5) map uint8 to (ritnet.py:73-77), CLAHE(clipLimit 1.5, 8x8 tiles) restated from OpenCV.
+ * params: isx_ritnet_param_floats() floats = the DenseNet2D state dict in network order: per down block conv1, conv21,
+ * conv22, conv31, conv32 (each weight as [kh*kw][Cin][32] then bias[32]) then the BatchNorm folded to scale[32], shift[32];
+ * per up block conv11, conv12, conv21, conv22; then out_conv1 weight [4][32] and bias[4].  fp32 throughout. */
+/* RITnet_transform alone (any H, W >= 8): x fp32 [B,1,H,W] -> out fp32 [B,1,H,W], the network's input */
+int64_t isx_ritnet_transform_workspace_bytes(int B, int H, int W);
+int isx_ritnet_transform(const float* x, const uint8_t* gamma_lut, const float* norm_lut, void* workspace, float* out, int B,
+                         int H, int W, isx_stream stream);
+int64_t isx_ritnet_param_floats(void);
+int64_t isx_ritnet_workspace_bytes(int B, int H, int W);
+int isx_ritnet_forward(const float* x, const float* params, const uint8_t* gamma_lut, const float* norm_lut, void* workspace,
+                       int64_t* labels, float* logits, int B, int H, int W, isx_stream stream);
 
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------
  * isx_launch_count: kernels launched by this library since load.  isx_prof_enable(1) brackets every launch

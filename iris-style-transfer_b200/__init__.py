@@ -11,6 +11,8 @@ try:  # torch-dependent surface (the ctypes layer and the synthetic generators i
     from .utils import (ContentLoss_L2, GramMatrix, StyleLoss_BN, StyleLoss_Gram, crop_image,  # noqa: F401
                         style_features)
     from .vgg import VGG19, random_vgg19_weights  # noqa: F401
-    from . import features, sharding  # noqa: F401
+    from .frames import stylize_frames  # noqa: F401
+    from .ritnet import RITnet  # noqa: F401
+    from . import features, frames, sharding  # noqa: F401
 except ImportError:  # pragma: no cover
     pass

@@ -525,16 +525,18 @@ def mask_and_crop_iris(x: torch.Tensor,
                        seg: Optional[torch.Tensor] = None,
                        ) -> tuple[torch.Tensor, torch.Tensor, int, int, int, int]:
     """pipelines.py:112-166: m = (ritnet(x) == 2) * (x <= glint_threshold); x*m; trim to the bbox of the nonzero
-    pixels; repeat to 3 channels.  The segmenter is the caller's (the mask PRODUCER is outside the accelerated
-    path): pass `ritnet` (any callable returning the (1,H,W) label map) or the label map itself as `seg`.
+    pixels; repeat to 3 channels.  `ritnet`: any callable returning the (1,H,W) label map -- iris_b200.RITnet (the
+    segmenter on the device), the reference's RITnet, ... -- default = iris_b200.RITnet() like pipelines.py:133-135; or
+    pass the label map itself as `seg`.
     Returns (x (3,h,w) fp32, m (1,h,w) bool, x_min, y_min, x_max, y_max) like the reference."""
     from .utils import _bbox_of
 
     x = x.to(device)
     if seg is None:
         if ritnet is None:
-            raise ValueError("mask_and_crop_iris: pass `ritnet` (a callable segmenter) or `seg` (its label map); "
-                             "the RITnet model itself is not part of this package")
+            from .ritnet import RITnet
+
+            ritnet = RITnet()  # pipelines.py:133-135: the default loads models/weights/ritnet_pretrained.pkl
         if hasattr(ritnet, "to"):
             ritnet.to(device)
         seg = ritnet(x)
@@ -558,15 +560,18 @@ def iris_masks_and_bboxes(frames: torch.Tensor, segs: torch.Tensor, glint_thresh
 
 
 def crop_resize_irises(frames: torch.Tensor, masks: torch.Tensor, bboxes: torch.Tensor, size=(224, 224)):
-    """…2019.py:66-79: (frame * mask)[bbox] -> Resize(size) (bilinear, antialias) -> repeat to 3 channels,
-    for the whole batch at once.  frames [B,1,H,W] fp32, masks uint8 [B,1,H,W], bboxes int32 [B,4]."""
+    """…2019.py:66-79: (frame * mask)[bbox] -> Resize(size) (bilinear, antialias) -> repeat to 3 channels, for the whole
+    batch in ONE launch (isx_crop_resize_masked: the mask multiply happens on the source taps inside the kernel).
+    frames [B,1,H,W] fp32, masks uint8 [B,1,H,W], bboxes int32 [B,4]."""
+    if not frames.is_cuda:
+        raise _lib.IsxError("iris_b200 needs CUDA tensors (B200); there is no CPU path")
     B, _, H, W = frames.shape
-    xm = (frames * masks).contiguous()  # masking multiply: plumbing-level elementwise on the caller's tensors
     # zero-initialised: a frame WITHOUT iris pixels (bbox sentinel row_max = -1) yields an all-zero crop, never
     # uninitialised memory; callers that must skip such frames test `bboxes[:, 2] < 0` (mask_and_crop_iris raises)
     out = torch.zeros(B, 3, size[0], size[1], device=frames.device, dtype=torch.float32)
     with torch.cuda.device(frames.device):
-        _lib.call("isx_resize_bilinear_aa", xm, 1, H, W, bboxes.contiguous(), out, 3, size[0], size[1], B,
+        _lib.call("isx_crop_resize_masked", frames.detach().to(torch.float32).contiguous(),
+                  masks.to(torch.uint8).contiguous(), bboxes.to(torch.int32).contiguous(), out, 3, size[0], size[1], B, H, W,
                   _lib.stream_ptr())
     return out
 

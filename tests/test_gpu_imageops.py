@@ -110,3 +110,55 @@ def test_composite_batched_ragged_bboxes(mods):
         m = (segs[i] == 2) & (frames[i] <= np.float32(0.8))
         ref = O.composite(frames[i], new[i].cpu().numpy(), m, bbox[i].tolist())
         np.testing.assert_allclose(out[i], ref, atol=1e-5)
+
+
+def test_stylize_frames_end_to_end(mods):
+    """The drivers' per-batch body (…2019.py:64-79,93-100,111-137) as ONE call: masks / bboxes bit-exact, the 224x224
+    crops and the composite equal to the oracle's per-image chain fed with the same new irises, frames without an iris
+    returned untouched, losses decreasing."""
+    ib, O = mods
+    H, W = 120, 96
+    frames, segs = ib.synthetic.synthetic_batch([21, 22, 23], H, W)
+    segs[1] = 0                                            # frame 1: the segmenter found no iris
+    sfr, sseg = ib.synthetic.synthetic_eye(31, H, W)
+    vgg = ib.VGG19(weights="random", seed=0)
+    ft = torch.from_numpy(frames)
+    # style iris prepared like …2020.py:238-249: masked, cropped, resized, UNBATCHED (1,h,w)
+    sm, sb = ib.iris_masks_and_bboxes(torch.from_numpy(sfr)[None].cuda(), torch.from_numpy(sseg)[None].cuda())
+    s_iris = ib.crop_resize_irises(torch.from_numpy(sfr)[None].cuda(), sm, sb, size=(64, 64))[0, :1]
+    out, info = ib.stylize_frames(ft, s_iris, segs=torch.from_numpy(segs), vgg=vgg, s_loss_weight=1e4, epochs=20, size=(64, 64))
+    assert info["valid"].tolist() == [True, False, True] and info["evals"] == 20
+    assert tuple(out.shape) == (3, 1, H, W) and out.is_cuda
+    got = out.cpu().numpy()
+    assert np.array_equal(got[1], frames[1])               # untouched
+    new = info["irises"].cpu().numpy()                     # the NST results of the two valid frames
+    for k, i in enumerate([0, 2]):
+        m = (segs[i] == 2) & (frames[i] <= np.float32(0.8))
+        xc, mc, *bb = O.mask_and_crop(frames[i], segs[i])
+        assert info["bboxes"][i].tolist() == bb and np.array_equal(info["masks"][i].cpu().numpy().astype(bool), m)
+        ref = O.composite(frames[i], new[k], m, bb)
+        np.testing.assert_allclose(got[i], ref, atol=1e-5)
+        assert np.abs(got[i] - frames[i])[m].mean() > 1e-4   # the iris texture did change
+    sh = info["s_loss_hist"]
+    assert np.isfinite(sh).all() and sh[-1] < sh[0]
+    # segmenter callable instead of label maps
+    out2, info2 = ib.stylize_frames(ft, s_iris, segmenter=lambda x: torch.from_numpy(segs).cuda(), vgg=vgg, s_loss_weight=1e4,
+                                    epochs=20, size=(64, 64))
+    assert float((out2 - out).abs().max()) < 1e-4
+
+
+def test_crop_resize_masked_matches_oracle_resize(mods):
+    """isx_crop_resize_masked (mask multiply on the source taps inside the kernel) == oracle: (frame*mask)[bbox] -> AA resize,
+    for down- and up-scaling windows and a size that needs more taps than the shared-memory table holds."""
+    ib, O = mods
+    frames, segs = ib.synthetic.synthetic_batch([5, 6], 640, 400)
+    ft, st = torch.from_numpy(frames).cuda(), torch.from_numpy(segs).cuda()
+    mask, bbox = ib.iris_masks_and_bboxes(ft, st)
+    for size in ((224, 224), (300, 64), (7, 5)):
+        crops = ib.crop_resize_irises(ft, mask, bbox, size=size).cpu().numpy()
+        for i in range(2):
+            m = (segs[i] == 2) & (frames[i] <= np.float32(0.8))
+            x0, y0, x1, y1 = bbox[i].tolist()
+            ref = O.resize_bilinear_aa((frames[i] * m)[:, x0:x1 + 1, y0:y1 + 1], size[0], size[1])
+            np.testing.assert_allclose(crops[i, :1], ref, atol=1e-5)
+            assert np.array_equal(crops[i, 0], crops[i, 2])

@@ -262,7 +262,13 @@ def test_nst_unbatched_content(mods, traj2, tag, BN, s4d):
     moved = float((ref_x - c1[0]).abs().mean())
     print("%s: s0 %.5g/%.5g s1 %.5g/%.5g final MAE %.5f moved %.5f" % (tag, sh[0], rs[0], sh[1], rs[1], mae, moved))
     assert sh[0] == pytest.approx(rs[0], rel=1e-2) and sh[1] == pytest.approx(rs[1], rel=2e-2)
-    assert mae <= max(1e-2, 0.3 * moved)
+    # 48x64 uniform noise: calibrated like the golden trajectories (module docstring), sensitivity measured live
+    O = mods["O"]
+    okw = dict(BN_loss=BN, s_loss_weight=1e4, epochs=20, keep_hist=False)
+    xe, _, _, _ = O.nst(c1[0], s1 if s4d else s1[0], mods["weights"], operand_dtype=torch.bfloat16, **okw)
+    sens = float((xe - ref_x).abs().mean())
+    print("   bf16-operand oracle vs reference: %.5f" % sens)
+    assert mae <= max(1e-2, 1.5 * sens) and mae <= 0.5 * moved
 
 
 def test_nst_streams_with_per_image_masks(mods):
