@@ -275,6 +275,21 @@ int64_t isx_ritnet_workspace_bytes(int B, int H, int W);
 int isx_ritnet_forward(const float* x, const float* params, const uint8_t* gamma_lut, const float* norm_lut, void* workspace,
                        int64_t* labels, float* logits, int B, int H, int W, isx_stream stream);
 
+/* ---- classifier heads (models/classifiers/classifiers.py:3-72; iris_classification.py:66-71, …2019.py:82-84) -----------
+ * A Linear layer over a batch of M <= 256 eyes is a weight-streaming tcgen05 GEMM out^T[N,M] = W'[N,K'] . X'[M,K']^T with
+ * K' = K + 64: column K of X' is 1 and column K of W' the bias (K a multiple of 64).  Packed operands are bf16:
+ *   isx_linear_pack        fp32 W [N,K] (nn.Linear layout), bias [N] -> W' [Npad, K+64] (rows >= N zero), once per model
+ *   isx_rows_pack          fp32 rows [M,K] (row stride ld_src)      -> X' [Mpad, K+64], Mpad a multiple of 64
+ *   isx_pool7_flatten_pack pool5 bf16 NHWC [B,h,w,C] -> AdaptiveAvgPool2d(7,7) + Flatten (c*49+i*7+j) -> X' [Mpad, 49C+64]
+ *   isx_linear_fwd         out^T bf16 [Npad, Mpad] = relu?(W' . X'^T)
+ *   isx_transpose_pack     out^T [N, Mpad] -> the next layer's X' [Mpad, N+64]; isx_transpose_out -> fp32 logits [M, N] */
+int isx_linear_pack(const float* W, const float* bias, int N, int K, int Npad, isx_bf16* dst, isx_stream stream);
+int isx_rows_pack(const float* src, int64_t ld_src, int M, int K, int Mpad, isx_bf16* dst, isx_stream stream);
+int isx_pool7_flatten_pack(const isx_bf16* pool5, int B, int h, int w, int C, int Mpad, isx_bf16* dst, isx_stream stream);
+int isx_linear_fwd(const isx_bf16* Xp, const isx_bf16* Wp, isx_bf16* outT, int Mpad, int Npad, int Kp, int relu, isx_stream stream);
+int isx_transpose_pack(const isx_bf16* srcT, int N, int Mpad, int M, isx_bf16* dst, isx_stream stream);
+int isx_transpose_out(const isx_bf16* srcT, int N, int Mpad, int M, float* dst, isx_stream stream);
+
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------
  * isx_launch_count: kernels launched by this library since load.  isx_prof_enable(1) brackets every launch
  * of the tensor-core conv (family 0), Gram (1) and L-BFGS pass (2) kernels with CUDA events on the launching

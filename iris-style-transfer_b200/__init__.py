@@ -13,6 +13,7 @@ try:  # torch-dependent surface (the ctypes layer and the synthetic generators i
     from .vgg import VGG19, random_vgg19_weights  # noqa: F401
     from .frames import stylize_frames  # noqa: F401
     from .ritnet import RITnet  # noqa: F401
+    from .classifiers import Classifier1, Classifier2  # noqa: F401
     from . import features, frames, sharding  # noqa: F401
 except ImportError:  # pragma: no cover
     pass

@@ -118,3 +118,28 @@ def extract_features_sharded(vgg: VGG19, images, batch: int = 32, gram: bool = T
         row += xd.shape[0]
         rows.flush(row)
     return rows.finish()
+
+
+@torch.no_grad()
+def cache_classifier_inputs(vgg: VGG19, images, batch: int = 32, device=None):
+    """What the frozen-VGG classifier training (iris_classification.py:59-108) needs from the VGG, computed ONCE instead of
+    once per epoch: for every image the Classifier2 input (mean | unbiased std of the style taps, fp32 [n, 2*sum C_l]) and the
+    Classifier1 input (AdaptiveAvgPool2d(7,7) + Flatten of pool5, bf16 [n, 25088]).  `images`: indexable [n,1|3,H,W]."""
+    n = len(images)
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    chans = [vgg.packed(dev).bias[c].numel() for c in vgg.style_convs]
+    D = feature_dim(chans, gram=False, stats=True)
+    stats = torch.empty(n, D, device=dev, dtype=torch.float32)
+    pool = torch.empty(n, 25088, device=dev, dtype=torch.bfloat16)
+    for lo in range(0, n, batch):
+        xb = torch.as_tensor(images[lo:lo + batch]).to(dev, torch.float32)
+        eng = vgg.run_forward(xb, full=True)
+        b = xb.shape[0]
+        with torch.cuda.device(dev):
+            eng.style_features(stats[lo:lo + b], stats=True, gram=False)
+            p5 = eng.feature_view(1, 4)                       # bf16 NHWC [b,h,w,512]
+            mpad = (b + 63) // 64 * 64
+            xp = torch.empty(mpad, 25088 + 64, device=dev, dtype=torch.bfloat16)
+            _lib.call("isx_pool7_flatten_pack", p5, b, p5.shape[1], p5.shape[2], 512, mpad, xp, _lib.stream_ptr())
+            pool[lo:lo + b] = xp[:b, :25088]
+    return stats, pool
