@@ -2,7 +2,7 @@
  * AnonymWriter/Iris-Style-Transfer.  C ABI: plain device pointers, explicit shapes, a cudaStream_t;
  * every function returns 0 on success and != 0 on failure (text via isx_last_error()).  Nothing
  * here allocates device memory: the caller (e.g. a framework's caching allocator) owns every buffer,
- * including workspaces whose size is queried first.  Thread-compatible; no global device state.
+ * including workspaces whose size is queried first.  Thread-compatible; no process-global mutable state (see isx_create).
  *
  * The reference has no FFI/plugin layer (it is pure Python): each entry point names the reference
  * call site (relative to the reference repo root) whose library kernels it replaces.
@@ -29,6 +29,19 @@ const char* isx_last_error(void);
 int isx_version(void);
 /* fails unless `device` is an sm_100 part: there is no fallback path */
 int isx_device_check(int device);
+
+/* ---- handles ---------------------------------------------------------------------------------
+ * The library keeps NO process-global mutable state.  Kernel-selection options (isx_set_option), the launch counter, the
+ * CUDA-event profiler and the device's SM count (grid sizing) live in a context.  isx_create makes one for `device`,
+ * isx_make_current binds it to the CALLING THREAD (NULL unbinds), isx_destroy frees it; every other entry point works on
+ * the calling thread's current context.  A thread that never binds a handle gets a private default context (device = its
+ * current CUDA device at first use), so single-threaded hosts -- the reference is one Python thread on one stream,
+ * SURVEY.md §8b -- need no handle at all.  Thread-compatible: distinct threads may use distinct handles concurrently. */
+typedef void* isx_handle;
+int isx_create(int device, isx_handle* out);
+int isx_destroy(isx_handle h);
+int isx_make_current(isx_handle h);
+int isx_sm_count(void);   /* SM count the current context sizes its grids with */
 
 /* ---- weights: torchvision vgg19.features Conv2d parameters (models/vgg/vgg.py:43-49) ---------
  * fp32 OIHW [Cout,Cin,3,3] -> bf16 [9][Cout][Cin] for the forward conv and the 180-degree-rotated,
@@ -302,7 +315,8 @@ unsigned long long isx_launch_count(void);
  * "halo2_stages": ring depths (0 = as many as fit); "smem_reserve_kb" (0): shared memory per SM the persistent conv CTAs leave
  * free (<= 22) so that one TMEM-free streaming CTA of another stream -- the L-BFGS history passes -- can be resident beside
  * them.  Unknown names return non-zero. */
-int isx_set_option(const char* name, int value);
+int isx_set_option(const char* name, int value);   /* on the calling thread's current context */
+int isx_get_option(const char* name, int* value);
 int isx_prof_enable(int on);
 int isx_prof_collect(double* out, int n_out);
 

@@ -93,3 +93,30 @@ def call_i64(name: str, *args) -> int:
     fn = getattr(lib, name)
     fn.restype = ctypes.c_int64
     return int(fn(*[_conv(a) for a in args]))
+
+
+class Handle:
+    """isx_create / isx_make_current / isx_destroy: a library context (options, launch counter, profiler, SM count) for
+    hosts that drive several devices or threads.  `with Handle(device): ...` binds it to the calling thread."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        self.h = ctypes.c_void_p()
+        rc = self.lib.isx_create(int(device), ctypes.byref(self.h))
+        if rc != 0:
+            raise IsxError("isx_create failed (rc=%d): %s" % (rc, self.lib.isx_last_error().decode()))
+
+    def make_current(self):
+        self.lib.isx_make_current(self.h)
+
+    def __enter__(self):
+        self.make_current()
+        return self
+
+    def __exit__(self, *exc):
+        self.lib.isx_make_current(ctypes.c_void_p(0))
+
+    def destroy(self):
+        if self.h:
+            self.lib.isx_destroy(self.h)
+            self.h = ctypes.c_void_p(0)

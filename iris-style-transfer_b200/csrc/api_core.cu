@@ -80,74 +80,125 @@ int isx_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint6
 }
 
 // ---------------------------------------------------------------------------------------------
-// launch counter and per-family CUDA-event timing (used by bench.py; off by default)
+// contexts (handles): options, launch counter, per-family CUDA-event timing, SM count
 // ---------------------------------------------------------------------------------------------
 #include <vector>
-unsigned long long g_isx_launches = 0;
 
-namespace {
-struct ProfRec { cudaEvent_t e0, e1; int family; double work; };
-bool g_prof_on = false;
-std::vector<ProfRec> g_prof;
-std::vector<cudaEvent_t> g_pool;
-size_t g_pool_next = 0;
-cudaEvent_t g_open[ISX_PROF_FAMILIES];
-double g_open_work[ISX_PROF_FAMILIES];
-bool g_is_open[ISX_PROF_FAMILIES] = {false, false, false};
-const size_t kMaxRecs = 32768;
-
-cudaEvent_t pool_event() {
-  if (g_pool_next == g_pool.size()) {
-    cudaEvent_t e;
-    cudaEventCreate(&e);
-    g_pool.push_back(e);
+struct IsxProfRec { cudaEvent_t e0, e1; int family; double work; };
+struct IsxProfiler {
+  bool on = false;
+  std::vector<IsxProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+  size_t pool_next = 0;
+  cudaEvent_t open[ISX_PROF_FAMILIES];
+  double open_work[ISX_PROF_FAMILIES];
+  bool is_open[ISX_PROF_FAMILIES] = {false, false, false};
+  cudaEvent_t event() {
+    if (pool_next == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[pool_next++];
   }
-  return g_pool[g_pool_next++];
+};
+static const size_t kMaxRecs = 32768;
+
+static thread_local IsxContext* t_current = nullptr;   // bound with isx_make_current
+static thread_local IsxContext* t_default = nullptr;   // this thread's private default context
+
+static void query_device(IsxContext* c, int device) {
+  c->device = device;
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) c->num_sms = sms;
+  cudaGetLastError();  // a thread without a usable device keeps the B200 default; the first launch reports the real error
 }
-}  // namespace
+
+IsxContext* isx_ctx() {
+  if (t_current) return t_current;
+  if (!t_default) {
+    t_default = new IsxContext();
+    t_default->prof = new IsxProfiler();
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) query_device(t_default, dev);
+    cudaGetLastError();
+  }
+  return t_default;
+}
+
+extern "C" int isx_create(int device, isx_handle* out) {
+  ISX_REQUIRE(out != nullptr, "isx_create: null handle pointer");
+  if (int rc = isx_device_check(device)) return rc;
+  IsxContext* c = new IsxContext();
+  c->prof = new IsxProfiler();
+  query_device(c, device);
+  *out = c;
+  return 0;
+}
+
+extern "C" int isx_destroy(isx_handle h) {
+  IsxContext* c = static_cast<IsxContext*>(h);
+  if (!c) return 0;
+  if (t_current == c) t_current = nullptr;
+  for (cudaEvent_t e : c->prof->pool) cudaEventDestroy(e);
+  delete c->prof;
+  delete c;
+  return 0;
+}
+
+extern "C" int isx_make_current(isx_handle h) {
+  t_current = static_cast<IsxContext*>(h);   // NULL: back to the thread's default context
+  return 0;
+}
+
+extern "C" int isx_sm_count(void) { return isx_ctx()->num_sms; }
 
 void isx_prof_begin(int family, double work, cudaStream_t s) {
-  if (!g_prof_on || g_prof.size() >= kMaxRecs) return;
+  IsxProfiler& P = *isx_ctx()->prof;
+  if (!P.on || P.recs.size() >= kMaxRecs) return;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(s, &cs);
   if (cs != cudaStreamCaptureStatusNone) return;
-  g_open[family] = pool_event();
-  g_open_work[family] = work;
-  g_is_open[family] = true;
-  cudaEventRecord(g_open[family], s);
+  P.open[family] = P.event();
+  P.open_work[family] = work;
+  P.is_open[family] = true;
+  cudaEventRecord(P.open[family], s);
 }
 void isx_prof_end(int family, cudaStream_t s) {
-  if (!g_prof_on || !g_is_open[family]) return;
-  ProfRec r;
-  r.e0 = g_open[family];
-  r.e1 = pool_event();
+  IsxProfiler& P = *isx_ctx()->prof;
+  if (!P.on || !P.is_open[family]) return;
+  IsxProfRec r;
+  r.e0 = P.open[family];
+  r.e1 = P.event();
   r.family = family;
-  r.work = g_open_work[family];
+  r.work = P.open_work[family];
   cudaEventRecord(r.e1, s);
-  g_prof.push_back(r);
-  g_is_open[family] = false;
+  P.recs.push_back(r);
+  P.is_open[family] = false;
 }
 
-extern "C" unsigned long long isx_launch_count(void) { return g_isx_launches; }
+extern "C" unsigned long long isx_launch_count(void) { return isx_ctx()->launches; }
 extern "C" int isx_prof_enable(int on) {
-  g_prof_on = on != 0;
-  g_prof.clear();
-  g_pool_next = 0;
-  for (int f = 0; f < ISX_PROF_FAMILIES; ++f) g_is_open[f] = false;
+  IsxProfiler& P = *isx_ctx()->prof;
+  P.on = on != 0;
+  P.recs.clear();
+  P.pool_next = 0;
+  for (int f = 0; f < ISX_PROF_FAMILIES; ++f) P.is_open[f] = false;
   return 0;
 }
 // After a device synchronisation: per family {launches, total ms, total work (FLOPs or bytes)}; out[3*family + k].
 extern "C" int isx_prof_collect(double* out, int n_out) {
   ISX_REQUIRE(out && n_out >= 3 * ISX_PROF_FAMILIES, "isx_prof_collect: need %d doubles", 3 * ISX_PROF_FAMILIES);
+  IsxProfiler& P = *isx_ctx()->prof;
   for (int i = 0; i < 3 * ISX_PROF_FAMILIES; ++i) out[i] = 0.0;
-  for (const ProfRec& r : g_prof) {
+  for (const IsxProfRec& r : P.recs) {
     float ms = 0.f;
     ISX_CHECK_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
     out[3 * r.family + 0] += 1.0;
     out[3 * r.family + 1] += ms;
     out[3 * r.family + 2] += r.work;
   }
-  g_prof.clear();
-  g_pool_next = 0;
+  P.recs.clear();
+  P.pool_next = 0;
   return 0;
 }

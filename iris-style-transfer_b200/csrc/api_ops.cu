@@ -218,21 +218,25 @@ extern "C" int isx_tap_add_mask(const isx_bf16* g, const isx_bf16* add, const fl
   return tap_add_mask(P(g), P(add), aff_a, aff_b, P(act), P(out), B, HW, C, S(stream));
 }
 
-namespace isx {
-extern int g_isx_c64;
-extern int g_isx_c64_slots;
-extern int g_isx_halo2;
-extern int g_isx_tail_n;
-extern int g_isx_halo2_stages;
-extern int g_isx_smem_reserve_kb;
-}
 extern "C" int isx_set_option(const char* name, int value) {
   ISX_REQUIRE(name != nullptr, "isx_set_option: null name");
-  if (strcmp(name, "c64") == 0) { isx::g_isx_c64 = value; return 0; }
-  if (strcmp(name, "tail_n") == 0) { isx::g_isx_tail_n = value; return 0; }
-  if (strcmp(name, "halo2") == 0) { isx::g_isx_halo2 = value; return 0; }
-  if (strcmp(name, "halo2_stages") == 0) { isx::g_isx_halo2_stages = value; return 0; }
-  if (strcmp(name, "c64_slots") == 0) { isx::g_isx_c64_slots = value; return 0; }
-  if (strcmp(name, "smem_reserve_kb") == 0) { isx::g_isx_smem_reserve_kb = value; return 0; }
+  if (strcmp(name, "c64") == 0) { isx_ctx()->opt_c64 = value; return 0; }
+  if (strcmp(name, "tail_n") == 0) { isx_ctx()->opt_tail_n = value; return 0; }
+  if (strcmp(name, "halo2") == 0) { isx_ctx()->opt_halo2 = value; return 0; }
+  if (strcmp(name, "halo2_stages") == 0) { isx_ctx()->opt_halo2_stages = value; return 0; }
+  if (strcmp(name, "c64_slots") == 0) { isx_ctx()->opt_c64_slots = value; return 0; }
+  if (strcmp(name, "smem_reserve_kb") == 0) { isx_ctx()->opt_smem_reserve_kb = value; return 0; }
   ISX_REQUIRE(false, "isx_set_option: unknown option '%s'", name);
+}
+
+extern "C" int isx_get_option(const char* name, int* value) {
+  ISX_REQUIRE(name != nullptr && value != nullptr, "isx_get_option: null pointer");
+  const IsxContext* c = isx_ctx();
+  if (strcmp(name, "c64") == 0) { *value = c->opt_c64; return 0; }
+  if (strcmp(name, "tail_n") == 0) { *value = c->opt_tail_n; return 0; }
+  if (strcmp(name, "halo2") == 0) { *value = c->opt_halo2; return 0; }
+  if (strcmp(name, "halo2_stages") == 0) { *value = c->opt_halo2_stages; return 0; }
+  if (strcmp(name, "c64_slots") == 0) { *value = c->opt_c64_slots; return 0; }
+  if (strcmp(name, "smem_reserve_kb") == 0) { *value = c->opt_smem_reserve_kb; return 0; }
+  ISX_REQUIRE(false, "isx_get_option: unknown option '%s'", name);
 }

@@ -193,7 +193,6 @@ conv1_1_tail_kernel(const __grid_constant__ CUtensorMap tmA, const TailParams p)
   }
 }
 
-int g_isx_tail_n = 1;  // isx_set_option("tail_n"): 1 = taps-in-N tail (default), 0 = generic 36-MMA tail
 
 int conv1_1_tail_n(const __nv_bfloat16* dy, const __nv_bfloat16* wd, const float* mask, int mask_b, float* dx, int xc,
                    int B, int H, int W, cudaStream_t stream) {

@@ -380,8 +380,6 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-extern int g_isx_smem_reserve_kb;
-int g_isx_c64_slots = 0;  // isx_set_option("c64_slots"): halo ring depth override (0 = as many of 4 as fit)
 
 template <int BN, int EPI>
 static int launch_c64(const ConvArgs& a, cudaStream_t stream) {
@@ -398,9 +396,9 @@ static int launch_c64(const ConvArgs& a, cudaStream_t stream) {
   ISX_REQUIRE(!p.use_gram || a.gram_act == a.mask_act, "conv_c64: the fused Gram operand must be the ReLU-mask activation");
   p.fuse_pool = (EPI == 0 && a.pool_out != nullptr && a.H >= 2 && a.W >= 2) ? 1 : 0;
   p.dx_nchw = a.dx_nchw; p.xc = a.xc; p.in_mask = a.in_mask; p.mask_b = a.mask_b;
-  int hs = g_isx_c64_slots > 0 ? g_isx_c64_slots : 4;
+  int hs = isx_ctx()->opt_c64_slots > 0 ? isx_ctx()->opt_c64_slots : 4;
   C64Layout L = c64_layout<BN, EPI>(hs, p.use_mask, p.use_gram, p.fuse_pool);
-  const int cap = (227 - std::max(0, std::min(g_isx_smem_reserve_kb, 22))) * 1024;  // see conv_halo.cu
+  const int cap = (227 - std::max(0, std::min(isx_ctx()->opt_smem_reserve_kb, 22))) * 1024;  // see conv_halo.cu
   while (hs > 2 && 1024 + L.total > cap) { --hs; L = c64_layout<BN, EPI>(hs, p.use_mask, p.use_gram, p.fuse_pool); }
   ISX_REQUIRE(1024 + L.total <= 227 * 1024, "conv_c64: %d B of shared memory exceed 227 KB", 1024 + L.total);
   p.halo_slots = hs;

@@ -407,8 +407,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-int g_isx_smem_reserve_kb = 0;  // isx_set_option("smem_reserve_kb"): shared memory the persistent conv CTAs leave free per SM
-int g_isx_halo2_stages = 0;  // isx_set_option("halo2_stages"): weight-ring depth override (0 = as many of 6 as fit)
 
 template <int BN, bool VERT>
 static int launch_halo(const ConvArgs& a, cudaStream_t stream) {
@@ -426,11 +424,11 @@ static int launch_halo(const ConvArgs& a, cudaStream_t stream) {
   p.relu = a.relu; p.bias = a.bias; p.add_buf = a.add_buf; p.aff_a = a.aff_a; p.aff_b = a.aff_b;
   p.use_mask = a.mask_act != nullptr ? 1 : 0;
   p.fuse_pool = (a.pool_out != nullptr && a.H >= 2 && a.W >= 2) ? 1 : 0;
-  int ws = g_isx_halo2_stages > 0 ? std::min(g_isx_halo2_stages, 8) : 6;
+  int ws = isx_ctx()->opt_halo2_stages > 0 ? std::min(isx_ctx()->opt_halo2_stages, 8) : 6;
   HaloLayout L = halo_layout<BN>(ws, p.use_mask, p.fuse_pool);
   // "smem_reserve_kb" (<= 22): leave that much of the SM's shared memory free, so that one TMEM-free streaming CTA (the
   // L-BFGS passes of another stream) can be resident beside this persistent CTA and use the HBM bandwidth it leaves idle
-  const int cap = (227 - std::max(0, std::min(g_isx_smem_reserve_kb, 22))) * 1024;
+  const int cap = (227 - std::max(0, std::min(isx_ctx()->opt_smem_reserve_kb, 22))) * 1024;
   while (ws > 2 && 1024 + L.total > cap) { --ws; L = halo_layout<BN>(ws, p.use_mask, p.fuse_pool); }
   ISX_REQUIRE(1024 + L.total <= 227 * 1024, "conv_halo: %d B of shared memory exceed 227 KB", 1024 + L.total);
   p.w_stages = ws;

@@ -471,25 +471,24 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
 // tuning knobs (isx_set_option)
 // Specialised Cin = 64 kernel (resident weights + halo patch, conv_c64.cu).  0: never; 1 (default): the 64 -> 64 layers
 // when there is at least one tile per SM; 2: every applicable call, including the N = 16 tail and tiny inputs (tests).
-int g_isx_c64 = 1;
+// (isx_ctx()->opt_c64, default 1)
 
 // Halo-patch pair kernel (conv_halo.cu).  0: never; 1: layers with enough work items and little padding; 2: every
 // applicable call (tests).
-int g_isx_halo2 = 1;
+// (isx_ctx()->opt_halo2, default 1)
 
-extern int g_isx_tail_n;
 
 int conv_tc(const ConvArgs& a_in, cudaStream_t stream) {
   ConvArgs a = a_in;
-  if (a.dx_nchw != nullptr && g_isx_tail_n > 0 && g_isx_c64 < 2 && a.force_bn == 0 &&
+  if (a.dx_nchw != nullptr && isx_ctx()->opt_tail_n > 0 && isx_ctx()->opt_c64 < 2 && a.force_bn == 0 &&
       a.Cin == 64 && a.Cout == 16 && a.ntaps == 9)
     return conv1_1_tail_n(a.in, a.weight, a.in_mask, a.mask_b, a.dx_nchw, a.xc, a.B, a.H, a.W, stream);
-  if (g_isx_c64 > 0 && a.force_bn == 0 && conv_c64_applicable(a) &&
-      (g_isx_c64 >= 2 || (a.dx_nchw == nullptr && static_cast<long>(a.B) * ((a.H + 15) / 16) * ((a.W + 7) / 8) >= kNumSMs)))
+  if (isx_ctx()->opt_c64 > 0 && a.force_bn == 0 && conv_c64_applicable(a) &&
+      (isx_ctx()->opt_c64 >= 2 || (a.dx_nchw == nullptr && static_cast<long>(a.B) * ((a.H + 15) / 16) * ((a.W + 7) / 8) >= kNumSMs)))
     return conv_c64(a, stream);
-  if (g_isx_halo2 > 0 && a.force_bn == 0 && conv_halo_applicable(a)) {
+  if (isx_ctx()->opt_halo2 > 0 && a.force_bn == 0 && conv_halo_applicable(a)) {
     const long items = static_cast<long>(a.B) * ((a.H + 15) / 16) * ((a.W + 15) / 16) * (a.Cout / (a.Cout % 128 == 0 ? 128 : 64));
-    if (g_isx_halo2 >= 2 || (items >= 2 * kNumSMs && conv_halo_efficiency(a) >= 0.85)) return conv_halo(a, stream);
+    if (isx_ctx()->opt_halo2 >= 2 || (items >= 2 * kNumSMs && conv_halo_efficiency(a) >= 0.85)) return conv_halo(a, stream);
   }
   if (a.dx_nchw != nullptr) {  // conv1_1 dgrad tail: N = 16 (3 real output channels), fp32 NCHW epilogue
     ISX_REQUIRE(a.Cin == 64 && a.Cout == 16 && a.ntaps == 9, "conv_tc: image-gradient mode needs Cin 64, Cout 16 (padded)");

@@ -32,7 +32,7 @@ __global__ void pack_w_kernel(const float* __restrict__ w, int Cout, int Cin, __
 
 int pack_conv_weights(const float* w, int Cout, int Cin, __nv_bfloat16* wf, __nv_bfloat16* wd, cudaStream_t s) {
   const long n = static_cast<long>(Cout) * Cin * 9;
-  const int blocks = static_cast<int>(std::min<long>((n + 255) / 256, 148 * 8));
+  const int blocks = static_cast<int>(std::min<long>((n + 255) / 256, isx_num_sms() * 8));
   pack_w_kernel<<<blocks, 256, 0, s>>>(w, Cout, Cin, wf, wd);
   ISX_LAUNCH_CHECK();
   return 0;
@@ -230,7 +230,7 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ in, __nv_bf
 int maxpool_fwd(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t s) {
   ISX_REQUIRE(C % 8 == 0 && H >= 2 && W >= 2, "maxpool: bad shape H=%d W=%d C=%d", H, W, C);
   const long n = static_cast<long>(B) * (H / 2) * (W / 2) * (C / 8);
-  const int blocks = static_cast<int>(std::min<long>((n + 255) / 256, 148L * 16));
+  const int blocks = static_cast<int>(std::min<long>((n + 255) / 256, static_cast<long>(isx_num_sms()) * 16));
   maxpool_fwd_kernel<<<blocks, 256, 0, s>>>(in, out, B, H, W, C);
   ISX_LAUNCH_CHECK();
   return 0;
@@ -275,7 +275,7 @@ int maxpool_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* act, __nv_bfloat16
   if ((H & 1) || (W & 1))  // the last row / column belongs to no window: gradient 0
     ISX_CHECK_CUDA(cudaMemsetAsync(dx, 0, static_cast<size_t>(B) * H * W * C * 2, s));
   const long n = static_cast<long>(B) * (H / 2) * (W / 2) * (C / 8);
-  const int blocks = static_cast<int>(std::min<long>((n + 255) / 256, 148L * 16));
+  const int blocks = static_cast<int>(std::min<long>((n + 255) / 256, static_cast<long>(isx_num_sms()) * 16));
   maxpool_bwd_kernel<<<blocks, 256, 0, s>>>(dy, act, dx, B, H, W, C);
   ISX_LAUNCH_CHECK();
   return 0;
@@ -303,7 +303,7 @@ __global__ void mask_features_kernel(const __nv_bfloat16* __restrict__ f, const 
 int mask_features(const __nv_bfloat16* f, const float* m, int mask_b, __nv_bfloat16* fm, __nv_bfloat16* fm2, int B,
                   long HW, int C, cudaStream_t s) {
   const long n8 = static_cast<long>(B) * HW * C / 8;
-  const int blocks = static_cast<int>(std::min<long>((n8 + 255) / 256, 148L * 16));
+  const int blocks = static_cast<int>(std::min<long>((n8 + 255) / 256, static_cast<long>(isx_num_sms()) * 16));
   mask_features_kernel<<<blocks, 256, 0, s>>>(f, m, mask_b, fm, fm2, HW, C / 8, n8);
   ISX_LAUNCH_CHECK();
   return 0;
@@ -325,7 +325,7 @@ __global__ void avgpool2x2_f32_kernel(const float* __restrict__ in, float* __res
 
 int avgpool2x2_f32(const float* in, float* out, int B, int H, int W, cudaStream_t s) {
   const long n = static_cast<long>(B) * (H / 2) * (W / 2);
-  const int blocks = static_cast<int>(std::min<long>((n + 255) / 256, 148L * 8));
+  const int blocks = static_cast<int>(std::min<long>((n + 255) / 256, static_cast<long>(isx_num_sms()) * 8));
   avgpool2x2_f32_kernel<<<blocks, 256, 0, s>>>(in, out, B, H, W);
   ISX_LAUNCH_CHECK();
   return 0;
@@ -365,7 +365,7 @@ __global__ void tap_add_mask_kernel(const __nv_bfloat16* __restrict__ g, const _
 int tap_add_mask(const __nv_bfloat16* g, const __nv_bfloat16* add, const float* aff_a, const float* aff_b,
                  const __nv_bfloat16* act, __nv_bfloat16* out, int B, long HW, int C, cudaStream_t s) {
   const long n8 = static_cast<long>(B) * HW * C / 8;
-  const int blocks = static_cast<int>(std::min<long>((n8 + 255) / 256, 148L * 16));
+  const int blocks = static_cast<int>(std::min<long>((n8 + 255) / 256, static_cast<long>(isx_num_sms()) * 16));
   tap_add_mask_kernel<<<blocks, 256, 0, s>>>(g, add, aff_a, aff_b, act, out, n8, C, HW * C / 8);
   ISX_LAUNCH_CHECK();
   return 0;
@@ -493,7 +493,7 @@ int content_mse(const __nv_bfloat16* pred, const __nv_bfloat16* target, int targ
                 long per_image, double loss_scale, float grad_scale, double* loss, cudaStream_t s) {
   ISX_REQUIRE(per_image % 8 == 0, "content_mse: per-image size %ld not a multiple of 8", per_image);
   const long n8 = per_image / 8;
-  int bx = static_cast<int>(std::min<long>((n8 + 255) / 256, 148L * 8 / std::max(1, std::min(B, 8)) + 1));
+  int bx = static_cast<int>(std::min<long>((n8 + 255) / 256, static_cast<long>(isx_num_sms()) * 8 / std::max(1, std::min(B, 8)) + 1));
   dim3 grid(bx, B);
   content_mse_kernel<<<grid, 256, 0, s>>>(pred, target, target_b, grad, n8, loss_scale, grad_scale, loss);
   ISX_LAUNCH_CHECK();
@@ -541,7 +541,7 @@ int chan_sums(const __nv_bfloat16* f, int B, long HW, int C, double* sums, cudaS
   ISX_REQUIRE(C % 8 == 0 && C / 8 <= 64 && 256 % (C / 8) == 0, "chan_sums: C=%d unsupported", C);
   const int lanes = 256 / (C / 8);
   long bx = (HW + lanes * 8 - 1) / (lanes * 8);  // >= 8 pixels per lane
-  const long cap = std::max<long>(1, 148L * 4 / B);
+  const long cap = std::max<long>(1, static_cast<long>(isx_num_sms()) * 4 / B);
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   dim3 grid(static_cast<unsigned>(bx), B);

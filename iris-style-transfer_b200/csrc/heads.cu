@@ -99,7 +99,7 @@ __global__ void pool7_flatten_kernel(const __nv_bfloat16* __restrict__ p5, int B
   }
 }
 
-static int grid_for(long total) { return static_cast<int>(std::min<long>((total + 255) / 256, 148L * 16)); }
+static int grid_for(long total) { return static_cast<int>(std::min<long>((total + 255) / 256, static_cast<long>(isx_num_sms()) * 16)); }
 
 }  // namespace isx
 

@@ -220,7 +220,7 @@ extern "C" int isx_mask_bbox(const float* x, const int64_t* seg, int label, int 
   const bool vec = (W % 4 == 0) && al16(x) && al16(seg) && al16(xm) && (mask == nullptr || (reinterpret_cast<uintptr_t>(mask) & 3) == 0);
   const long items = vec ? hw / 4 : hw;
   // whole waves of 256-thread blocks: 148 SMs x 8 resident blocks, split over the images
-  const int bx = static_cast<int>(std::min<long>((items + 255) / 256, std::max<long>(1, 148L * 8 / B)));
+  const int bx = static_cast<int>(std::min<long>((items + 255) / 256, std::max<long>(1, static_cast<long>(isx_num_sms()) * 8 / B)));
   dim3 grid(bx, B);
   if (vec)
     mask_bbox_kernel<4><<<grid, 256, 0, S(stream)>>>(x, seg, label, use_threshold, threshold, mask, xm, bbox, H, W);

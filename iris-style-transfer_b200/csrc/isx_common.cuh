@@ -30,11 +30,32 @@ void isx_set_error(const char* fmt, ...);
     }                            \
   } while (0)
 
+// ------------------------------------------------------------------------------------------
+// Per-handle library state (isx_create / isx_destroy / isx_make_current, include/isx.h): kernel-selection options, the
+// launch counter, the CUDA-event profiler and the device's SM count.  There is NO process-global mutable state: every
+// entry point works on the calling thread's CURRENT context -- the handle it bound with isx_make_current, or a private
+// default context created on first use (device = the thread's current CUDA device).
+// ------------------------------------------------------------------------------------------
+struct IsxProfiler;
+struct IsxContext {
+  int device = 0;
+  int num_sms = 148;                 // cudaDevAttrMultiProcessorCount of `device` (B200: 148)
+  int opt_c64 = 1;                   // "c64": resident-weight kernel for the 64 -> 64 layers (0 never, 1 heuristic, 2 always)
+  int opt_halo2 = 1;                 // "halo2": halo-patch pair kernel for the mid layers
+  int opt_tail_n = 1;                // "tail_n": taps-in-N image-gradient tail
+  int opt_c64_slots = 0;             // "c64_slots": halo ring depth override
+  int opt_halo2_stages = 0;          // "halo2_stages": weight ring depth override
+  int opt_smem_reserve_kb = 0;       // "smem_reserve_kb": shared memory the persistent conv CTAs leave free per SM
+  unsigned long long launches = 0;   // kernels launched through this context
+  IsxProfiler* prof = nullptr;
+};
+IsxContext* isx_ctx();
+inline int isx_num_sms() { return isx_ctx()->num_sms; }
+
 // every kernel launch of the library goes through this: error check + launch counter (bench.py's gpu_launches)
-extern unsigned long long g_isx_launches;
 #define ISX_LAUNCH_CHECK()               \
   do {                                   \
-    ++g_isx_launches;                    \
+    ++isx_ctx()->launches;               \
     ISX_CHECK_CUDA(cudaGetLastError());  \
   } while (0)
 
@@ -51,7 +72,8 @@ int isx_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint6
 #ifdef __CUDACC__
 namespace isx {
 
-static constexpr int kNumSMs = 148;
+// SM count of the current context's device (host-side grid sizing only; kernels read gridDim)
+#define kNumSMs (isx_num_sms())
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

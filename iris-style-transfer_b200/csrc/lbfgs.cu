@@ -468,7 +468,7 @@ int lbfgs_init(LbfgsState* states, int P, cudaStream_t s) {
 }
 
 int clamp01(float* x, long n, cudaStream_t s) {
-  const int blocks = static_cast<int>(std::min<long>((n + 255) / 256, 148L * 8));
+  const int blocks = static_cast<int>(std::min<long>((n + 255) / 256, static_cast<long>(isx_num_sms()) * 8));
   clamp01_kernel<<<blocks, 256, 0, s>>>(x, n);
   ISX_LAUNCH_CHECK();
   return 0;

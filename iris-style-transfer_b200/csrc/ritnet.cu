@@ -325,7 +325,7 @@ int run_transform(const float* x, const uint8_t* gamma_lut, const float* norm_lu
                   int B, int H, int W, cudaStream_t s) {
   const size_t hw = static_cast<size_t>(H) * W;
   const long n = static_cast<long>(B) * hw;
-  const int blocks = static_cast<int>(std::min<long>((n + 255) / 256, 148L * 16));
+  const int blocks = static_cast<int>(std::min<long>((n + 255) / 256, static_cast<long>(isx_num_sms()) * 16));
   rit_quant_gamma_kernel<<<blocks, 256, 0, s>>>(x, gamma_lut, g8, n);
   ISX_LAUNCH_CHECK();
   ClaheGeom g;
@@ -339,7 +339,7 @@ int run_transform(const float* x, const uint8_t* gamma_lut, const float* norm_lu
   g.inv_th = 1.0f / static_cast<float>(g.th); g.inv_tw = 1.0f / static_cast<float>(g.tw);
   rit_clahe_lut_kernel<<<dim3(kTiles * kTiles, B), 256, 0, s>>>(g8, g, lut);
   ISX_LAUNCH_CHECK();
-  rit_clahe_interp_kernel<<<dim3(static_cast<unsigned>(std::min<long>((hw + 255) / 256, 148L * 8)), B), 256, 0, s>>>(g8, lut, norm_lut, g, out);
+  rit_clahe_interp_kernel<<<dim3(static_cast<unsigned>(std::min<long>((hw + 255) / 256, static_cast<long>(isx_num_sms()) * 8)), B), 256, 0, s>>>(g8, lut, norm_lut, g, out);
   ISX_LAUNCH_CHECK();
   return 0;
 }
@@ -389,7 +389,7 @@ extern "C" int isx_ritnet_forward(const float* x, const float* params, const uin
       in = RitSrc{xin, 1, 0};
     } else {
       const long n4 = static_cast<long>(B) * h * w * 8;
-      rit_avgpool_kernel<<<static_cast<int>(std::min<long>((n4 + 255) / 256, 148L * 16)), 256, 0, s>>>(buf[l - 1][4], buf[l][0], B, H >> (l - 1), W >> (l - 1));
+      rit_avgpool_kernel<<<static_cast<int>(std::min<long>((n4 + 255) / 256, static_cast<long>(isx_num_sms()) * 16)), 256, 0, s>>>(buf[l - 1][4], buf[l][0], B, H >> (l - 1), W >> (l - 1));
       ISX_LAUNCH_CHECK();
       in = RitSrc{buf[l][0], 32, 0};
     }
@@ -410,7 +410,7 @@ extern "C" int isx_ritnet_forward(const float* x, const float* params, const uin
     if (int rc = launch_conv(P.up[k][3], params, t, none, none, 1, 1, nullptr, nullptr, buf[l][3], B, h, w, s)) return rc;      // out
     prev = buf[l][3];
   }
-  rit_classify_kernel<<<static_cast<int>(std::min<long>((n + 255) / 256, 148L * 16)), 256, 0, s>>>(prev, params + P.out_w, params + P.out_b, labels, logits,
+  rit_classify_kernel<<<static_cast<int>(std::min<long>((n + 255) / 256, static_cast<long>(isx_num_sms()) * 16)), 256, 0, s>>>(prev, params + P.out_w, params + P.out_b, labels, logits,
                                                                                                    static_cast<long>(hw), n);
   ISX_LAUNCH_CHECK();
   return 0;

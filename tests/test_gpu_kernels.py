@@ -1,6 +1,8 @@
 """Kernel-level parity on the B200: every C-ABI kernel against a plain PyTorch fp32 evaluation of
 the same op on the same (bf16-rounded) inputs.  Tolerances: one bf16 rounding of the output
 (2^-8 relative) for bf16 results, 1e-4 relative for fp32 results (fp32 accumulation order)."""
+import ctypes
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -515,3 +517,32 @@ def test_bn_stats(isx, C):
     g_ref = fr.grad.permute(0, 2, 3, 1)
     g_got = aa[:, None, None, :] + ab[:, None, None, :] * f.float()
     assert torch.allclose(g_got, g_ref, rtol=2e-3, atol=2e-3 * g_ref.abs().max().item())
+
+
+def test_handles_isolate_options_and_counters(isx):
+    """isx_create / isx_make_current / isx_destroy: options, launch counter and profiler belong to a handle, not to the
+    process; a thread without a bound handle uses its private default context."""
+    lib = isx.load()
+    lib.isx_launch_count.restype = ctypes.c_ulonglong
+
+    def opt(name):
+        v = ctypes.c_int(-1)
+        assert lib.isx_get_option(name, ctypes.byref(v)) == 0
+        return v.value
+
+    assert opt(b"c64") == 1 and lib.isx_sm_count() == torch.cuda.get_device_properties(0).multi_processor_count
+    base = lib.isx_launch_count()
+    h1, h2 = isx.Handle(0), isx.Handle(0)
+    x = torch.rand(1000, device="cuda")
+    with h1:
+        assert lib.isx_set_option(b"c64", 0) == 0 and opt(b"c64") == 0
+        assert lib.isx_launch_count() == 0
+        isx.call("isx_clamp01", x, isx.i64(x.numel()), isx.stream_ptr())
+        assert lib.isx_launch_count() == 1
+    with h2:
+        assert opt(b"c64") == 1 and lib.isx_launch_count() == 0
+    assert opt(b"c64") == 1 and lib.isx_launch_count() == base        # the default context saw none of it
+    assert lib.isx_set_option(b"no_such_option", 1) != 0
+    bad = ctypes.c_void_p()
+    assert lib.isx_create(99, ctypes.byref(bad)) != 0                   # no such device
+    h1.destroy(); h2.destroy()
