@@ -11,6 +11,54 @@ from .engine import (CONV_OF_FEATURE_INDEX, N_CONVS, POOL_OF_FEATURE_INDEX, VGG1
 
 vgg19_layers = dict(VGG19_LAYERS)  # same public name as models/vgg/vgg.py:6
 
+# models/vgg/vgg.py:12-17 (torchvision vgg19_bn.features indices): conv -> bn -> relu triples
+vgg19_bn_layers: Dict[str, int] = {}
+_BN_CONV_OF_INDEX: Dict[int, int] = {}    # bn / relu index -> conv ordinal (the in-place ReLU overwrites the BN output)
+_BN_RAW_CONV_INDEX = set()                # conv indices: their PRE-BatchNorm output is a separate tensor
+_i, _blk, _sub, _c = 0, 1, 1, 0
+for _v in [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512, "M"]:
+    if _v == "M":
+        vgg19_bn_layers["pool%d" % _blk] = _i
+        _i, _blk, _sub = _i + 1, _blk + 1, 1
+    else:
+        vgg19_bn_layers["conv%d_%d" % (_blk, _sub)] = _i
+        vgg19_bn_layers["bn%d_%d" % (_blk, _sub)] = _i + 1
+        vgg19_bn_layers["relu%d_%d" % (_blk, _sub)] = _i + 2
+        _BN_RAW_CONV_INDEX.add(_i)
+        _BN_CONV_OF_INDEX[_i + 1] = _c
+        _BN_CONV_OF_INDEX[_i + 2] = _c
+        _i, _sub, _c = _i + 3, _sub + 1, _c + 1
+assert vgg19_bn_layers["relu4_2"] == 32 and vgg19_bn_layers["pool5"] == 52
+
+
+def fold_batchnorm(w, b, gamma, beta, mean, var, eps: float = 1e-5):
+    """Conv2d followed by an eval-mode BatchNorm2d == one Conv2d: w' = w * g/sqrt(var+eps), b' = (b - mean) * g/sqrt(var+eps) + beta."""
+    scale = (gamma.double() / torch.sqrt(var.double() + eps))
+    return (w.double() * scale[:, None, None, None]).float(), ((b.double() - mean.double()) * scale + beta.double()).float()
+
+
+def random_vgg19_bn_weights(seed: int = 0):
+    """torchvision vgg19_bn(weights=None) under torch.manual_seed(seed), BatchNorm folded into the 16 (weight, bias) pairs."""
+    import torchvision.models as tvm
+
+    torch.manual_seed(seed)
+    net = tvm.vgg19_bn(weights=None).features.eval()
+    return vgg19_bn_pairs(net)
+
+
+def vgg19_bn_pairs(features: torch.nn.Module):
+    """The 16 folded (weight, bias) pairs of a torchvision vgg19_bn `.features` stack in eval mode."""
+    mods = list(features)
+    out = []
+    for i, m in enumerate(mods):
+        if isinstance(m, torch.nn.Conv2d):
+            bn = mods[i + 1]
+            assert isinstance(bn, torch.nn.BatchNorm2d)
+            out.append(fold_batchnorm(m.weight.detach(), m.bias.detach(), bn.weight.detach(), bn.bias.detach(),
+                                      bn.running_mean.detach(), bn.running_var.detach(), bn.eps))
+    assert len(out) == N_CONVS
+    return out
+
 
 def random_vgg19_weights(seed: int = 0) -> List[Tuple[torch.Tensor, torch.Tensor]]:
     """BASELINE's "random-init VGG-19": torchvision vgg19(weights=None) under torch.manual_seed(seed)."""
@@ -68,31 +116,42 @@ class _VGGForward(torch.autograd.Function):
 
 class VGG19(torch.nn.Module):
     """models/vgg/vgg.py:19-92.  `weights`: 'imagenet' (the reference's IMAGENET1K_V1 via torchvision; needs the
-    checkpoint to be available), 'random' (torchvision init under `seed`), or the 16 (weight, bias) pairs."""
+    checkpoint to be available), 'random' (torchvision init under `seed`), or the 16 (weight, bias) pairs.
+    `bn=True` (vgg19_bn, vgg.py:41-44): the model is frozen in eval mode (vgg.py:49-53), so every BatchNorm2d is an affine
+    map of its conv and is folded into the 16 conv kernels once; `bn*` / `relu*` taps are the usual post-ReLU tensors
+    (the in-place ReLU overwrites the BatchNorm output), `conv*` taps of the bn model -- the PRE-BatchNorm tensor -- are
+    not representable after folding and raise."""
 
     def __init__(self, content_layers: Sequence[str] = ("relu4_2",),
                  style_layers: Sequence[str] = ("relu1_1", "relu2_1", "relu3_1", "relu4_1"), bn: bool = False,
                  weights="imagenet", seed: int = 0) -> None:
         super().__init__()
-        if bn:
-            raise NotImplementedError("vgg19_bn (models/vgg/vgg.py:41-42) is outside the accelerated path")
+        self.bn = bool(bn)
         self.content_layers = list(content_layers)
         self.style_layers = list(style_layers)
-        self.content_layers_idx = [VGG19_LAYERS[i] for i in self.content_layers]
-        self.style_layers_idx = [VGG19_LAYERS[i] for i in self.style_layers]
+        table = vgg19_bn_layers if bn else VGG19_LAYERS
+        conv_of = _BN_CONV_OF_INDEX if bn else CONV_OF_FEATURE_INDEX
+        self.content_layers_idx = [table[i] for i in self.content_layers]
+        self.style_layers_idx = [table[i] for i in self.style_layers]
         for idx in self.content_layers_idx + self.style_layers_idx:
-            if idx not in CONV_OF_FEATURE_INDEX:
+            if bn and idx in _BN_RAW_CONV_INDEX:
+                raise NotImplementedError("conv* taps of vgg19_bn are the pre-BatchNorm tensors; BatchNorm is folded into the "
+                                          "convolutions here -- tap bn* / relu* instead")
+            if idx not in conv_of:
                 raise NotImplementedError("taps on pooling layers are not supported by the accelerated path")
-        self.content_convs = [CONV_OF_FEATURE_INDEX[i] for i in self.content_layers_idx]
-        self.style_convs = [CONV_OF_FEATURE_INDEX[i] for i in self.style_layers_idx]
+        self.content_convs = [conv_of[i] for i in self.content_layers_idx]
+        self.style_convs = [conv_of[i] for i in self.style_layers_idx]
         if isinstance(weights, str):
             if weights == "imagenet":
                 import torchvision.models as tvm
 
-                net = tvm.vgg19(weights=tvm.VGG19_Weights.IMAGENET1K_V1).features
-                weights = [(m.weight.detach(), m.bias.detach()) for m in net if isinstance(m, torch.nn.Conv2d)]
+                if bn:
+                    weights = vgg19_bn_pairs(tvm.vgg19_bn(weights=tvm.VGG19_BN_Weights.IMAGENET1K_V1).features.eval())
+                else:
+                    net = tvm.vgg19(weights=tvm.VGG19_Weights.IMAGENET1K_V1).features
+                    weights = [(m.weight.detach(), m.bias.detach()) for m in net if isinstance(m, torch.nn.Conv2d)]
             elif weights == "random":
-                weights = random_vgg19_weights(seed)
+                weights = random_vgg19_bn_weights(seed) if bn else random_vgg19_weights(seed)
             else:
                 raise ValueError("weights must be 'imagenet', 'random' or 16 (weight, bias) pairs")
         assert len(weights) == N_CONVS

@@ -90,10 +90,26 @@ def test_vgg19_surface_and_no_cpu_fallback():
     assert net.content_convs == [9] and net.style_convs == [0, 2, 4, 8]
     net5 = iris_b200.VGG19(style_layers=["conv1_1", "relu2_1", "relu3_1", "relu4_1", "relu5_1"], weights=w)
     assert net5.style_convs == [0, 2, 4, 8, 12]
+    # vgg19_bn (models/vgg/vgg.py:12-17,41-44): BatchNorm folded; bn* / relu* taps map to the conv ordinals, conv* taps raise
+    from iris_b200 import vgg as V
+
+    assert V.vgg19_bn_layers["relu4_2"] == 32 and V.vgg19_bn_layers["bn1_1"] == 1 and V.vgg19_bn_layers["pool5"] == 52
+    nb = iris_b200.VGG19(bn=True, weights=w, style_layers=["relu1_1", "bn2_1", "relu3_1", "relu4_1"])
+    assert nb.style_layers_idx == [2, 8, 16, 29] and nb.style_convs == [0, 2, 4, 8] and nb.content_convs == [9]
     with pytest.raises(NotImplementedError):
-        iris_b200.VGG19(bn=True, weights=w)
+        iris_b200.VGG19(bn=True, weights=w, style_layers=["conv1_1"])
     with pytest.raises(NotImplementedError):
         iris_b200.VGG19(style_layers=["pool1"], weights=w)
+    g = torch.Generator().manual_seed(1)
+    cw, cb = torch.randn(8, 4, 3, 3, generator=g), torch.randn(8, generator=g)
+    bn = torch.nn.BatchNorm2d(8).eval()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(8, generator=g) + 0.5); bn.bias.copy_(torch.randn(8, generator=g))
+        bn.running_mean.copy_(torch.randn(8, generator=g)); bn.running_var.copy_(torch.rand(8, generator=g) + 0.2)
+        fw, fb = V.fold_batchnorm(cw, cb, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+        xin = torch.randn(2, 4, 9, 9, generator=g)
+        ref = bn(torch.nn.functional.conv2d(xin, cw, cb, padding=1))
+        assert torch.allclose(torch.nn.functional.conv2d(xin, fw, fb, padding=1), ref, atol=1e-5)
     x = torch.rand(1, 3, 32, 32)
     if not torch.cuda.is_available():
         with pytest.raises(Exception):

@@ -664,6 +664,41 @@ def test_eval_layer_configurations(mods, cfg_id, BN):
     assert cos > 0.97 and 0.8 < float(gc.norm() / rg.norm()) < 1.25
 
 
+def test_vgg19_bn_features_match_torchvision(mods):
+    """VGG19(bn=True) (models/vgg/vgg.py:41-44): eval-mode BatchNorm folded into the convs; features vs torchvision's
+    vgg19_bn.features with non-trivial BatchNorm statistics."""
+    import torchvision.models as tvm
+    import iris_b200
+    from iris_b200 import vgg as V
+
+    torch.manual_seed(3)
+    net = tvm.vgg19_bn(weights=None).features.eval()
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for m in net:
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.copy_(torch.rand(m.num_features, generator=g) * 0.5 + 0.75)
+                m.bias.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.num_features, generator=g) * 0.5 + 0.75)
+    ours = iris_b200.VGG19(bn=True, weights=V.vgg19_bn_pairs(net))
+    x = rand_img(5, (2, 3, 64, 48))
+    with torch.no_grad():
+        _, c_f, s_f = ours(x.cuda())
+        mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+        std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+        h = (x - mean) / std
+        ref = {}
+        for i, m in enumerate(net):
+            h = m(h)
+            ref[i] = h
+    for name, got in zip(ours.content_layers + ours.style_layers, c_f + s_f):
+        r = ref[V.vgg19_bn_layers[name]]
+        err = float((got.cpu() - r).abs().max()) / float(r.abs().max())
+        print("vgg19_bn %s: max rel err %.4f" % (name, err))
+        assert err < 3e-2
+
+
 def test_cpu_device_is_refused(mods):
     with pytest.raises(Exception):
         mods["pipelines"].nst(rand_img(1, (1, 3, 32, 32)), rand_img(2, (1, 3, 32, 32)), vgg=mods["vgg"],
