@@ -349,7 +349,8 @@ def nst_leg(args, dev, vgg, c_dev, s_dev, BN_loss, independent, K, Wm, world, ra
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return dict(ms=ms, ms_max=float(t.item()), launches=launches, prof=list(prof), clocks=clocks, moved=moved,
                 loss_first=loss_first, loss_last=loss_last, pairs_min=int(min(pairs0.min(), pairs1.min())),
-                pairs_max=int(max(pairs0.max(), pairs1.max())), problems=P, problems_running=evals_alive,
+                pairs_max=int(max(pairs0.max(), pairs1.max())),
+                pairs_mean=0.5 * (float(pairs0.float().mean()) + float(pairs1.float().mean())), problems=P, problems_running=evals_alive,
                 prefill=prefill)
 
 
@@ -611,7 +612,7 @@ def main():
     # m = number of stored pairs (constant = the full ring in the timed region when prefilled)
     N_img = 3 * h * w
     esz = 2 if args.history_bf16 else 4
-    m_avg = 0.5 * (r["pairs_min"] + r["pairs_max"])
+    m_avg = r["pairs_mean"]
     lbfgs_bytes = K * B * N_img * (4.0 * esz * m_avg + 36.0)
     hbm_peak = peaks.get("hbm_gbs") or 6650.0
     lbfgs_gbs = lbfgs_bytes / (prof[7] / 1e3) / 1e9 if prof[7] > 0 else None
@@ -686,7 +687,7 @@ def main():
         "config": {"workload": workload, "name": cfgname,
                    "batch_per_gpu": B, "image": "3x%dx%d" % (h, w), "l2": "inputs larger than L2 (activations %.1f GB per step)"
                    % (B * 139e6 * (h * w) / (H * W) / 1e9), "history_slots": 100,
-                   "history_pairs_min": r["pairs_min"], "history_pairs_max": r["pairs_max"],
+                   "history_pairs_min": r["pairs_min"], "history_pairs_max": r["pairs_max"], "history_pairs_mean": r["pairs_mean"],
                    "untimed_prefill_ticks": r["prefill"] + Wm, "problems": r["problems"],
                    "problems_still_running_at_end": r["problems_running"],
                    "history_dtype": "bf16" if args.history_bf16 else "f32", "streams": args.streams,
