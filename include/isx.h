@@ -129,6 +129,13 @@ int isx_gram_bwd(const isx_bf16* feat, const isx_bf16* D, isx_bf16* dF, int B, i
  * content: loss[b] += loss_scale * sum((p-t)^2); grad = grad_scale*(p-t)*(p>0) (bf16, may be NULL). */
 int isx_content_mse_fwd_bwd(const isx_bf16* pred, const isx_bf16* target, int target_b, isx_bf16* grad, int B,
                             int64_t per_image, double loss_scale, float grad_scale, double* loss, isx_stream stream);
+/* the same without the fused ReLU backward when relu_mask == 0: grad = grad_scale*(p-t) (autograd of F.mse_loss, utils.py:288) */
+int isx_mse_fwd_bwd(const isx_bf16* pred, const isx_bf16* target, int target_b, isx_bf16* grad, int B, int64_t per_image,
+                    double loss_scale, float grad_scale, int relu_mask, double* loss, isx_stream stream);
+/* out[b,p,c] = a[b,c] + b[b,c] * feat[b,p,c]  [* (feat > 0)]: the backward of per-channel mean / std statistics
+ * (autograd of utils.py:337-338 / classifiers.py:71) is affine in the feature map */
+int isx_channel_affine(const isx_bf16* feat, const float* a, const float* b, isx_bf16* out, int B, int64_t HW, int C,
+                       int relu_mask, isx_stream stream);
 /* sums: double [B,C,2] workspace.  mean/std fp32 [B,C] (std unbiased).  With targets: loss[b] +=
  * loss_scale * sum_c[(mu-mu_t)^2+(sd-sd_t)^2] and affine tap-gradient coefficients aff_a/aff_b [B,C]. */
 int isx_bn_stats_fwd(const isx_bf16* feat, int B, int64_t HW, int C, double* sums, float* mean, float* std_,

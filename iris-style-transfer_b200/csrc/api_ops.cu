@@ -188,6 +188,20 @@ extern "C" int isx_content_mse_fwd_bwd(const isx_bf16* pred, const isx_bf16* tar
   return content_mse(P(pred), P(target), target_b, P(grad), B, per_image, loss_scale, grad_scale, loss, S(stream));
 }
 
+extern "C" int isx_mse_fwd_bwd(const isx_bf16* pred, const isx_bf16* target, int target_b, isx_bf16* grad, int B,
+                               int64_t per_image, double loss_scale, float grad_scale, int relu_mask, double* loss,
+                               isx_stream stream) {
+  ISX_REQUIRE(pred && target && loss, "isx_mse_fwd_bwd: null pointer");
+  ISX_REQUIRE(target_b == 1 || target_b == B, "isx_mse_fwd_bwd: target batch %d must be 1 or %d", target_b, B);
+  return content_mse(P(pred), P(target), target_b, P(grad), B, per_image, loss_scale, grad_scale, loss, S(stream), relu_mask);
+}
+
+extern "C" int isx_channel_affine(const isx_bf16* feat, const float* a, const float* b, isx_bf16* out, int B, int64_t HW, int C,
+                                  int relu_mask, isx_stream stream) {
+  ISX_REQUIRE(feat && a && b && out && C % 8 == 0, "isx_channel_affine: bad arguments");
+  return tap_add_mask(nullptr, nullptr, a, b, P(feat), P(out), B, HW, C, S(stream), relu_mask);
+}
+
 extern "C" int isx_bn_stats_fwd(const isx_bf16* feat, int B, int64_t HW, int C, double* sums, float* mean, float* std_,
                                 const float* t_mean, const float* t_std, int target_b, double loss_scale,
                                 double grad_scale, double* loss, float* aff_a, float* aff_b, isx_stream stream) {

@@ -335,7 +335,7 @@ int avgpool2x2_f32(const float* in, float* out, int B, int H, int W, cudaStream_
 __global__ void tap_add_mask_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ add,
                                     const float* __restrict__ aff_a, const float* __restrict__ aff_b,
                                     const __nv_bfloat16* __restrict__ act, __nv_bfloat16* __restrict__ out, long n8,
-                                    int C, long per_image8) {
+                                    int C, long per_image8, int relu_mask) {
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n8;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
     float a[8], v[8], t[8];
@@ -357,16 +357,16 @@ __global__ void tap_add_mask_kernel(const __nv_bfloat16* __restrict__ g, const _
       for (int j = 0; j < 8; ++j) v[j] += aff_a[b * C + c + j] + aff_b[b * C + c + j] * a[j];
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = a[j] > 0.f ? v[j] : 0.f;
+    for (int j = 0; j < 8; ++j) v[j] = (!relu_mask || a[j] > 0.f) ? v[j] : 0.f;
     reinterpret_cast<uint4*>(out)[i] = pack8(v);
   }
 }
 
 int tap_add_mask(const __nv_bfloat16* g, const __nv_bfloat16* add, const float* aff_a, const float* aff_b,
-                 const __nv_bfloat16* act, __nv_bfloat16* out, int B, long HW, int C, cudaStream_t s) {
+                 const __nv_bfloat16* act, __nv_bfloat16* out, int B, long HW, int C, cudaStream_t s, int relu_mask) {
   const long n8 = static_cast<long>(B) * HW * C / 8;
   const int blocks = static_cast<int>(std::min<long>((n8 + 255) / 256, static_cast<long>(isx_num_sms()) * 16));
-  tap_add_mask_kernel<<<blocks, 256, 0, s>>>(g, add, aff_a, aff_b, act, out, n8, C, HW * C / 8);
+  tap_add_mask_kernel<<<blocks, 256, 0, s>>>(g, add, aff_a, aff_b, act, out, n8, C, HW * C / 8, relu_mask);
   ISX_LAUNCH_CHECK();
   return 0;
 }
@@ -459,7 +459,7 @@ int gram_finalize(const float* partial, int B, int splits, int C, float inv_n, f
 __global__ void __launch_bounds__(256)
 content_mse_kernel(const __nv_bfloat16* __restrict__ pred, const __nv_bfloat16* __restrict__ target, int target_b,
                    __nv_bfloat16* __restrict__ grad, long per_image8, double loss_scale, float grad_scale,
-                   double* __restrict__ loss) {
+                   double* __restrict__ loss, int relu_mask) {
   const int b = blockIdx.y;
   const uint4* p = reinterpret_cast<const uint4*>(pred) + b * per_image8;
   const uint4* t = reinterpret_cast<const uint4*>(target) + (target_b > 1 ? b : 0) * per_image8;
@@ -474,7 +474,7 @@ content_mse_kernel(const __nv_bfloat16* __restrict__ pred, const __nv_bfloat16* 
     for (int j = 0; j < 8; ++j) {
       const float d = a[j] - c[j];
       acc = fmaf(d, d, acc);
-      o[j] = a[j] > 0.f ? d * grad_scale : 0.f;
+      o[j] = (!relu_mask || a[j] > 0.f) ? d * grad_scale : 0.f;
     }
     if (g) g[i] = pack8(o);
   }
@@ -490,12 +490,12 @@ content_mse_kernel(const __nv_bfloat16* __restrict__ pred, const __nv_bfloat16* 
 }
 
 int content_mse(const __nv_bfloat16* pred, const __nv_bfloat16* target, int target_b, __nv_bfloat16* grad, int B,
-                long per_image, double loss_scale, float grad_scale, double* loss, cudaStream_t s) {
+                long per_image, double loss_scale, float grad_scale, double* loss, cudaStream_t s, int relu_mask) {
   ISX_REQUIRE(per_image % 8 == 0, "content_mse: per-image size %ld not a multiple of 8", per_image);
   const long n8 = per_image / 8;
   int bx = static_cast<int>(std::min<long>((n8 + 255) / 256, static_cast<long>(isx_num_sms()) * 8 / std::max(1, std::min(B, 8)) + 1));
   dim3 grid(bx, B);
-  content_mse_kernel<<<grid, 256, 0, s>>>(pred, target, target_b, grad, n8, loss_scale, grad_scale, loss);
+  content_mse_kernel<<<grid, 256, 0, s>>>(pred, target, target_b, grad, n8, loss_scale, grad_scale, loss, relu_mask);
   ISX_LAUNCH_CHECK();
   return 0;
 }
@@ -592,6 +592,32 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int B, int C
       if (threadIdx.x == 0) atomicAdd(loss + b, v * loss_scale);
     }
   }
+}
+
+// mean / unbiased std from what the Gram kernel left behind: S1 = sum over splits of its fused channel sums, S2 = sum over
+// splits of the diagonal of the raw Gram partials (sum of squares); double arithmetic from here on
+__global__ void stats_from_gram_kernel(const float* __restrict__ partial, const float* __restrict__ csum, int splits, int C,
+                                       double n, float* __restrict__ mean, float* __restrict__ stdv, long out_ld) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int s = 0; s < splits; ++s) {
+      s1 += static_cast<double>(csum[(static_cast<long>(b) * splits + s) * C + c]);
+      s2 += static_cast<double>(partial[((static_cast<long>(b) * splits + s) * C + c) * C + c]);
+    }
+    const double mu = s1 / n;
+    double var = (s2 - s1 * mu) / (n - 1.0);
+    if (var < 0.0) var = 0.0;
+    mean[b * out_ld + c] = static_cast<float>(mu);
+    stdv[b * out_ld + c] = static_cast<float>(sqrt(var));
+  }
+}
+
+int stats_from_gram(const float* partial, const float* csum, int B, int splits, int C, long HW, float* mean, float* stdv,
+                    long out_ld, cudaStream_t s) {
+  stats_from_gram_kernel<<<B, 128, 0, s>>>(partial, csum, splits, C, static_cast<double>(HW), mean, stdv, out_ld);
+  ISX_LAUNCH_CHECK();
+  return 0;
 }
 
 int bn_finalize(const double* sums, int B, int C, long HW, float* mean, float* stdv, const float* t_mean,

@@ -44,6 +44,8 @@ struct GramParams {
   int n_units;
   GramUnit units[6];
   float* partial;  // [B][splits][C][C]
+  float* csum;     // optional [B][splits][C]: per-channel sums of the (weighted) features, C <= 128 only -- one extra N = 16
+                   // MMA per 16 pixels against a constant tile whose column 0 is 1 (the tensor core adds the channel up)
   // MASKED only
   const float* mask;          // [mask_b][HW]
   int mask_b;
@@ -60,7 +62,8 @@ gram_sym_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = p.stages;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * p.stage_bytes);
+  uint8_t* ones = smem + stages * p.stage_bytes;                       // [KP][128 B], only when p.csum
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ones + (p.csum ? kBlkBytes : 0));
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* xf_bar = empty_bar + stages;
   uint64_t* tmem_full_bar = xf_bar + stages;
@@ -90,10 +93,20 @@ gram_sym_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
+  const int ncols = p.csum ? (N == 64 ? 128 : 256) : N;   // + 16 columns for the channel sums, power of two
   if (warp == 1) {
-    if (N == 256) tmem_alloc<256>(tmem_ptr_smem);
-    else if (N == 128) tmem_alloc<128>(tmem_ptr_smem);
+    if (ncols == 256) tmem_alloc<256>(tmem_ptr_smem);
+    else if (ncols == 128) tmem_alloc<128>(tmem_ptr_smem);
     else tmem_alloc<64>(tmem_ptr_smem);
+  }
+  if (p.csum && warp >= 2 && warp < 6) {  // constant B tile: element (pixel r, channel 0) = 1, MN-major SWIZZLE_128B
+    const int t = threadIdx.x - 64;
+    for (int i = t; i < KP * 8; i += 128) {
+      const int r = i >> 3, c16 = i & 7;
+      const uint32_t one = (c16 == (r & 7)) ? 0x00003F80u : 0u;   // logical chunk 0 sits at physical chunk r % 8
+      *reinterpret_cast<uint4*>(ones + r * 128 + c16 * 16) = make_uint4(one, 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -120,6 +133,8 @@ gram_sym_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
       // issue-thread rules of profiles/r01_umma_issue_probe.txt: descriptor built once and advanced by immediates,
       // running ring counters
       const uint32_t idesc = umma_idesc_bf16(128, N, true, true);
+      const uint32_t idesc1 = umma_idesc_bf16(128, 16, true, true);
+      const uint32_t ones_lo = static_cast<uint32_t>(umma_desc_sw128(smem_u32(ones), kBlkBytes, 1024));
       const uint64_t d0 = umma_desc_sw128(smem_u32(smem), kBlkBytes, 1024);
       const uint32_t d_hi = static_cast<uint32_t>(d0 >> 32);
       const uint32_t lo0 = static_cast<uint32_t>(d0);
@@ -137,6 +152,8 @@ gram_sym_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < KP / 16; ++k) {
           umma_bf16_lohi(tmem_base, cur + a_off + ((k * 2048) >> 4), d_hi, cur + b_off + ((k * 2048) >> 4), d_hi, idesc, acc);
+          if (p.csum)
+            umma_bf16_lohi(tmem_base + N, cur + a_off + ((k * 2048) >> 4), d_hi, ones_lo + ((k * 2048) >> 4), d_hi, idesc1, acc);
           acc = 1u;
         }
         umma_commit(&empty_bar[s]);
@@ -167,6 +184,15 @@ gram_sym_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
         for (int i = 0; i < 32; i += 4)
           *reinterpret_cast<uint4*>(dst + c0 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
+    }
+    if (p.csum) {
+      uint32_t v[16];
+      v[0] = 0u;
+      if (any) {
+        tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + N, v);
+        tmem_ld_wait();
+      }
+      if (ch < p.C) p.csum[(static_cast<size_t>(b) * p.splits + split) * p.C + ch] = __uint_as_float(v[0]);
     }
     tc_fence_before();
   } else if (MASKED) {
@@ -209,8 +235,8 @@ gram_sym_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    if (N == 256) tmem_dealloc<256>(tmem_base);
-    else if (N == 128) tmem_dealloc<128>(tmem_base);
+    if (ncols == 256) tmem_dealloc<256>(tmem_base);
+    else if (ncols == 128) tmem_dealloc<128>(tmem_base);
     else tmem_dealloc<64>(tmem_base);
   }
 }
@@ -295,13 +321,14 @@ int gram_mask_flags(const float* m, int mask_b, int HW, int C, uint8_t* flags, c
 
 template <int KP, bool MASKED>
 static int launch_gram(const __nv_bfloat16* feat, int B, int HW, int C, int splits, float* partial, const GramMask* mask,
-                       cudaStream_t stream) {
+                       float* csum, cudaStream_t stream) {
   GramParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.HW = HW; p.C = C; p.splits = splits;
   p.chunk = ((HW + splits - 1) / splits + KP - 1) / KP * KP;
   p.n_units = build_units(C, p.units);
   p.partial = partial;
+  p.csum = csum;
   int max_load = 0;
   for (int i = 0; i < p.n_units; ++i) max_load = std::max(max_load, p.units[i].nload);
   p.stage_bytes = max_load * KP * 128;
@@ -313,7 +340,7 @@ static int launch_gram(const __nv_bfloat16* feat, int B, int HW, int C, int spli
     p.mask = mask->m; p.mask_b = mask->mask_b; p.kb_flags = mask->kb_flags; p.fm2 = mask->fm2;
     p.n_kb_total = (HW + KP - 1) / KP;
   }
-  const size_t smem_bytes = 1024 + static_cast<size_t>(stages) * p.stage_bytes + 256;
+  const size_t smem_bytes = 1024 + static_cast<size_t>(stages) * p.stage_bytes + (csum ? KP * 128 : 0) + 256;
   CUtensorMap tmF;
   uint64_t dims[3] = {(uint64_t)C, (uint64_t)HW, (uint64_t)B};
   uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)HW * C * 2};
@@ -332,17 +359,18 @@ static int launch_gram(const __nv_bfloat16* feat, int B, int HW, int C, int spli
 }
 
 int gram_sym_partial(const __nv_bfloat16* feat, int B, int HW, int C, int splits, float* partial, const GramMask* mask,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, float* csum) {
   ISX_REQUIRE(B > 0 && HW > 0, "gram: empty feature map");
   ISX_REQUIRE(splits >= 1, "gram: splits must be >= 1");
   ISX_REQUIRE(C == 64 || C == 128 || C == 256 || C == 512, "gram: C=%d unsupported (64/128/256/512)", C);
+  ISX_REQUIRE(csum == nullptr || C <= 128, "gram: fused channel sums exist for C <= 128 only");
   if (mask) {
     ISX_REQUIRE(mask->m && mask->kb_flags && mask->fm2 && (mask->mask_b == 1 || mask->mask_b == B), "gram: bad mask arguments");
-    return C <= 128 ? launch_gram<64, true>(feat, B, HW, C, splits, partial, mask, stream)
-                    : launch_gram<32, true>(feat, B, HW, C, splits, partial, mask, stream);
+    return C <= 128 ? launch_gram<64, true>(feat, B, HW, C, splits, partial, mask, csum, stream)
+                    : launch_gram<32, true>(feat, B, HW, C, splits, partial, mask, csum, stream);
   }
-  return C <= 128 ? launch_gram<64, false>(feat, B, HW, C, splits, partial, nullptr, stream)
-                  : launch_gram<32, false>(feat, B, HW, C, splits, partial, nullptr, stream);
+  return C <= 128 ? launch_gram<64, false>(feat, B, HW, C, splits, partial, nullptr, csum, stream)
+                  : launch_gram<32, false>(feat, B, HW, C, splits, partial, nullptr, csum, stream);
 }
 
 int gram_tc_partial(const __nv_bfloat16* feat, int B, int HW, int C, int splits, float* partial, cudaStream_t stream) {

@@ -53,8 +53,9 @@ struct GramMask {
   const uint8_t* kb_flags;
   __nv_bfloat16* fm2;
 };
+// csum (optional, C <= 128): fp32 [B][splits][C] per-channel sums of the features, computed by the tensor core alongside
 int gram_sym_partial(const __nv_bfloat16* feat, int B, int HW, int C, int splits, float* partial, const GramMask* mask,
-                     cudaStream_t stream);
+                     cudaStream_t stream, float* csum = nullptr);
 int gram_mask_flags_bytes(int mask_b, int HW, int C);
 int gram_mask_flags(const float* m, int mask_b, int HW, int C, uint8_t* flags, cudaStream_t stream);
 

@@ -19,7 +19,7 @@ int maxpool_fwd(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W
 int maxpool_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* act, __nv_bfloat16* dx, int B, int H, int W, int C,
                 cudaStream_t s);
 int tap_add_mask(const __nv_bfloat16* g, const __nv_bfloat16* add, const float* aff_a, const float* aff_b,
-                 const __nv_bfloat16* act, __nv_bfloat16* out, int B, long HW, int C, cudaStream_t s);
+                 const __nv_bfloat16* act, __nv_bfloat16* out, int B, long HW, int C, cudaStream_t s, int relu_mask = 1);
 int mask_features(const __nv_bfloat16* f, const float* m, int mask_b, __nv_bfloat16* fm, __nv_bfloat16* fm2, int B,
                   long HW, int C, cudaStream_t s);
 int avgpool2x2_f32(const float* in, float* out, int B, int H, int W, cudaStream_t s);
@@ -27,8 +27,10 @@ int gram_finalize(const float* partial, int B, int splits, int C, float inv_n, f
                   int target_b, double loss_scale, double* loss, float grad_scale, __nv_bfloat16* D_out,
                   cudaStream_t s, float* triu = nullptr, long triu_ld = 0);
 int content_mse(const __nv_bfloat16* pred, const __nv_bfloat16* target, int target_b, __nv_bfloat16* grad, int B,
-                long per_image, double loss_scale, float grad_scale, double* loss, cudaStream_t s);
+                long per_image, double loss_scale, float grad_scale, double* loss, cudaStream_t s, int relu_mask = 1);
 int chan_sums(const __nv_bfloat16* f, int B, long HW, int C, double* sums, cudaStream_t s);
+int stats_from_gram(const float* partial, const float* csum, int B, int splits, int C, long HW, float* mean, float* stdv,
+                    long out_ld, cudaStream_t s);
 int bn_finalize(const double* sums, int B, int C, long HW, float* mean, float* stdv, const float* t_mean,
                 const float* t_std, int target_b, double loss_scale, double grad_scale, double* loss, float* aff_a,
                 float* aff_b, cudaStream_t s, long out_ld = 0);  // out_ld: row stride of mean / stdv (0 = C)

@@ -27,7 +27,7 @@ struct Layout {
   size_t pool[5];     // byte offsets of pool outputs
   size_t gradA, gradB, tapbuf;
   size_t cgrad[ISX_MAX_TAPS];
-  size_t gram_ws, D[ISX_MAX_TAPS], sums, aff_a[ISX_MAX_TAPS], aff_b[ISX_MAX_TAPS];
+  size_t gram_ws, D[ISX_MAX_TAPS], sums, csum, aff_a[ISX_MAX_TAPS], aff_b[ISX_MAX_TAPS];
   size_t fm2[ISX_MAX_TAPS], kbflags[ISX_MAX_TAPS];  // row G': F * m^2 (Gram-backward operand), non-zero K-block flags
   size_t total;
 };
@@ -75,12 +75,13 @@ int make_layout(const isx_nst_config* c, Layout* L) {
     L->cgrad[t] = off;
     off += align_up(static_cast<size_t>(c->B) * L->H[kLevel[i]] * L->W[kLevel[i]] * kCout[i] * 2);
   }
-  size_t gram_ws = 256;
+  size_t gram_ws = 256, csum_ws = 256;
   for (int t = 0; t < c->n_style; ++t) {
     const int i = c->style_conv[t];
     const int C = kCout[i];
     const int HW = L->H[kLevel[i]] * L->W[kLevel[i]];
     gram_ws = std::max<size_t>(gram_ws, static_cast<size_t>(gram_pick_splits(c->B, HW, C)) * c->B * C * C * 4);
+    if (C <= 128) csum_ws = std::max<size_t>(csum_ws, static_cast<size_t>(gram_pick_splits(c->B, HW, C)) * c->B * C * 4);
     L->D[t] = off; off += align_up(static_cast<size_t>(c->B) * C * C * 2);
     L->aff_a[t] = off; off += align_up(static_cast<size_t>(c->B) * C * 4);
     L->aff_b[t] = off; off += align_up(static_cast<size_t>(c->B) * C * 4);
@@ -93,6 +94,7 @@ int make_layout(const isx_nst_config* c, Layout* L) {
   }
   L->gram_ws = off; off += align_up(gram_ws);
   L->sums = off; off += align_up(static_cast<size_t>(c->B) * 512 * 2 * 8);
+  L->csum = off; off += align_up(csum_ws);   // fused channel sums of the Gram kernel (feature extraction, C <= 128)
   L->total = off;
   return 0;
 }
@@ -412,29 +414,33 @@ extern "C" int isx_nst_style_features(const isx_nst_config* c, const isx_nst_buf
     need += (want_stats ? 2 * C : 0) + (want_gram ? C * (C + 1) / 2 : 0);
   }
   ISX_REQUIRE(ld >= need, "isx_nst_style_features: row stride %lld < feature dimension %lld", (long long)ld, (long long)need);
-  int64_t off = 0;
-  if (want_stats) {
-    double* sums = reinterpret_cast<double*>(static_cast<char*>(b->workspace) + L.sums);
-    for (int t = 0; t < c->n_style; ++t) {
-      const int i = c->style_conv[t], lv = kLevel[i], C = kCout[i];
-      const long HW = static_cast<long>(L.H[lv]) * L.W[lv];
-      ISX_REQUIRE(HW >= 2, "isx_nst_style_features: unbiased std needs >= 2 pixels at conv %d", i);
+  // column offsets: [per tap: mean | std] then [per tap: Gram upper triangle]
+  int64_t stat_off[ISX_MAX_TAPS], gram_off[ISX_MAX_TAPS], off = 0;
+  for (int t = 0; t < c->n_style; ++t) { stat_off[t] = off; if (want_stats) off += 2 * kCout[c->style_conv[t]]; }
+  for (int t = 0; t < c->n_style; ++t) { gram_off[t] = off; if (want_gram) off += static_cast<int64_t>(kCout[c->style_conv[t]]) * (kCout[c->style_conv[t]] + 1) / 2; }
+  double* sums = reinterpret_cast<double*>(static_cast<char*>(b->workspace) + L.sums);
+  for (int t = 0; t < c->n_style; ++t) {
+    const int i = c->style_conv[t], lv = kLevel[i], C = kCout[i];
+    const int HW = L.H[lv] * L.W[lv];
+    ISX_REQUIRE(!want_stats || HW >= 2, "isx_nst_style_features: unbiased std needs >= 2 pixels at conv %d", i);
+    const int splits = gram_pick_splits(B, HW, C);
+    // C <= 128 (HBM-bound layers, 80 % of the feature bytes): when both outputs are wanted, the statistics come out of the
+    // Gram pass itself -- sum f from one extra N = 16 MMA per 16 pixels, sum f^2 from the Gram diagonal -- instead of a
+    // second pass over the map
+    const bool fused = want_stats && want_gram && C <= 128;
+    if (want_stats && !fused) {
       ISX_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * B * C * 2, s));
       if (int rc = chan_sums(at(b, L.act[i]), B, HW, C, sums, s)) return rc;
-      if (int rc = bn_finalize(sums, B, C, HW, out + off, out + off + C, nullptr, nullptr, 1, 0.0, 0.0, nullptr, nullptr,
-                               nullptr, s, ld)) return rc;
-      off += 2 * C;
+      if (int rc = bn_finalize(sums, B, C, HW, out + stat_off[t], out + stat_off[t] + C, nullptr, nullptr, 1, 0.0, 0.0, nullptr,
+                               nullptr, nullptr, s, ld)) return rc;
     }
-  }
-  if (want_gram) {
-    for (int t = 0; t < c->n_style; ++t) {
-      const int i = c->style_conv[t], lv = kLevel[i], C = kCout[i];
-      const int HW = L.H[lv] * L.W[lv];
-      const int splits = gram_pick_splits(B, HW, C);
-      if (int rc = gram_sym_partial(at(b, L.act[i]), B, HW, C, splits, atf(b, L.gram_ws), nullptr, s)) return rc;
+    if (want_gram) {
+      float* csum = fused ? atf(b, L.csum) : nullptr;
+      if (int rc = gram_sym_partial(at(b, L.act[i]), B, HW, C, splits, atf(b, L.gram_ws), nullptr, s, csum)) return rc;
+      if (fused)
+        if (int rc = stats_from_gram(atf(b, L.gram_ws), csum, B, splits, C, HW, out + stat_off[t], out + stat_off[t] + C, ld, s)) return rc;
       if (int rc = gram_finalize(atf(b, L.gram_ws), B, splits, C, static_cast<float>(1.0 / (static_cast<double>(C) * HW)),
-                                 nullptr, nullptr, 1, 0.0, nullptr, 0.f, nullptr, s, out + off, ld)) return rc;
-      off += static_cast<int64_t>(C) * (C + 1) / 2;
+                                 nullptr, nullptr, 1, 0.0, nullptr, 0.f, nullptr, s, out + gram_off[t], ld)) return rc;
     }
   }
   return 0;

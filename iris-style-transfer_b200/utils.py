@@ -61,8 +61,63 @@ def GramMatrix(x: torch.Tensor) -> torch.Tensor:
     return G[0] if unbatched else G
 
 
+class _MseFunction(torch.autograd.Function):
+    """F.mse_loss(p, t) (mean over ALL elements, utils.py:288) with its gradient from ONE kernel pass (isx_mse_fwd_bwd)."""
+
+    @staticmethod
+    def forward(ctx, p, t):
+        unb = p.dim() == 3
+        pn, tn = _to_nhwc_bf16(p), _to_nhwc_bf16(t)
+        B = pn.shape[0]
+        per_image = pn[0].numel()
+        n = float(per_image * B)
+        loss = torch.zeros(B, device=p.device, dtype=torch.float64)
+        grad = torch.empty_like(pn)
+        with torch.cuda.device(p.device):
+            _lib.call("isx_mse_fwd_bwd", pn, tn, tn.shape[0], grad, B, _lib.i64(per_image), _lib.f64(1.0 / n),
+                      _lib.f32(2.0 / n), 0, loss, _lib.stream_ptr())
+        ctx.save_for_backward(grad)
+        ctx.unb = unb
+        return loss.sum().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        d = grad.permute(0, 3, 1, 2).float() * g
+        return (d[0] if ctx.unb else d), None
+
+
+class _ChannelStatsFunction(torch.autograd.Function):
+    """(mean, unbiased std) over (H,W) per (image, channel) -- utils.py:337-338, classifiers.py:71 -- from isx_bn_stats_fwd;
+    the backward is affine in the feature map, dF = g_mean/n + g_std (F - mean) / ((n-1) std), one pass of isx_channel_affine."""
+
+    @staticmethod
+    def forward(ctx, p):
+        unb = p.dim() == 3
+        f = _to_nhwc_bf16(p)
+        mean, std = stats_of(f)
+        ctx.save_for_backward(f, mean, std)
+        ctx.unb = unb
+        return (mean[0], std[0]) if unb else (mean, std)
+
+    @staticmethod
+    def backward(ctx, g_mean, g_std):
+        f, mean, std = ctx.saved_tensors
+        B, H, W, C = f.shape
+        n = float(H * W)
+        if ctx.unb:
+            g_mean, g_std = g_mean[None], g_std[None]
+        bcoef = torch.where(std > 0, g_std.float() / ((n - 1.0) * std), torch.zeros_like(std))
+        acoef = (g_mean.float() / n - bcoef * mean).contiguous()
+        out = torch.empty_like(f)
+        with torch.cuda.device(f.device):
+            _lib.call("isx_channel_affine", f, acoef, bcoef.contiguous(), out, B, _lib.i64(H * W), C, 0, _lib.stream_ptr())
+        d = out.permute(0, 3, 1, 2).float()
+        return d[0] if ctx.unb else d
+
+
 class ContentLoss_L2(torch.nn.Module):
-    """utils.py:259-290 (forward only; the differentiable path is nst()'s fused driver)."""
+    """utils.py:259-290; differentiable through _MseFunction (nst() itself uses the fused driver)."""
 
     def __init__(self, targets: List[torch.Tensor] = None, weights: List[float] = None) -> None:
         super().__init__()
@@ -71,9 +126,9 @@ class ContentLoss_L2(torch.nn.Module):
 
     def forward(self, preds: List[torch.Tensor]) -> torch.Tensor:
         if torch.is_grad_enabled() and any(p.requires_grad for p in preds):
-            loss = 0  # the reference's own expression (utils.py:285-290); autograd supplies d/dp
+            loss = 0  # utils.py:285-290 with the mse and its gradient computed by libisx
             for p, t, w in zip(preds, self.targets, self.weights):
-                loss = loss + torch.nn.functional.mse_loss(p, t) * w
+                loss = loss + _MseFunction.apply(p, t) * w
             return loss * 0.5
         with torch.no_grad():
             return self._forward_kernels(preds)
@@ -119,9 +174,9 @@ class StyleLoss_BN(torch.nn.Module):
 
     def forward(self, preds: List[torch.Tensor]) -> torch.Tensor:
         if torch.is_grad_enabled() and any(p.requires_grad for p in preds):
-            loss = 0  # the reference's own expression (utils.py:350-355); autograd supplies d/dp
+            loss = 0  # utils.py:350-355; the statistics and their backward run in libisx, the (B,C) arithmetic is plain torch
             for p, tm, ts, w in zip(preds, self.targets_mean, self.targets_std, self.weights):
-                pm, ps = p.mean(dim=(-2, -1)), p.std(dim=(-2, -1))
+                pm, ps = _ChannelStatsFunction.apply(p)
                 loss = loss + ((pm - tm) ** 2 + (ps - ts) ** 2).sum() * w / pm.shape[-1]
             return loss
         with torch.no_grad():
