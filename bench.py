@@ -433,6 +433,7 @@ def main():
     ap.add_argument("--smem-reserve-kb", type=int, default=0, help="shared memory per SM the persistent conv CTAs leave free")
     ap.add_argument("--history-bf16", action="store_true", help="opt-in: store the L-BFGS (s, y) history in bf16")
     ap.add_argument("--feature-images", type=int, default=512, help="images per GPU of the feature-extraction leg")
+    ap.add_argument("--feature-batch", type=int, default=32, help="images per forward pass of the feature-extraction leg")
     ap.add_argument("--e2e-evals", type=int, default=300, help="evaluations of the end-to-end job (BASELINE config[1]: 300)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -477,7 +478,7 @@ def main():
 
     # ------------------------------------------------------------------ feature-only configs
     if cfgname in ("feat4", "feat5"):
-        feat = feature_leg(dev, vgg, cfgname == "feat5", args.feature_images, world)
+        feat = feature_leg(dev, vgg, cfgname == "feat5", args.feature_images, world, batch=args.feature_batch)
         if rank == 0:
             line = {"metric": feat["metric"], "value": feat["value"], "unit": "images/s", "n_gpus": world, "steps": 1,
                     "warmup": 1, "ms_per_step": 1e3 * feat["n_images"] / feat["value"], "higher_is_better": True,
@@ -591,8 +592,8 @@ def main():
     # ------------------------------------------------------------------ secondary metric: Gram-feature images/s
     feat = feat5 = None
     if not args.no_features and cfgname == "nst640":
-        feat = feature_leg(dev, vgg, False, args.feature_images, world)
-        feat5 = feature_leg(dev, vgg, True, args.feature_images, world)
+        feat = feature_leg(dev, vgg, False, args.feature_images, world, batch=args.feature_batch)
+        feat5 = feature_leg(dev, vgg, True, args.feature_images, world, batch=args.feature_batch)
 
     if rank != 0:
         finish()
