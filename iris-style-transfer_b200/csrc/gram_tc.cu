@@ -196,34 +196,45 @@ gram_sym_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
     }
     tc_fence_before();
   } else if (MASKED) {
-    // transform warps: tile row (= pixel) *= m[pixel] in place; F * m^2 of the A blocks goes to global memory
+    // transform warps: tile row (= pixel) *= m[pixel] in place; F * m^2 of the A blocks goes to global memory.
+    // Thread t owns 16-byte chunk (t & 7) of rows (t >> 3) + 16 j: its KP/16 mask values are fetched BEFORE it waits for the
+    // tile, so the global-load latency hides behind the TMA (a per-row load inside the loop made this stage latency-bound).
     const int t = threadIdx.x - 192;
+    const int r0 = t >> 3, c16 = t & 7;
     const float* mrow = p.mask + static_cast<long>(p.mask_b > 1 ? b : 0) * p.HW;
     int s = 0;
     uint32_t ph = 0;
-    const int n_chunks = u.nload * KP * 8;
     for (int kb = 0; kb < num_kb; ++kb) {
       if (!active(kb)) continue;
+      const int pix0 = p_begin + kb * KP;
+      float mv[KP / 16];
+#pragma unroll
+      for (int j = 0; j < KP / 16; ++j) {
+        const int pix = pix0 + r0 + 16 * j;
+        mv[j] = pix < p.HW ? __ldg(mrow + pix) : 0.f;
+      }
       mbar_wait(&full_bar[s], ph);
       uint8_t* st = smem + s * p.stage_bytes;
-      const int pix0 = p_begin + kb * KP;
-      for (int idx = t; idx < n_chunks; idx += 128) {
-        const int blk = idx / (KP * 8);
-        const int r = (idx >> 3) % KP;
-        const int c16 = idx & 7;
-        const int pix = pix0 + r;
-        const float mv = pix < p.HW ? __ldg(mrow + pix) : 0.f;
-        uint4* ptr = reinterpret_cast<uint4*>(st + blk * kBlkBytes + r * 128 + c16 * 16);
-        const uint4 v = *ptr;
-        float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y), f2 = unpack_bf16x2(v.z), f3 = unpack_bf16x2(v.w);
-        f0.x *= mv; f0.y *= mv; f1.x *= mv; f1.y *= mv; f2.x *= mv; f2.y *= mv; f3.x *= mv; f3.y *= mv;
-        *ptr = make_uint4(pack_bf16x2(f0.x, f0.y), pack_bf16x2(f1.x, f1.y), pack_bf16x2(f2.x, f2.y), pack_bf16x2(f3.x, f3.y));
-        if (u.write_fm2 && blk >= u.a_slot && blk < u.a_slot + 2 && pix < p.HW) {
-          const int chan = u.load_blk[blk] * 64 + ((c16 ^ (r & 7)) << 3);  // 128-byte swizzle: chunk ^ (row % 8)
-          if (chan < p.C)
+      for (int blk = 0; blk < u.nload; ++blk) {
+        const int chan0 = u.load_blk[blk] * 64;
+        if (chan0 >= p.C) continue;                     // zero-filled out-of-bounds block (C = 64): nothing to scale
+        const bool wr = u.write_fm2 && blk >= u.a_slot && blk < u.a_slot + 2;
+#pragma unroll
+        for (int j = 0; j < KP / 16; ++j) {
+          const int r = r0 + 16 * j;
+          uint4* ptr = reinterpret_cast<uint4*>(st + blk * kBlkBytes + r * 128 + c16 * 16);
+          const uint4 v = *ptr;
+          const float m1 = mv[j];
+          float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y), f2 = unpack_bf16x2(v.z), f3 = unpack_bf16x2(v.w);
+          f0.x *= m1; f0.y *= m1; f1.x *= m1; f1.y *= m1; f2.x *= m1; f2.y *= m1; f3.x *= m1; f3.y *= m1;
+          *ptr = make_uint4(pack_bf16x2(f0.x, f0.y), pack_bf16x2(f1.x, f1.y), pack_bf16x2(f2.x, f2.y), pack_bf16x2(f3.x, f3.y));
+          const int pix = pix0 + r;
+          if (wr && pix < p.HW) {
+            const int chan = chan0 + ((c16 ^ (r & 7)) << 3);  // 128-byte swizzle: chunk ^ (row % 8)
             *reinterpret_cast<uint4*>(p.fm2 + (static_cast<long>(b) * p.HW + pix) * p.C + chan) =
-                make_uint4(pack_bf16x2(f0.x * mv, f0.y * mv), pack_bf16x2(f1.x * mv, f1.y * mv),
-                           pack_bf16x2(f2.x * mv, f2.y * mv), pack_bf16x2(f3.x * mv, f3.y * mv));
+                make_uint4(pack_bf16x2(f0.x * m1, f0.y * m1), pack_bf16x2(f1.x * m1, f1.y * m1),
+                           pack_bf16x2(f2.x * m1, f2.y * m1), pack_bf16x2(f3.x * m1, f3.y * m1));
+          }
         }
       }
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
@@ -278,9 +289,10 @@ int gram_pick_splits(int B, int HW, int C) {
   GramUnit tmp[6];
   const int n_units = std::max(1, build_units(C, tmp));
   const int kp = gram_kp(C);
-  // two (C >= 256) to three CTAs per SM, a few waves of them
+  // two (C >= 256) to three CTAs are resident per SM; aim at just UNDER two full waves of them -- rounding the split count
+  // up gave 2.02-2.6 waves, i.e. a third, almost empty wave (ncu: 61-65 % of the DRAM peak on the HBM-bound layers)
   const int per_sm = C >= 256 ? 4 : 6;
-  int want = (per_sm * kNumSMs + B * n_units - 1) / (B * n_units);
+  int want = (per_sm * kNumSMs) / (B * n_units);
   int max_splits = HW / (kp * 4);  // keep >= 4 K blocks per split
   if (max_splits < 1) max_splits = 1;
   if (want > max_splits) want = max_splits;
