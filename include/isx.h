@@ -191,12 +191,14 @@ int isx_clamp01(float* x, int64_t n, isx_stream stream);
 /* ---- fused driver: one closure evaluation of pipelines.py:80-91 ------------------------------- */
 #define ISX_MAX_TAPS 8
 #define ISX_VGG19_CONVS 16
+#define ISX_TAP_POOL0 16       /* tap ids: 0..15 = ReLU output of conv i; 16..20 = output of MaxPool 0..4 (pool1..pool5) */
+#define ISX_VGG19_TAPS 21
 typedef struct {
   int32_t B, H, W, xc;                  /* image batch fp32 [B,xc,H,W] */
   int32_t n_conv;                       /* number of convs to run (deepest tapped conv index + 1) */
   int32_t style_mode;                   /* 0: Gram (utils.StyleLoss_Gram), 1: mean/std (utils.StyleLoss_BN) */
   int32_t n_style;
-  int32_t style_conv[ISX_MAX_TAPS];     /* conv index (0..15) whose ReLU output is tapped */
+  int32_t style_conv[ISX_MAX_TAPS];     /* tap id: conv index (0..15) whose ReLU output is tapped, or ISX_TAP_POOL0 + k */
   float style_w[ISX_MAX_TAPS];
   int32_t n_content;
   int32_t content_conv[ISX_MAX_TAPS];
@@ -228,8 +230,9 @@ typedef struct {
 } isx_nst_buffers;
 
 int64_t isx_nst_workspace_bytes(const isx_nst_config* cfg);
-/* autograd of VGG19.forward alone (pipelines.py:90 when the caller owns the loss): feat_grads[j] = bf16 NHWC gradient
- * w.r.t. the ReLU output of conv j (NULL where none), last_pool_grad = gradient w.r.t. the pool after the deepest conv
+/* autograd of VGG19.forward alone (pipelines.py:90 when the caller owns the loss): feat_grads has ISX_VGG19_TAPS entries,
+ * feat_grads[id] = bf16 NHWC gradient w.r.t. tap id (ReLU output of conv id, or pool id - 16; NULL where none),
+ * last_pool_grad = gradient w.r.t. the pool after the deepest conv
  * (or NULL); uses the activations the preceding isx_nst_forward left in the workspace; grad fp32 [B,xc,H,W]. */
 int isx_nst_backward(const isx_nst_config* cfg, const isx_nst_buffers* bufs, const isx_bf16* const* feat_grads,
                      const isx_bf16* last_pool_grad, float* grad, isx_stream stream);

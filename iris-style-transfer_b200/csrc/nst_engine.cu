@@ -19,6 +19,14 @@ static const int kCout[16] = {64, 64, 128, 128, 256, 256, 256, 256, 512, 512, 51
 static const int kCin[16] = {3, 64, 64, 128, 128, 256, 256, 256, 256, 512, 512, 512, 512, 512, 512, 512};
 static const int kLevel[16] = {0, 0, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4};  // resolution level = #pools before
 static inline bool pool_after(int i) { return i == 1 || i == 3 || i == 7 || i == 11 || i == 15; }
+// Tap ids (isx_nst_config.style_conv / content_conv): 0..15 = ReLU output of that conv, 16..20 = output of pool 0..4
+// (models/vgg/vgg.py:6-10 lets any layer of vgg19.features be tapped, pools included).
+static const int kConvBefore[5] = {1, 3, 7, 11, 15};
+static inline int pool_index(int conv) { return conv == 1 ? 0 : conv == 3 ? 1 : conv == 7 ? 2 : conv == 11 ? 3 : 4; }
+static inline bool tap_is_pool(int id) { return id >= ISX_TAP_POOL0; }
+static inline int tap_conv(int id) { return tap_is_pool(id) ? kConvBefore[id - ISX_TAP_POOL0] : id; }   // the conv that must have run
+static inline int tap_level(int id) { return tap_is_pool(id) ? id - ISX_TAP_POOL0 + 1 : kLevel[id]; }
+static inline int tap_C(int id) { return kCout[tap_conv(id)]; }
 
 namespace {
 struct Layout {
@@ -61,25 +69,26 @@ int make_layout(const isx_nst_config* c, Layout* L) {
     if (conv_before[k] < c->n_conv)
       off += align_up(static_cast<size_t>(c->B) * L->H[k + 1] * L->W[k + 1] * kCout[conv_before[k]] * 2);
   }
+  auto tap_ok = [&](int id) { return id >= 0 && id < ISX_VGG19_TAPS && tap_conv(id) < c->n_conv && L->H[tap_level(id)] >= 1 && L->W[tap_level(id)] >= 1; };
   for (int t = 0; t < c->n_style; ++t) {
     const int i = c->style_conv[t];
-    ISX_REQUIRE(i >= 0 && i < c->n_conv, "nst: style tap conv %d beyond n_conv %d", i, c->n_conv);
-    max_tap = std::max(max_tap, static_cast<size_t>(c->B) * L->H[kLevel[i]] * L->W[kLevel[i]] * kCout[i] * 2);
+    ISX_REQUIRE(tap_ok(i), "nst: style tap conv %d beyond n_conv %d", i, c->n_conv);
+    max_tap = std::max(max_tap, static_cast<size_t>(c->B) * L->H[tap_level(i)] * L->W[tap_level(i)] * tap_C(i) * 2);
   }
   L->gradA = off; off += align_up(max_act);
   L->gradB = off; off += align_up(max_act);
   L->tapbuf = off; off += align_up(std::max<size_t>(max_tap, 256));
   for (int t = 0; t < c->n_content; ++t) {
     const int i = c->content_conv[t];
-    ISX_REQUIRE(i >= 0 && i < c->n_conv, "nst: content tap conv %d beyond n_conv %d", i, c->n_conv);
+    ISX_REQUIRE(tap_ok(i), "nst: content tap conv %d beyond n_conv %d", i, c->n_conv);
     L->cgrad[t] = off;
-    off += align_up(static_cast<size_t>(c->B) * L->H[kLevel[i]] * L->W[kLevel[i]] * kCout[i] * 2);
+    off += align_up(static_cast<size_t>(c->B) * L->H[tap_level(i)] * L->W[tap_level(i)] * tap_C(i) * 2);
   }
   size_t gram_ws = 256, csum_ws = 256;
   for (int t = 0; t < c->n_style; ++t) {
     const int i = c->style_conv[t];
-    const int C = kCout[i];
-    const int HW = L->H[kLevel[i]] * L->W[kLevel[i]];
+    const int C = tap_C(i);
+    const int HW = L->H[tap_level(i)] * L->W[tap_level(i)];
     gram_ws = std::max<size_t>(gram_ws, static_cast<size_t>(gram_pick_splits(c->B, HW, C)) * c->B * C * C * 4);
     if (C <= 128) csum_ws = std::max<size_t>(csum_ws, static_cast<size_t>(gram_pick_splits(c->B, HW, C)) * c->B * C * 4);
     L->D[t] = off; off += align_up(static_cast<size_t>(c->B) * C * C * 2);
@@ -102,6 +111,12 @@ int make_layout(const isx_nst_config* c, Layout* L) {
 inline bf16* at(const isx_nst_buffers* b, size_t off) { return reinterpret_cast<bf16*>(static_cast<char*>(b->workspace) + off); }
 inline float* atf(const isx_nst_buffers* b, size_t off) { return reinterpret_cast<float*>(static_cast<char*>(b->workspace) + off); }
 
+inline size_t tap_off(const Layout& L, int id) { return tap_is_pool(id) ? L.pool[id - ISX_TAP_POOL0] : L.act[id]; }
+bool pool_tapped(const isx_nst_config* c, int k) {
+  for (int t = 0; t < c->n_style; ++t) if (c->style_conv[t] == ISX_TAP_POOL0 + k) return true;
+  for (int t = 0; t < c->n_content; ++t) if (c->content_conv[t] == ISX_TAP_POOL0 + k) return true;
+  return false;
+}
 int style_tap_of(const isx_nst_config* c, int conv) {
   for (int t = 0; t < c->n_style; ++t) if (c->style_conv[t] == conv) return t;
   return -1;
@@ -149,7 +164,7 @@ extern "C" int isx_nst_forward(const isx_nst_config* c, const isx_nst_buffers* b
   if (int rc = make_layout(c, &L)) return rc;
   cudaStream_t s = S(stream);
   for (int i = 0; i < c->n_conv; ++i) {
-    const bool want_pool = pool_after(i) && (i + 1 < c->n_conv || with_last_pool);
+    const bool want_pool = pool_after(i) && (i + 1 < c->n_conv || with_last_pool || pool_tapped(c, pool_index(i)));
     if (int rc = run_conv_fwd(c, b, L, i, x, want_pool && i > 0, s)) return rc;
     if (want_pool && i == 0) {  // (conv1_1 is never followed by a pool in VGG-19; kept for completeness)
       const int lv = kLevel[i];
@@ -194,29 +209,56 @@ struct TapSrc {
 // the tap gradients injected where they arise.  gm = ReLU-masked gradient w.r.t. a conv's output, ready for its dgrad.
 int run_backward(const isx_nst_config* c, const isx_nst_buffers* b, const Layout& L, const TapSrc* src,
                  const bf16* last_pool_grad, float* grad, cudaStream_t s) {
+  // src: ISX_VGG19_TAPS entries, [0..15] sources at conv ReLU outputs, [16..20] sources at pool outputs
   const int B = c->B;
+  auto pool_src = [&](int conv) -> const TapSrc* {   // sources at the pool right after `conv`, if any
+    if (!pool_after(conv)) return nullptr;
+    const TapSrc& ps = src[ISX_TAP_POOL0 + pool_index(conv)];
+    return ps.any() ? &ps : nullptr;
+  };
   int deepest = c->n_conv - 1;  // start at the deepest conv that receives a gradient (layers above it contribute nothing)
   if (!last_pool_grad)
-    while (deepest > 0 && !src[deepest].any()) --deepest;
+    while (deepest > 0 && !src[deepest].any() && !pool_src(deepest)) --deepest;
   bf16* ping = at(b, L.gradA);
   bf16* pong = at(b, L.gradB);
   bf16* tapbuf = at(b, L.tapbuf);
   const bf16* gm = nullptr;
-  auto gram_1x1 = [&](int j, bf16* out, bool mask) -> int {  // out = gram_A . D_b  [* relu'(act_j)]
-    const int lv = kLevel[j];
+  // out = A . D_b  [* relu'(A)]   (Gram tap gradient as a 1x1 tcgen05 GEMM with per-image weights); A lives at tap `id`
+  auto gram_1x1 = [&](int id, bf16* out, bool mask) -> int {
+    const int lv = tap_level(id);
     ConvArgs a;
-    a.in = src[j].gram_A; a.weight = src[j].gram_D; a.out = out;
-    a.B = B; a.H = L.H[lv]; a.W = L.W[lv]; a.Cin = kCout[j]; a.Cout = kCout[j]; a.ntaps = 1; a.per_image_weights = true;
-    a.mask_act = mask ? at(b, L.act[j]) : nullptr;
+    a.in = src[id].gram_A; a.weight = src[id].gram_D; a.out = out;
+    a.B = B; a.H = L.H[lv]; a.W = L.W[lv]; a.Cin = tap_C(id); a.Cout = tap_C(id); a.ntaps = 1; a.per_image_weights = true;
+    a.mask_act = mask ? at(b, tap_off(L, id)) : nullptr;
     return conv_tc(a, s);
+  };
+  // gradient w.r.t. a POOL output: out = g (may be NULL) + every source of that pool tap; no ReLU mask (the max-pool
+  // backward that follows applies the ReLU mask of the pre-pool activation)
+  auto pool_combine = [&](int k, const bf16* g, bf16* out) -> int {
+    const int id = ISX_TAP_POOL0 + k, lv = k + 1, C = tap_C(id);
+    const long HW = static_cast<long>(L.H[lv]) * L.W[lv];
+    const TapSrc& t = src[id];
+    const bf16* add2 = t.add;
+    if (t.gram_D) {
+      if (int rc = gram_1x1(id, tapbuf, false)) return rc;
+      if (t.add)
+        if (int rc = tap_add_mask(t.add, tapbuf, nullptr, nullptr, at(b, L.pool[k]), tapbuf, B, HW, C, s, 0)) return rc;
+      add2 = tapbuf;
+    }
+    return tap_add_mask(g, add2, t.aa, t.ab, at(b, L.pool[k]), out, B, HW, C, s, 0);
   };
   {
     const int i = deepest, lv = kLevel[i], C = kCout[i];
     const long HW = static_cast<long>(L.H[lv]) * L.W[lv];
     const TapSrc& t = src[i];
     const bf16* up = nullptr;  // gradient arriving from above (only through the trailing pool)
-    if (last_pool_grad) {
-      if (int rc = maxpool_bwd(last_pool_grad, at(b, L.act[i]), pong, B, L.H[lv], L.W[lv], C, s)) return rc;
+    const bf16* pg = last_pool_grad;
+    if (pool_src(i)) {          // taps on the pool after the deepest conv
+      if (int rc = pool_combine(pool_index(i), pg, ping)) return rc;
+      pg = ping;
+    }
+    if (pg) {
+      if (int rc = maxpool_bwd(pg, at(b, L.act[i]), pong, B, L.H[lv], L.W[lv], C, s)) return rc;
       up = pong;
     }
     ISX_REQUIRE(up || t.any(), "nst backward: conv %d carries no gradient", i);
@@ -268,7 +310,9 @@ int run_backward(const isx_nst_config* c, const isx_nst_buffers* b, const Layout
       if (int rc = conv_tc(a, s)) return rc;
       gm = a.out;
     } else {
-      if (int rc = conv_tc(a, s)) return rc;  // gradient w.r.t. the pooled map: no ReLU, no tap
+      if (int rc = conv_tc(a, s)) return rc;  // gradient w.r.t. the pooled map: no ReLU
+      if (pool_src(j))                        // taps on this pool add their gradient in place
+        if (int rc = pool_combine(pool_index(j), a.out, a.out)) return rc;
       // `other` held this dgrad's input, which is consumed now
       if (int rc = maxpool_bwd(a.out, at(b, L.act[j]), other, B, L.H[lvj], L.W[lvj], Cj, s)) return rc;
       gm = other;
@@ -308,18 +352,19 @@ extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, c
   cudaStream_t s = S(stream);
   const int B = c->B;
   const int deepest = c->n_conv - 1;
-  ISX_REQUIRE(style_tap_of(c, deepest) >= 0 || content_tap_of(c, deepest) >= 0, "isx_nst_eval: conv %d is not tapped",
-              deepest);
+  const bool last_pool_tapped = pool_after(deepest) && pool_tapped(c, pool_index(deepest));
+  ISX_REQUIRE(style_tap_of(c, deepest) >= 0 || content_tap_of(c, deepest) >= 0 || last_pool_tapped,
+              "isx_nst_eval: conv %d is not tapped", deepest);
   ISX_CHECK_CUDA(cudaMemsetAsync(loss_c, 0, sizeof(double) * B, s));
   ISX_CHECK_CUDA(cudaMemsetAsync(loss_s, 0, sizeof(double) * B, s));
 
-  // ---------------- forward + losses ----------------
-  for (int i = 0; i < c->n_conv; ++i) {
-    if (int rc = run_conv_fwd(c, b, L, i, x, pool_after(i) && i + 1 < c->n_conv, s)) return rc;
-    const int lv = kLevel[i];
-    const int C = kCout[i];
+  // losses of everything tapped at `id` (a conv's ReLU output or a pool output), evaluated on the stored activation
+  auto tap_losses = [&](int id) -> int {
+    const int lv = tap_level(id);
+    const int C = tap_C(id);
     const long HW = static_cast<long>(L.H[lv]) * L.W[lv];
-    const int st = style_tap_of(c, i);
+    const bf16* act = at(b, tap_off(L, id));
+    const int st = style_tap_of(c, id);
     if (st >= 0) {
       const double w = c->style_w[st];
       if (c->style_mode == 0) {  // StyleLoss_Gram (utils.py:317-322); GramMatrix n = C*H*W (utils.py:254)
@@ -332,48 +377,58 @@ extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, c
           gm.kb_flags = reinterpret_cast<const uint8_t*>(at(b, L.kbflags[st]));  // isx_nst_prepare_style_masks
           gm.fm2 = at(b, L.fm2[st]);
         }
-        int rc = gram_sym_partial(at(b, L.act[i]), B, static_cast<int>(HW), C, gram_pick_splits(B, static_cast<int>(HW), C),
-                                  atf(b, L.gram_ws), c->style_mask_b > 0 ? &gm : nullptr, s);
+        const int splits = gram_pick_splits(B, static_cast<int>(HW), C);
+        int rc = gram_sym_partial(act, B, static_cast<int>(HW), C, splits, atf(b, L.gram_ws), c->style_mask_b > 0 ? &gm : nullptr, s);
         if (rc) return rc;
-        rc = gram_finalize(atf(b, L.gram_ws), B, gram_pick_splits(B, static_cast<int>(HW), C), C,
-                           static_cast<float>(inv_n), nullptr, b->gram_target[st], c->style_target_b, 0.25 * w, loss_s,
-                           static_cast<float>(c->s_weight * w * inv_n), at(b, L.D[st]), s);
+        rc = gram_finalize(atf(b, L.gram_ws), B, splits, C, static_cast<float>(inv_n), nullptr, b->gram_target[st],
+                           c->style_target_b, 0.25 * w, loss_s, static_cast<float>(c->s_weight * w * inv_n), at(b, L.D[st]), s);
         if (rc) return rc;
       } else {  // StyleLoss_BN (utils.py:350-355)
         ISX_REQUIRE(b->bn_target_mean[st] && b->bn_target_std[st], "nst: BN target %d missing", st);
-        ISX_REQUIRE(HW >= 2, "nst: unbiased std needs >= 2 pixels at conv %d", i);
+        ISX_REQUIRE(HW >= 2, "nst: unbiased std needs >= 2 pixels at tap %d", id);
         double* sums = reinterpret_cast<double*>(static_cast<char*>(b->workspace) + L.sums);
         ISX_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * B * C * 2, s));
-        int rc = chan_sums(at(b, L.act[i]), B, HW, C, sums, s);
+        int rc = chan_sums(act, B, HW, C, sums, s);
         if (rc) return rc;
         rc = bn_finalize(sums, B, C, HW, nullptr, nullptr, b->bn_target_mean[st], b->bn_target_std[st],
                          c->style_target_b, w / C, c->s_weight * w / C, loss_s, atf(b, L.aff_a[st]), atf(b, L.aff_b[st]), s);
         if (rc) return rc;
       }
     }
-    const int ct = content_tap_of(c, i);
+    const int ct = content_tap_of(c, id);
     if (ct >= 0) {  // ContentLoss_L2 (utils.py:285-290): 0.5 * w * mean((p-t)^2)
       ISX_REQUIRE(b->content_target[ct], "nst: content target %d missing", ct);
       const long per_image = HW * C;
       const double denom = static_cast<double>(per_image) * (c->coupled ? B : 1);
-      int rc = content_mse(at(b, L.act[i]), reinterpret_cast<const bf16*>(b->content_target[ct]), c->content_target_b,
+      int rc = content_mse(act, reinterpret_cast<const bf16*>(b->content_target[ct]), c->content_target_b,
                            at(b, L.cgrad[ct]), B, per_image, 0.5 * c->content_w[ct] / denom,
                            static_cast<float>(c->c_weight * c->content_w[ct] / denom), loss_c, s);
       if (rc) return rc;
     }
+    return 0;
+  };
+
+  // ---------------- forward + losses ----------------
+  for (int i = 0; i < c->n_conv; ++i) {
+    const bool want_pool = pool_after(i) && (i + 1 < c->n_conv || pool_tapped(c, pool_index(i)));
+    if (int rc = run_conv_fwd(c, b, L, i, x, want_pool, s)) return rc;
+    if (int rc = tap_losses(i)) return rc;
+    if (want_pool && pool_tapped(c, pool_index(i)))
+      if (int rc = tap_losses(ISX_TAP_POOL0 + pool_index(i))) return rc;
   }
 
   // ---------------- backward ----------------
-  TapSrc src[16];
-  for (int j = 0; j < c->n_conv; ++j) {
-    const int st = style_tap_of(c, j), ct = content_tap_of(c, j);
-    if (ct >= 0) { src[j].add = at(b, L.cgrad[ct]); src[j].add_is_masked = true; }  // content_mse masks its gradient
+  TapSrc src[ISX_VGG19_TAPS];
+  for (int id = 0; id < ISX_VGG19_TAPS; ++id) {
+    if (tap_conv(id) >= c->n_conv) continue;
+    const int st = style_tap_of(c, id), ct = content_tap_of(c, id);
+    if (ct >= 0) { src[id].add = at(b, L.cgrad[ct]); src[id].add_is_masked = true; }  // content_mse masks its gradient
     if (st >= 0 && c->style_mode == 0) {
-      src[j].gram_D = at(b, L.D[st]);
-      src[j].gram_A = c->style_mask_b > 0 ? at(b, L.fm2[st]) : at(b, L.act[j]);
+      src[id].gram_D = at(b, L.D[st]);
+      src[id].gram_A = c->style_mask_b > 0 ? at(b, L.fm2[st]) : at(b, tap_off(L, id));
     } else if (st >= 0) {
-      src[j].aa = atf(b, L.aff_a[st]);
-      src[j].ab = atf(b, L.aff_b[st]);
+      src[id].aa = atf(b, L.aff_a[st]);
+      src[id].ab = atf(b, L.aff_b[st]);
     }
   }
   return run_backward(c, b, L, src, nullptr, grad, s);
@@ -387,8 +442,8 @@ extern "C" int isx_nst_prepare_style_masks(const isx_nst_config* c, const isx_ns
   cudaStream_t s = S(stream);
   for (int t = 0; t < c->n_style; ++t) {
     const int i = c->style_conv[t];
-    const int C = kCout[i];
-    const int HW = L.H[kLevel[i]] * L.W[kLevel[i]];
+    const int C = tap_C(i);
+    const int HW = L.H[tap_level(i)] * L.W[tap_level(i)];
     ISX_REQUIRE(b->style_mask[t], "isx_nst_prepare_style_masks: style mask %d missing", t);
     // F * m^2 is rewritten by every evaluation on the K blocks whose mask is not all zero; everything else stays zero
     ISX_CHECK_CUDA(cudaMemsetAsync(at(b, L.fm2[t]), 0, static_cast<size_t>(c->B) * HW * C * 2, s));
@@ -410,17 +465,17 @@ extern "C" int isx_nst_style_features(const isx_nst_config* c, const isx_nst_buf
   const int B = c->B;
   int64_t need = 0;
   for (int t = 0; t < c->n_style; ++t) {
-    const int64_t C = kCout[c->style_conv[t]];
+    const int64_t C = tap_C(c->style_conv[t]);
     need += (want_stats ? 2 * C : 0) + (want_gram ? C * (C + 1) / 2 : 0);
   }
   ISX_REQUIRE(ld >= need, "isx_nst_style_features: row stride %lld < feature dimension %lld", (long long)ld, (long long)need);
   // column offsets: [per tap: mean | std] then [per tap: Gram upper triangle]
   int64_t stat_off[ISX_MAX_TAPS], gram_off[ISX_MAX_TAPS], off = 0;
-  for (int t = 0; t < c->n_style; ++t) { stat_off[t] = off; if (want_stats) off += 2 * kCout[c->style_conv[t]]; }
-  for (int t = 0; t < c->n_style; ++t) { gram_off[t] = off; if (want_gram) off += static_cast<int64_t>(kCout[c->style_conv[t]]) * (kCout[c->style_conv[t]] + 1) / 2; }
+  for (int t = 0; t < c->n_style; ++t) { stat_off[t] = off; if (want_stats) off += 2 * tap_C(c->style_conv[t]); }
+  for (int t = 0; t < c->n_style; ++t) { gram_off[t] = off; if (want_gram) off += static_cast<int64_t>(tap_C(c->style_conv[t])) * (tap_C(c->style_conv[t]) + 1) / 2; }
   double* sums = reinterpret_cast<double*>(static_cast<char*>(b->workspace) + L.sums);
   for (int t = 0; t < c->n_style; ++t) {
-    const int i = c->style_conv[t], lv = kLevel[i], C = kCout[i];
+    const int i = c->style_conv[t], lv = tap_level(i), C = tap_C(i);
     const int HW = L.H[lv] * L.W[lv];
     ISX_REQUIRE(!want_stats || HW >= 2, "isx_nst_style_features: unbiased std needs >= 2 pixels at conv %d", i);
     const int splits = gram_pick_splits(B, HW, C);
@@ -430,13 +485,13 @@ extern "C" int isx_nst_style_features(const isx_nst_config* c, const isx_nst_buf
     const bool fused = want_stats && want_gram && C <= 128;
     if (want_stats && !fused) {
       ISX_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * B * C * 2, s));
-      if (int rc = chan_sums(at(b, L.act[i]), B, HW, C, sums, s)) return rc;
+      if (int rc = chan_sums(at(b, tap_off(L, i)), B, HW, C, sums, s)) return rc;
       if (int rc = bn_finalize(sums, B, C, HW, out + stat_off[t], out + stat_off[t] + C, nullptr, nullptr, 1, 0.0, 0.0, nullptr,
                                nullptr, nullptr, s, ld)) return rc;
     }
     if (want_gram) {
       float* csum = fused ? atf(b, L.csum) : nullptr;
-      if (int rc = gram_sym_partial(at(b, L.act[i]), B, HW, C, splits, atf(b, L.gram_ws), nullptr, s, csum)) return rc;
+      if (int rc = gram_sym_partial(at(b, tap_off(L, i)), B, HW, C, splits, atf(b, L.gram_ws), nullptr, s, csum)) return rc;
       if (fused)
         if (int rc = stats_from_gram(atf(b, L.gram_ws), csum, B, splits, C, HW, out + stat_off[t], out + stat_off[t] + C, ld, s)) return rc;
       if (int rc = gram_finalize(atf(b, L.gram_ws), B, splits, C, static_cast<float>(1.0 / (static_cast<double>(C) * HW)),
@@ -451,11 +506,12 @@ extern "C" int isx_nst_backward(const isx_nst_config* c, const isx_nst_buffers* 
   ISX_REQUIRE(c && b && feat_grads && grad && b->workspace, "isx_nst_backward: null pointer");
   Layout L;
   if (int rc = make_layout(c, &L)) return rc;
-  TapSrc src[16];
+  TapSrc src[ISX_VGG19_TAPS];
   bool any = last_pool_grad != nullptr;
-  for (int j = 0; j < c->n_conv; ++j) {
-    src[j].add = reinterpret_cast<const bf16*>(feat_grads[j]);
-    any = any || src[j].add != nullptr;
+  for (int id = 0; id < ISX_VGG19_TAPS; ++id) {
+    if (tap_conv(id) >= c->n_conv) continue;
+    src[id].add = reinterpret_cast<const bf16*>(feat_grads[id]);
+    any = any || src[id].add != nullptr;
   }
   ISX_REQUIRE(any, "isx_nst_backward: no gradient given");
   ISX_REQUIRE(!last_pool_grad || pool_after(c->n_conv - 1), "isx_nst_backward: conv %d is not followed by a pool", c->n_conv - 1);

@@ -12,6 +12,9 @@ from . import _lib
 
 MAX_TAPS = 8
 N_CONVS = 16
+TAP_POOL0 = 16          # tap ids: 0..15 = ReLU output of conv i, 16..20 = output of pool 0..4 (include/isx.h ISX_TAP_POOL0)
+N_TAPS = 21
+CONV_BEFORE_POOL = [1, 3, 7, 11, 15]
 
 # models/vgg/vgg.py:6-10 (torchvision vgg19.features indices)
 VGG19_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512, "M"]
@@ -121,7 +124,7 @@ class NstEngine:
         cfg = NstConfig()
         cfg.B, cfg.H, cfg.W, cfg.xc = B, H, W, xc
         taps = list(content_convs) + list(style_convs)
-        cfg.n_conv = n_conv if n_conv is not None else (max(taps) + 1 if taps else N_CONVS)
+        cfg.n_conv = n_conv if n_conv is not None else (max(tap_conv(t) for t in taps) + 1 if taps else N_CONVS)
         cfg.style_mode = style_mode
         if len(style_convs) > MAX_TAPS or len(content_convs) > MAX_TAPS:
             raise ValueError("at most %d style and %d content layers" % (MAX_TAPS, MAX_TAPS))
@@ -227,6 +230,13 @@ class NstEngine:
         _lib.call("isx_nst_style_features", ctypes.byref(self.cfg), ctypes.byref(self.bufs), int(stats), int(gram), out,
                   _lib.i64(out.stride(0)), _lib.stream_ptr())
 
+    def tap_view(self, tap: int) -> torch.Tensor:
+        """bf16 NHWC view of tap id `tap` (conv ReLU output 0..15 or pool output 16..20)."""
+        return self.feature_view(1, tap - TAP_POOL0) if tap >= TAP_POOL0 else self.feature_view(0, tap)
+
+    def tap(self, tap: int) -> torch.Tensor:
+        return self.tap_view(tap).clone()
+
     def feature_view(self, kind: int, idx: int) -> torch.Tensor:
         """bf16 NHWC VIEW into the workspace (valid until the next forward / eval on this engine)."""
         ptr = ctypes.c_void_p()
@@ -238,9 +248,9 @@ class NstEngine:
         return self.workspace[off:off + 2 * n].view(torch.bfloat16).view(self.cfg.B, h.value, w.value, c.value)
 
     def backward(self, feat_grads: Dict[int, torch.Tensor], last_pool_grad: Optional[torch.Tensor], grad: torch.Tensor):
-        """isx_nst_backward: feat_grads {conv index: bf16 NHWC gradient w.r.t. its ReLU output}; uses the activations of
+        """isx_nst_backward: feat_grads {tap id: bf16 NHWC gradient w.r.t. that tap}; uses the activations of
         the forward() that ran last on this engine."""
-        arr = (ctypes.c_void_p * N_CONVS)()
+        arr = (ctypes.c_void_p * N_TAPS)()
         keep = []
         for j, g in feat_grads.items():
             g = g.contiguous()
@@ -299,6 +309,16 @@ def masked_features(feat_nhwc: torch.Tensor, m: torch.Tensor) -> torch.Tensor:
 
 
 CONV_LEVEL = [0, 0, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4]  # number of 2x2 pools before each conv
+CONV_LEVEL += [1, 2, 3, 4, 5]                                   # ... and before the output of pool 0..4 (tap ids 16..20)
+
+
+def tap_conv(tap: int) -> int:
+    """The conv that must have run for tap id `tap` to exist."""
+    return CONV_BEFORE_POOL[tap - TAP_POOL0] if tap >= TAP_POOL0 else tap
+
+
+def tap_channels(tap: int) -> int:
+    return CONV_COUT[tap_conv(tap)]
 
 
 def gram_of(feat_nhwc: torch.Tensor, inv_n: Optional[float] = None) -> torch.Tensor:

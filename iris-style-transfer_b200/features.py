@@ -9,6 +9,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
+from .engine import tap_channels
 from .vgg import VGG19
 
 
@@ -32,7 +33,7 @@ def style_features_batch(vgg: VGG19, x: torch.Tensor, gram: bool = True, stats: 
     if not (gram or stats):
         raise ValueError("nothing to extract")
     eng = vgg.run_forward(x, full=False)
-    chans = [vgg.packed(eng.device).bias[c].numel() for c in vgg.style_convs]
+    chans = [tap_channels(c) for c in vgg.style_convs]
     D = feature_dim(chans, gram, stats)
     if out is None:
         out = torch.empty(eng.cfg.B, D, device=eng.device, dtype=torch.float32)
@@ -61,7 +62,7 @@ def extract_features_sharded(vgg: VGG19, images, batch: int = 32, gram: bool = T
 
     n = len(images)
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-    chans = [vgg.packed(dev).bias[c].numel() for c in vgg.style_convs]
+    chans = [tap_channels(c) for c in vgg.style_convs]
     rows = RowGatherer(n, feature_dim(chans, gram, stats), dev, chunk_rows=gather_chunk)
     lo, hi = rows.lo, rows.hi
     # Host -> device copies run on a side stream, one batch ahead of the kernels, into two device buffers that are
@@ -127,7 +128,7 @@ def cache_classifier_inputs(vgg: VGG19, images, batch: int = 32, device=None):
     Classifier1 input (AdaptiveAvgPool2d(7,7) + Flatten of pool5, bf16 [n, 25088]).  `images`: indexable [n,1|3,H,W]."""
     n = len(images)
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-    chans = [vgg.packed(dev).bias[c].numel() for c in vgg.style_convs]
+    chans = [tap_channels(c) for c in vgg.style_convs]
     D = feature_dim(chans, gram=False, stats=True)
     stats = torch.empty(n, D, device=dev, dtype=torch.float32)
     pool = torch.empty(n, 25088, device=dev, dtype=torch.bfloat16)

@@ -86,17 +86,17 @@ class NstJob:
         if cmask_b:
             eng.set_style_masks(mask_pyramid(c_mask, levels))
         eng.forward(c_img)
-        eng.set_content_targets([eng.feature(0, i) for i in cc])
+        eng.set_content_targets([eng.tap(i) for i in cc])
         Bs, xs, Hs, Ws = s_img.shape
         if (Bs, xs, Hs, Ws) == (B, xc, H, W):
             eng.forward(s_img)
-            s_feats = [eng.feature_view(0, i) for i in sc]   # consumed below, before the engine runs again
+            s_feats = [eng.tap_view(i) for i in sc]   # consumed below, before the engine runs again
         else:
             if Bs not in (1, B):
                 raise ValueError("style batch %d must be 1 or %d" % (Bs, B))
             seng = NstEngine(packed, Bs, Hs, Ws, xs, cc, sc)
             seng.forward(s_img)
-            s_feats = [seng.feature_view(0, i) for i in sc]
+            s_feats = [seng.tap_view(i) for i in sc]
         if BN_loss:
             st = [stats_of(f) for f in s_feats]
             eng.set_bn_targets([m for m, _ in st], [s for _, s in st])

@@ -7,7 +7,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from .engine import (CONV_OF_FEATURE_INDEX, N_CONVS, POOL_OF_FEATURE_INDEX, VGG19_LAYERS, NstEngine, PackedVGG)
+from .engine import (CONV_OF_FEATURE_INDEX, N_CONVS, POOL_OF_FEATURE_INDEX, TAP_POOL0, VGG19_LAYERS, NstEngine, PackedVGG,
+                     tap_conv)
 
 vgg19_layers = dict(VGG19_LAYERS)  # same public name as models/vgg/vgg.py:6
 
@@ -130,7 +131,9 @@ class VGG19(torch.nn.Module):
         self.content_layers = list(content_layers)
         self.style_layers = list(style_layers)
         table = vgg19_bn_layers if bn else VGG19_LAYERS
-        conv_of = _BN_CONV_OF_INDEX if bn else CONV_OF_FEATURE_INDEX
+        conv_of = dict(_BN_CONV_OF_INDEX if bn else CONV_OF_FEATURE_INDEX)
+        for k in range(5):   # pooling layers are taps too (vgg.py:6-17): tap id 16 + k
+            conv_of[table["pool%d" % (k + 1)]] = TAP_POOL0 + k
         self.content_layers_idx = [table[i] for i in self.content_layers]
         self.style_layers_idx = [table[i] for i in self.style_layers]
         for idx in self.content_layers_idx + self.style_layers_idx:
@@ -138,7 +141,7 @@ class VGG19(torch.nn.Module):
                 raise NotImplementedError("conv* taps of vgg19_bn are the pre-BatchNorm tensors; BatchNorm is folded into the "
                                           "convolutions here -- tap bn* / relu* instead")
             if idx not in conv_of:
-                raise NotImplementedError("taps on pooling layers are not supported by the accelerated path")
+                raise ValueError("unknown feature layer index %d" % idx)
         self.content_convs = [conv_of[i] for i in self.content_layers_idx]
         self.style_convs = [conv_of[i] for i in self.style_layers_idx]
         if isinstance(weights, str):
@@ -196,7 +199,7 @@ class VGG19(torch.nn.Module):
         x = x.detach().to(dev, torch.float32).contiguous()
         B, xc, H, W = x.shape
         taps = self.content_convs + self.style_convs
-        n_conv = N_CONVS if full else max(taps) + 1
+        n_conv = N_CONVS if full else max(tap_conv(t) for t in taps) + 1
         eng = self._engine(B, H, W, xc, n_conv, dev)
         eng.set_input_mask(mask)
         self._last_engine = eng
@@ -212,8 +215,8 @@ class VGG19(torch.nn.Module):
         eng = self.run_forward(x, mask, full)
         with torch.cuda.device(eng.device):
             last = eng.feature(1, 4) if full else None
-            c = [eng.feature(0, i) for i in self.content_convs]
-            s = [eng.feature(0, i) for i in self.style_convs]
+            c = [eng.tap(i) for i in self.content_convs]
+            s = [eng.tap(i) for i in self.style_convs]
         return last, c, s, unbatched
 
     def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None):

@@ -98,8 +98,15 @@ def test_vgg19_surface_and_no_cpu_fallback():
     assert nb.style_layers_idx == [2, 8, 16, 29] and nb.style_convs == [0, 2, 4, 8] and nb.content_convs == [9]
     with pytest.raises(NotImplementedError):
         iris_b200.VGG19(bn=True, weights=w, style_layers=["conv1_1"])
-    with pytest.raises(NotImplementedError):
-        iris_b200.VGG19(style_layers=["pool1"], weights=w)
+    # pooling layers are taps too (vgg.py:6-10): tap ids 16 + k
+    netp = iris_b200.VGG19(content_layers=["pool4"], style_layers=["pool1", "relu2_1"], weights=w)
+    assert netp.style_convs == [16, 2] and netp.content_convs == [19] and netp.style_layers_idx == [4, 6]
+    cfgp = engine.NstConfig()
+    cfgp.B, cfgp.H, cfgp.W, cfgp.xc, cfgp.n_conv, cfgp.n_style, cfgp.n_content = 1, 64, 64, 3, 12, 2, 1
+    cfgp.style_conv[0], cfgp.style_conv[1], cfgp.content_conv[0] = 16, 2, 19
+    assert _lib.call_i64("isx_nst_workspace_bytes", ctypes.byref(cfgp)) > 0
+    cfgp.n_conv = 11                      # pool4 follows conv index 11: not computed with n_conv = 11
+    assert _lib.call_i64("isx_nst_workspace_bytes", ctypes.byref(cfgp)) == -1
     g = torch.Generator().manual_seed(1)
     cw, cb = torch.randn(8, 4, 3, 3, generator=g), torch.randn(8, generator=g)
     bn = torch.nn.BatchNorm2d(8).eval()

@@ -148,9 +148,9 @@ def test_eval_matches_golden(mods, ev, name, BN):
     eng = E.NstEngine(net.packed(dev), 2, H, W, 3, net.content_convs, net.style_convs, style_mode=int(BN),
                       c_weight=1.0, s_weight=1e6, coupled=True)
     eng.forward(c)
-    eng.set_content_targets([eng.feature(0, i) for i in net.content_convs])
+    eng.set_content_targets([eng.tap(i) for i in net.content_convs])
     eng.forward(s)
-    feats = [eng.feature(0, i) for i in net.style_convs]
+    feats = [eng.tap(i) for i in net.style_convs]
     if BN:
         st = [E.stats_of(f) for f in feats]
         eng.set_bn_targets([m for m, _ in st], [d for _, d in st])
@@ -386,9 +386,9 @@ def test_masked_gram_eval_matches_oracle(mods):
         if m is not None:
             eng.set_style_masks(E.mask_pyramid(m.to(dev), levels))
         eng.forward(c.to(dev))
-        eng.set_content_targets([eng.feature(0, i) for i in net.content_convs])
+        eng.set_content_targets([eng.tap(i) for i in net.content_convs])
         eng.forward(s.to(dev))
-        eng.set_gram_targets([E.gram_of(eng.feature(0, i)) for i in net.style_convs])
+        eng.set_gram_targets([E.gram_of(eng.tap(i)) for i in net.style_convs])
         g = torch.empty(2, 3, H, W, device=dev)
         eng.eval(xq.to(dev), g)
         torch.cuda.synchronize()
@@ -536,9 +536,9 @@ def test_nst_five_style_layers_eval(mods):
                       s_weight=1e6, coupled=True)
     assert eng.cfg.n_conv == 13
     eng.forward(c.to(dev))
-    eng.set_content_targets([eng.feature(0, i) for i in net5.content_convs])
+    eng.set_content_targets([eng.tap(i) for i in net5.content_convs])
     eng.forward(s.to(dev))
-    eng.set_gram_targets([E.gram_of(eng.feature(0, i)) for i in net5.style_convs])
+    eng.set_gram_targets([E.gram_of(eng.tap(i)) for i in net5.style_convs])
     g = torch.empty(1, 3, H, W, device=dev)
     eng.eval(xq.to(dev), g)
     torch.cuda.synchronize()
@@ -617,6 +617,9 @@ LAYER_CONFIGS = [
     (["relu2_1", "relu4_2"], ["conv3_1"]),                                 # two content taps, conv* alias of a ReLU tap (note N2)
     ([], ["relu1_1", "relu2_1"]),                                          # style only
     (["relu3_2"], []),                                                     # content only
+    (["relu3_1"], ["pool1", "relu2_1", "pool2"]),                          # style taps on POOLING layers (vgg.py:6-10 allows any layer)
+    (["pool3"], ["relu1_1", "pool1"]),                                     # the deepest tap is a pool (content), pool + conv style taps
+    (["pool2"], ["pool2"]),                                                # content and style on the same, deepest pool
 ]
 
 
@@ -641,9 +644,9 @@ def test_eval_layer_configurations(mods, cfg_id, BN):
     eng = E.NstEngine(net.packed(dev), 2, H, W, xc, net.content_convs, net.style_convs, style_mode=int(BN), c_weight=1.0,
                       s_weight=beta, coupled=True)
     eng.forward(c.to(dev))
-    eng.set_content_targets([eng.feature(0, i) for i in net.content_convs])
+    eng.set_content_targets([eng.tap(i) for i in net.content_convs])
     eng.forward(s.to(dev))
-    feats = [eng.feature(0, i) for i in net.style_convs]
+    feats = [eng.tap(i) for i in net.style_convs]
     if BN:
         st = [E.stats_of(f) for f in feats]
         eng.set_bn_targets([m for m, _ in st], [d for _, d in st])
@@ -704,6 +707,30 @@ def test_vgg19_bn_features_match_torchvision(mods):
         err = float((got.cpu() - r).abs().max()) / float(r.abs().max())
         print("vgg19_bn %s: max rel err %.4f" % (name, err))
         assert err < 3e-2
+
+
+def test_vgg_pool_taps_forward_and_autograd(mods):
+    """VGG19 with pooling-layer taps through the module surface: features equal the oracle's, autograd through a pool tap
+    and through the returned pool5 at once."""
+    import iris_b200
+
+    O = mods["O"]
+    net = iris_b200.VGG19(content_layers=["pool2"], style_layers=["pool1", "pool5"], weights=mods["weights"])
+    x = rand_img(7, (2, 3, 64, 96))
+    W_ = mods["weights"]
+    xr = x.clone().requires_grad_(True)
+    pr, cr, sr = O.vgg19_forward(xr, W_, content_layers=["pool2"], style_layers=["pool1", "pool5"], full=True)
+    xg = x.cuda().requires_grad_(True)
+    p5, c_f, s_f = net(xg)
+    for got, ref in zip([p5] + c_f + s_f, [pr] + cr + sr):
+        assert tuple(got.shape) == tuple(ref.shape)
+        assert float((got.detach().cpu() - ref.detach()).abs().max()) <= 3e-2 * float(ref.detach().abs().max())
+    (c_f[0].square().sum() + s_f[0].square().sum() + 0.5 * s_f[1].square().sum() + p5.sum()).backward()
+    (cr[0].square().sum() + sr[0].square().sum() + 0.5 * sr[1].square().sum() + pr.sum()).backward()
+    g, rg = xg.grad.cpu(), xr.grad
+    cos = float((g * rg).sum() / (g.norm() * rg.norm()))
+    print("pool-tap autograd cos %.4f |g| ratio %.3f" % (cos, float(g.norm() / rg.norm())))
+    assert cos > 0.95 and 0.8 < float(g.norm() / rg.norm()) < 1.25
 
 
 def test_cpu_device_is_refused(mods):

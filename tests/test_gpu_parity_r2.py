@@ -225,9 +225,9 @@ def test_eval_gradient_error_is_the_operand_precision(mods, BN):
     eng = E.NstEngine(net.packed(dev), 1, 160, 100, 3, net.content_convs, net.style_convs, style_mode=int(BN),
                       c_weight=1.0, s_weight=beta, coupled=True)
     eng.forward(c.to(dev))
-    eng.set_content_targets([eng.feature(0, i) for i in net.content_convs])
+    eng.set_content_targets([eng.tap(i) for i in net.content_convs])
     eng.forward(s.to(dev))
-    feats = [eng.feature(0, i) for i in net.style_convs]
+    feats = [eng.tap(i) for i in net.style_convs]
     if BN:
         st = [E.stats_of(f) for f in feats]
         eng.set_bn_targets([m for m, _ in st], [d for _, d in st])
