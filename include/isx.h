@@ -141,6 +141,9 @@ int isx_channel_affine(const isx_bf16* feat, const float* a, const float* b, isx
 int isx_bn_stats_fwd(const isx_bf16* feat, int B, int64_t HW, int C, double* sums, float* mean, float* std_,
                      const float* t_mean, const float* t_std, int target_b, double loss_scale, double grad_scale,
                      double* loss, float* aff_a, float* aff_b, isx_stream stream);
+/* mean / unbiased std of the MASK-WEIGHTED features F * m (m fp32 [mask_b,HW]): targets of the mask-weighted BN loss */
+int isx_bn_stats_masked_fwd(const isx_bf16* feat, const float* m, int mask_b, int B, int64_t HW, int C, double* sums, float* mean,
+                            float* std_, isx_stream stream);
 /* ---- G' (extension; hooks models/vgg/vgg.py:84-85, pipelines.py:83): mask-weighted Gram input.  fm = feat * m,
  * fm2 = feat * m^2 (optional) with m fp32 [mask_b,HW] the iris mask at the layer's resolution; the mask pyramid is
  * m_{l+1} = 2x2 average pool of m_l (isx_avgpool2x2_f32).  Gram(fm) == utils.GramMatrix(F * m_l). */
@@ -207,7 +210,7 @@ typedef struct {
   int32_t content_target_b;             /* 1 or B */
   int32_t coupled;                      /* 1: batch is ONE problem -> content loss is a mean over the batch too */
   int32_t mask_b;                       /* 0: no input mask, else 1 or B */
-  int32_t style_mask_b;                 /* 0: plain Gram; 1 or B: mask-weighted Gram (row G'), see style_mask */
+  int32_t style_mask_b;                 /* 0: plain losses; 1 or B: mask-weighted style loss (row G': Gram or BN statistics of F * m_l) */
   int32_t pred_unbatched;               /* 1: the content image was passed UNBATCHED (3,H,W): utils.GramMatrix then divides the
                                            prediction's Gram by H*W instead of C*H*W (utils.py:253-254, n = x[0].numel()) */
   double c_weight, s_weight;            /* alpha, beta */

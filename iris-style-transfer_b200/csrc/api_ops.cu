@@ -214,6 +214,17 @@ extern "C" int isx_bn_stats_fwd(const isx_bf16* feat, int B, int64_t HW, int C, 
                      S(stream));
 }
 
+extern "C" int isx_bn_stats_masked_fwd(const isx_bf16* feat, const float* m, int mask_b, int B, int64_t HW, int C, double* sums,
+                                       float* mean, float* std_, isx_stream stream) {
+  ISX_REQUIRE(feat && m && sums && mean && std_, "isx_bn_stats_masked_fwd: null pointer");
+  ISX_REQUIRE(mask_b == 1 || mask_b == B, "isx_bn_stats_masked_fwd: mask batch %d must be 1 or %d", mask_b, B);
+  ISX_REQUIRE(HW >= 2, "isx_bn_stats_masked_fwd: unbiased std needs at least 2 pixels");
+  ISX_CHECK_CUDA(cudaMemsetAsync(sums, 0, static_cast<size_t>(B) * C * 2 * sizeof(double), S(stream)));
+  int rc = chan_sums(P(feat), B, HW, C, sums, S(stream), m, mask_b);
+  if (rc) return rc;
+  return bn_finalize(sums, B, C, HW, mean, std_, nullptr, nullptr, 1, 0.0, 0.0, nullptr, nullptr, nullptr, S(stream));
+}
+
 extern "C" int isx_mask_features(const isx_bf16* feat, const float* m, int mask_b, isx_bf16* fm, isx_bf16* fm2, int B,
                                  int64_t HW, int C, isx_stream stream) {
   ISX_REQUIRE(feat && m && fm && C % 8 == 0, "isx_mask_features: bad arguments");

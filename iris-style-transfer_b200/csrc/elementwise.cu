@@ -362,6 +362,34 @@ __global__ void tap_add_mask_kernel(const __nv_bfloat16* __restrict__ g, const _
   }
 }
 
+// Tap gradient of the mask-weighted BN-statistics loss: statistics of Fm = F * m have the affine gradient a + b * Fm w.r.t.
+// Fm, hence m * a + m^2 * b * F w.r.t. F (per-pixel weight m, per-(image, channel) a, b)
+__global__ void masked_affine_grad_kernel(const __nv_bfloat16* __restrict__ f, const float* __restrict__ m, int mask_b,
+                                          const float* __restrict__ aff_a, const float* __restrict__ aff_b,
+                                          __nv_bfloat16* __restrict__ out, long HW, int C, long n8) {
+  const int C8 = C / 8;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long pix = i / C8;
+    const long b = pix / HW, pp = pix - b * HW;
+    const int c = static_cast<int>(i % C8) * 8;
+    const float mv = __ldg(m + (mask_b > 1 ? b : 0) * HW + pp);
+    float a[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(f) + i), a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = mv * (aff_a[b * C + c + j] + aff_b[b * C + c + j] * (mv * a[j]));
+    reinterpret_cast<uint4*>(out)[i] = pack8(o);
+  }
+}
+
+int masked_affine_grad(const __nv_bfloat16* f, const float* m, int mask_b, const float* aff_a, const float* aff_b,
+                       __nv_bfloat16* out, int B, long HW, int C, cudaStream_t s) {
+  const long n8 = static_cast<long>(B) * HW * C / 8;
+  const int blocks = static_cast<int>(std::min<long>((n8 + 255) / 256, static_cast<long>(isx_num_sms()) * 16));
+  masked_affine_grad_kernel<<<blocks, 256, 0, s>>>(f, m, mask_b, aff_a, aff_b, out, HW, C, n8);
+  ISX_LAUNCH_CHECK();
+  return 0;
+}
+
 int tap_add_mask(const __nv_bfloat16* g, const __nv_bfloat16* add, const float* aff_a, const float* aff_b,
                  const __nv_bfloat16* act, __nv_bfloat16* out, int B, long HW, int C, cudaStream_t s, int relu_mask) {
   const long n8 = static_cast<long>(B) * HW * C / 8;
@@ -505,7 +533,8 @@ int content_mse(const __nv_bfloat16* pred, const __nv_bfloat16* target, int targ
 // Classifier2 features classifiers.py:71).  sums[b][c][2] (double) must be zeroed by the caller.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-chan_sums_kernel(const __nv_bfloat16* __restrict__ f, long HW, int C, double* __restrict__ sums) {
+chan_sums_kernel(const __nv_bfloat16* __restrict__ f, long HW, int C, double* __restrict__ sums,
+                 const float* __restrict__ mask, int mask_b) {
   extern __shared__ float sred[];  // [256][16]
   const int b = blockIdx.y;
   const int C8 = C / 8;
@@ -520,6 +549,11 @@ chan_sums_kernel(const __nv_bfloat16* __restrict__ f, long HW, int C, double* __
     for (long p = blockIdx.x * static_cast<long>(lanes) + pl; p < HW; p += static_cast<long>(gridDim.x) * lanes) {
       float a[8];
       unpack8(__ldg(base + p * C8), a);
+      if (mask) {   // statistics of F * m (mask-weighted BN loss): per-pixel weight
+        const float mv = __ldg(mask + (mask_b > 1 ? b : 0) * HW + p);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] *= mv;
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s1[j] += a[j]; s2[j] = fmaf(a[j], a[j], s2[j]); }
     }
@@ -537,7 +571,7 @@ chan_sums_kernel(const __nv_bfloat16* __restrict__ f, long HW, int C, double* __
   }
 }
 
-int chan_sums(const __nv_bfloat16* f, int B, long HW, int C, double* sums, cudaStream_t s) {
+int chan_sums(const __nv_bfloat16* f, int B, long HW, int C, double* sums, cudaStream_t s, const float* mask, int mask_b) {
   ISX_REQUIRE(C % 8 == 0 && C / 8 <= 64 && 256 % (C / 8) == 0, "chan_sums: C=%d unsupported", C);
   const int lanes = 256 / (C / 8);
   long bx = (HW + lanes * 8 - 1) / (lanes * 8);  // >= 8 pixels per lane
@@ -545,7 +579,7 @@ int chan_sums(const __nv_bfloat16* f, int B, long HW, int C, double* sums, cudaS
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   dim3 grid(static_cast<unsigned>(bx), B);
-  chan_sums_kernel<<<grid, 256, 256 * 16 * sizeof(float), s>>>(f, HW, C, sums);
+  chan_sums_kernel<<<grid, 256, 256 * 16 * sizeof(float), s>>>(f, HW, C, sums, mask, mask_b);
   ISX_LAUNCH_CHECK();
   return 0;
 }

@@ -28,7 +28,10 @@ int gram_finalize(const float* partial, int B, int splits, int C, float inv_n, f
                   cudaStream_t s, float* triu = nullptr, long triu_ld = 0);
 int content_mse(const __nv_bfloat16* pred, const __nv_bfloat16* target, int target_b, __nv_bfloat16* grad, int B,
                 long per_image, double loss_scale, float grad_scale, double* loss, cudaStream_t s, int relu_mask = 1);
-int chan_sums(const __nv_bfloat16* f, int B, long HW, int C, double* sums, cudaStream_t s);
+int chan_sums(const __nv_bfloat16* f, int B, long HW, int C, double* sums, cudaStream_t s, const float* mask = nullptr,
+              int mask_b = 0);
+int masked_affine_grad(const __nv_bfloat16* f, const float* m, int mask_b, const float* aff_a, const float* aff_b,
+                       __nv_bfloat16* out, int B, long HW, int C, cudaStream_t s);
 int stats_from_gram(const float* partial, const float* csum, int B, int splits, int C, long HW, float* mean, float* stdv,
                     long out_ld, cudaStream_t s);
 int bn_finalize(const double* sums, int B, int C, long HW, float* mean, float* stdv, const float* t_mean,

@@ -345,7 +345,6 @@ extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, c
                             double* loss_s, float* grad, isx_stream stream) {
   ISX_REQUIRE(c && b && x && loss_c && loss_s && grad && b->workspace, "isx_nst_eval: null pointer");
   ISX_REQUIRE(c->n_style + c->n_content > 0, "isx_nst_eval: no loss taps");
-  ISX_REQUIRE(c->style_mask_b == 0 || c->style_mode == 0, "isx_nst_eval: the mask-weighted variant exists for the Gram loss only");
   ISX_REQUIRE(c->style_mask_b == 0 || c->style_mask_b == 1 || c->style_mask_b == c->B, "isx_nst_eval: style mask batch %d", c->style_mask_b);
   Layout L;
   if (int rc = make_layout(c, &L)) return rc;
@@ -388,11 +387,18 @@ extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, c
         ISX_REQUIRE(HW >= 2, "nst: unbiased std needs >= 2 pixels at tap %d", id);
         double* sums = reinterpret_cast<double*>(static_cast<char*>(b->workspace) + L.sums);
         ISX_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * B * C * 2, s));
-        int rc = chan_sums(act, B, HW, C, sums, s);
+        const float* m = nullptr;
+        if (c->style_mask_b > 0) {  // mask-weighted variant: StyleLoss_BN(F * m_l), statistics of the weighted features
+          ISX_REQUIRE(b->style_mask[st], "nst: style mask %d missing", st);
+          m = b->style_mask[st];
+        }
+        int rc = chan_sums(act, B, HW, C, sums, s, m, c->style_mask_b);
         if (rc) return rc;
         rc = bn_finalize(sums, B, C, HW, nullptr, nullptr, b->bn_target_mean[st], b->bn_target_std[st],
                          c->style_target_b, w / C, c->s_weight * w / C, loss_s, atf(b, L.aff_a[st]), atf(b, L.aff_b[st]), s);
         if (rc) return rc;
+        if (m)  // the gradient is no longer affine in F alone: m a + m^2 b F, materialised as a gradient map (buffer fm2)
+          if (int rc2 = masked_affine_grad(act, m, c->style_mask_b, atf(b, L.aff_a[st]), atf(b, L.aff_b[st]), at(b, L.fm2[st]), B, HW, C, s)) return rc2;
       }
     }
     const int ct = content_tap_of(c, id);
@@ -426,6 +432,14 @@ extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, c
     if (st >= 0 && c->style_mode == 0) {
       src[id].gram_D = at(b, L.D[st]);
       src[id].gram_A = c->style_mask_b > 0 ? at(b, L.fm2[st]) : at(b, tap_off(L, id));
+    } else if (st >= 0 && c->style_mask_b > 0) {   // masked BN loss: a ready gradient map
+      if (src[id].add) {  // a content tap on the same layer already supplies a map: sum them
+        const long HWt = static_cast<long>(L.H[tap_level(id)]) * L.W[tap_level(id)];
+        if (int rc = tap_add_mask(src[id].add, at(b, L.fm2[st]), nullptr, nullptr, at(b, tap_off(L, id)), at(b, L.fm2[st]), B, HWt,
+                                  tap_C(id), s, 0)) return rc;
+      }
+      src[id].add = at(b, L.fm2[st]);
+      src[id].add_is_masked = false;
     } else if (st >= 0) {
       src[id].aa = atf(b, L.aff_a[st]);
       src[id].ab = atf(b, L.aff_b[st]);
@@ -440,6 +454,7 @@ extern "C" int isx_nst_prepare_style_masks(const isx_nst_config* c, const isx_ns
   Layout L;
   if (int rc = make_layout(c, &L)) return rc;
   cudaStream_t s = S(stream);
+  if (c->style_mode != 0) return 0;  // mask-weighted BN loss: the mask is read directly by the statistics / gradient kernels
   for (int t = 0; t < c->n_style; ++t) {
     const int i = c->style_conv[t];
     const int C = tap_C(i);

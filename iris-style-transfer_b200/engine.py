@@ -335,6 +335,18 @@ def gram_of(feat_nhwc: torch.Tensor, inv_n: Optional[float] = None) -> torch.Ten
     return G
 
 
+def masked_stats_of(feat_nhwc: torch.Tensor, m: torch.Tensor):
+    """mean / unbiased std over (H,W) of F * m (m fp32 [Bm,h,w], Bm in {1,B}) via isx_bn_stats_masked_fwd."""
+    B, H, W, C = feat_nhwc.shape
+    dev = feat_nhwc.device
+    m = m.to(dev, torch.float32).contiguous()
+    sums = torch.empty(B, C, 2, device=dev, dtype=torch.float64)
+    mean = torch.empty(B, C, device=dev, dtype=torch.float32)
+    std = torch.empty(B, C, device=dev, dtype=torch.float32)
+    _lib.call("isx_bn_stats_masked_fwd", feat_nhwc, m, m.shape[0], B, _lib.i64(H * W), C, sums, mean, std, _lib.stream_ptr())
+    return mean, std
+
+
 def stats_of(feat_nhwc: torch.Tensor):
     """Per-(image, channel) mean and unbiased std over (H,W) via isx_bn_stats_fwd -> fp32 [B,C] each."""
     B, H, W, C = feat_nhwc.shape

@@ -12,7 +12,8 @@ from typing import List, Optional, Tuple
 import torch
 
 from . import _lib
-from .engine import CONV_LEVEL, LbfgsConfig, NstEngine, gram_of, mask_pyramid, masked_gram_of, stats_of
+from .engine import (CONV_LEVEL, LbfgsConfig, NstEngine, gram_of, mask_pyramid, masked_gram_of, masked_stats_of,
+                     stats_of)
 from .vgg import VGG19
 
 last_info: dict = {}
@@ -71,8 +72,6 @@ class NstJob:
         self.epochs = int(epochs)
 
         # ---- targets (pipelines.py:62-68) ----
-        if (c_mask is not None or s_mask is not None) and BN_loss:
-            raise ValueError("mask-weighted style loss (c_mask / s_mask) exists for the Gram loss only (BN_loss=False)")
         levels = [CONV_LEVEL[i] for i in sc]
         cmask_b = 0
         if c_mask is not None:
@@ -98,7 +97,11 @@ class NstJob:
             seng.forward(s_img)
             s_feats = [seng.tap_view(i) for i in sc]
         if BN_loss:
-            st = [stats_of(f) for f in s_feats]
+            if s_mask is not None:  # mask-weighted BN loss: targets are the statistics of the style features times the style's mask
+                s_mask = _norm_mask(s_mask, Bs, Hs, Ws, "s_mask", dev)
+                st = [masked_stats_of(f, m) for f, m in zip(s_feats, mask_pyramid(s_mask, levels))]
+            else:
+                st = [stats_of(f) for f in s_feats]
             eng.set_bn_targets([m for m, _ in st], [s for _, s in st])
         else:
             # unbatched style image (…2020.py:103-104): GramMatrix divides by H*W only (SURVEY note N3)
@@ -434,9 +437,10 @@ def nst(c_img: torch.Tensor,
       overlap       (with streams > 1) run each sub-batch's L-BFGS passes on a low-priority stream of its own so that they are
                     resident beside the persistent conv CTAs of the other sub-batches (needs the conv kernels to leave some
                     shared memory free: _lib.call("isx_set_option", b"smem_reserve_kb", 16)).
-      c_mask/s_mask iris masks [B|1,1,H,W] of the content / style frames: the style loss then compares MASK-WEIGHTED Gram
-                    matrices GramMatrix(F * m_l), m_l = the mask average-pooled to layer l (row G' of SURVEY.md §8a; the
-                    reference only has the dormant hooks vgg.py:84-85 / pipelines.py:83).  All-ones masks == plain Gram.
+      c_mask/s_mask iris masks [B|1,1,H,W] of the content / style frames: the style loss then compares the statistics of the
+                    MASK-WEIGHTED features F * m_l -- GramMatrix(F * m_l) or, with BN_loss, mean / std of F * m_l --, m_l = the
+                    mask average-pooled to layer l (row G' of SURVEY.md §8a; the reference only has the dormant hooks
+                    vgg.py:84-85 / pipelines.py:83).  All-ones masks == the plain losses.
       cuda_graph    replay each tick from a captured CUDA graph.  Off by default: a tick has no host synchronisation,
                     so eager launches already queue ahead of the GPU; capture + instantiation (~0.25 s) only pays off
                     for very long single-image jobs (measured, profiles/r01_README.md).

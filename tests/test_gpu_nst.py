@@ -418,6 +418,59 @@ def test_masked_gram_eval_matches_oracle(mods):
     assert 20 <= len(sh) < 40 and np.isfinite(sh).all()
 
 
+def test_masked_bn_eval_matches_oracle(mods):
+    """Mask-weighted variant of the reference's DEFAULT style loss: StyleLoss_BN(F * m_l); an all-ones mask == plain BN loss;
+    also with a content tap on a style layer (two gradient maps on one layer)."""
+    from iris_b200 import synthetic
+    import iris_b200
+
+    E, O = mods["engine"], mods["O"]
+    dev = torch.device("cuda:0")
+    H, W = 64, 48
+    fr, seg = synthetic.synthetic_batch([7, 8], H, W)
+    c = torch.from_numpy(fr).repeat(1, 3, 1, 1)
+    s = rand_img(61, (2, 3, H, W))
+    xq = (0.6 * c + 0.4 * rand_img(62, (2, 3, H, W))).clamp(0, 1)
+    mask = torch.from_numpy((seg == 2) | (seg == 3)).float()          # [2,1,H,W]
+    W_ = mods["weights"]
+    for content, style in ((["relu4_2"], ["relu1_1", "relu2_1", "relu3_1", "relu4_1"]), (["relu2_1"], ["relu1_1", "relu2_1"])):
+        net = iris_b200.VGG19(content_layers=content, style_layers=style, weights=W_)
+        levels = [E.CONV_LEVEL[i] for i in net.style_convs]
+
+        def run(m):
+            eng = E.NstEngine(net.packed(dev), 2, H, W, 3, net.content_convs, net.style_convs, style_mode=1, c_weight=1.0,
+                              s_weight=1e4, coupled=True, style_mask_b=0 if m is None else 2)
+            if m is not None:
+                eng.set_style_masks(E.mask_pyramid(m.to(dev), levels))
+            eng.forward(c.to(dev))
+            eng.set_content_targets([eng.tap(i) for i in net.content_convs])
+            eng.forward(s.to(dev))
+            st = [E.stats_of(eng.tap(i)) for i in net.style_convs]
+            eng.set_bn_targets([a for a, _ in st], [d for _, d in st])
+            g = torch.empty(2, 3, H, W, device=dev)
+            eng.eval(xq.to(dev), g)
+            torch.cuda.synchronize()
+            return float(eng.loss_c.sum()), float(eng.loss_s.sum()), g.cpu()
+
+        with torch.no_grad():
+            _, cf, _ = O.vgg19_forward(c, W_, content_layers=content, style_layers=style, full=False)
+            _, _, sf = O.vgg19_forward(s, W_, content_layers=content, style_layers=style, full=False)
+        tg = ([t.mean(dim=(-2, -1)) for t in sf], [t.std(dim=(-2, -1)) for t in sf])
+        cl, sl, g = run(mask)
+        rcl, rsl, rg = O.nst_eval(xq, cf, tg, W_, True, 1.0, 1e4, content_layers=content, style_layers=style, layer_mask=mask)
+        cos = float((g * rg).sum() / (g.norm() * rg.norm()))
+        print("masked BN %s: c %.5g/%.5g s %.5g/%.5g grad cos %.4f |g| ratio %.3f" % (style, cl, rcl, sl, rsl, cos, float(g.norm() / rg.norm())))
+        assert sl == pytest.approx(rsl, rel=1e-2) and cl == pytest.approx(rcl, rel=1e-2)
+        assert cos > 0.97 and 0.8 < float(g.norm() / rg.norm()) < 1.25
+        _, sl1, g1 = run(torch.ones(2, 1, H, W))
+        _, sl0, g0 = run(None)
+        assert sl1 == pytest.approx(sl0, rel=1e-6) and float((g1 - g0).norm() / g0.norm()) < 2e-2
+    # through the public API: default BN loss with masks
+    x, _, ch, sh = _run(mods, c, s, BN_loss=True, s_loss_weight=1e4, epochs=20, c_mask=mask, s_mask=torch.ones(2, 1, H, W),
+                        x_hist_stride=0)
+    assert 20 <= len(sh) < 40 and np.isfinite(sh).all() and sh[-1] < sh[0]
+
+
 def test_feature_extraction_overlapped_copies(mods):
     """extract_features_sharded copies batch i+1 host->device on a side stream while batch i runs: pageable and pinned
     sources, a ragged last batch, and a device-resident source must all give the rows of a plain per-batch call."""
