@@ -121,7 +121,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int i = 0; i < 8; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr_smem);
+  // The persistent CTA owns its SM: it allocates ALL 512 TMEM columns, whatever it uses.  The allocation can then only succeed
+  // once nobody else holds tensor memory on this SM, so the base is column 0 by construction (the MMA loop relies on
+  // compile-time accumulator addresses) and a foreign tcgen05 kernel on another stream makes this CTA wait, not fault.
+  if (warp == 1) tmem_alloc<512>(tmem_ptr_smem);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -403,7 +406,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
