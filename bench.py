@@ -434,6 +434,7 @@ def main():
     ap.add_argument("--history-bf16", action="store_true", help="opt-in: store the L-BFGS (s, y) history in bf16")
     ap.add_argument("--feature-images", type=int, default=512, help="images per GPU of the feature-extraction leg")
     ap.add_argument("--feature-batch", type=int, default=32, help="images per forward pass of the feature-extraction leg")
+    ap.add_argument("--opt", action="append", default=[], help="name=value: libisx kernel-selection option (isx_set_option), repeatable")
     ap.add_argument("--e2e-evals", type=int, default=300, help="evaluations of the end-to-end job (BASELINE config[1]: 300)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -466,6 +467,10 @@ def main():
     _lib.call("isx_device_check", local)
     if args.smem_reserve_kb:
         lib.isx_set_option(b"smem_reserve_kb", int(args.smem_reserve_kb))
+    for kv in args.opt:
+        name, val = kv.split("=")
+        if lib.isx_set_option(name.encode(), int(val)) != 0:
+            raise SystemExit("unknown libisx option %r" % name)
 
     def finish():
         if world > 1:

@@ -81,6 +81,14 @@ int isx_conv3x3_bias_relu_fwd(const isx_bf16* in, const isx_bf16* w_fwd, const f
 int isx_conv3x3_bias_relu_pool_fwd(const isx_bf16* in, const isx_bf16* w_fwd, const float* bias, isx_bf16* out,
                                    isx_bf16* pool_out, int B, int H, int W, int Cin, int Cout, int tile_cfg,
                                    isx_stream stream);
+/* The same, and the ROUTING BYTES of the pool's backward: pool_idx uint8 [B,H/2,W/2,Cout], one byte per pooled element --
+ * 0..3 = window position (0,0),(0,1),(1,0),(1,1) of the FIRST maximum (ATen's rule), 4 = the maximum is <= 0, i.e. the ReLU
+ * passes nothing.  isx_maxpool2x2_bwd_idx then needs the pooled gradient and these bytes only, not the pre-pool activation
+ * (autograd of MaxPool2d + ReLU, pipelines.py:90).  skip_out != 0: the full-resolution output is not stored at all when the
+ * pool is fused into the epilogue (`out` must still point to a [B,H,W,Cout] buffer: the unfused fallback writes it). */
+int isx_conv3x3_bias_relu_pool_idx_fwd(const isx_bf16* in, const isx_bf16* w_fwd, const float* bias, isx_bf16* out,
+                                       isx_bf16* pool_out, uint8_t* pool_idx, int skip_out, int B, int H, int W, int Cin,
+                                       int Cout, int tile_cfg, isx_stream stream);
 
 /* ---- K3: conv dgrad (+ tap gradient, x ReLU mask) on tcgen05 (loss.backward(), pipelines.py:90)
  * dy bf16 [B,H,W,Cout] -> dx bf16 [B,H,W,Cin] for the forward conv Cin->Cout; weights frozen so
@@ -101,6 +109,11 @@ int isx_conv3x3_dgrad_gram(const isx_bf16* dy, const isx_bf16* w_dgrad, isx_bf16
 int isx_maxpool2x2_fwd(const isx_bf16* in, isx_bf16* out, int B, int H, int W, int C, isx_stream stream);
 int isx_maxpool2x2_bwd(const isx_bf16* dy_pooled, const isx_bf16* act_prepool, isx_bf16* dx, int B, int H, int W,
                        int C, isx_stream stream);
+/* the same pair through routing bytes (see isx_conv3x3_bias_relu_pool_idx_fwd): fwd writes out (may be NULL) and idx uint8
+ * [B,H/2,W/2,C]; bwd reads 3 bytes per pooled element instead of the four pre-pool activations */
+int isx_maxpool2x2_fwd_idx(const isx_bf16* in, isx_bf16* out, uint8_t* idx, int B, int H, int W, int C, isx_stream stream);
+int isx_maxpool2x2_bwd_idx(const isx_bf16* dy_pooled, const uint8_t* idx, isx_bf16* dx, int B, int H, int W, int C,
+                           isx_stream stream);
 
 /* ---- K4: Gram matrix (utils.py:242-257 GramMatrix) ---------------------------------------------
  * feat bf16 [B,HW,C] (NHWC flattened), C in {64,128,256,512}.  G = F^T F * inv_n (fp32 [B,C,C]).
@@ -239,9 +252,13 @@ int64_t isx_nst_workspace_bytes(const isx_nst_config* cfg);
  * (or NULL); uses the activations the preceding isx_nst_forward left in the workspace; grad fp32 [B,xc,H,W]. */
 int isx_nst_backward(const isx_nst_config* cfg, const isx_nst_buffers* bufs, const isx_bf16* const* feat_grads,
                      const isx_bf16* last_pool_grad, float* grad, isx_stream stream);
-/* forward only (VGG19.forward, models/vgg/vgg.py:69-92) up to conv index n_conv-1 (+ trailing pool when
- * with_last_pool); activations stay in the workspace, see isx_nst_feature. */
-int isx_nst_forward(const isx_nst_config* cfg, const isx_nst_buffers* bufs, const float* x, int with_last_pool,
+/* forward only (VGG19.forward, models/vgg/vgg.py:69-92) up to conv index n_conv-1; activations stay in the workspace, see
+ * isx_nst_feature.  flags: ISX_FWD_LAST_POOL = also the pool after the deepest conv; ISX_FWD_LEAN = a pre-pool ReLU output
+ * that is not a tap is NOT materialised (only its pooled map and the routing bytes of the pool's backward are written:
+ * isx_nst_backward and isx_nst_style_features never read it; isx_nst_feature(kind 0) of such a conv is then undefined). */
+#define ISX_FWD_LAST_POOL 1
+#define ISX_FWD_LEAN 2
+int isx_nst_forward(const isx_nst_config* cfg, const isx_nst_buffers* bufs, const float* x, int flags,
                     isx_stream stream);
 /* device pointer / shape of a stored activation: kind 0 = ReLU output of conv `idx`, 1 = output of pool `idx` (0..4) */
 int isx_nst_feature(const isx_nst_config* cfg, const isx_nst_buffers* bufs, int kind, int idx, isx_bf16** ptr,
@@ -327,7 +344,9 @@ unsigned long long isx_launch_count(void);
  * the call to the generic kernel, 2 ("c64", "halo2") forces the kernel on every applicable call; "c64_slots",
  * "halo2_stages": ring depths (0 = as many as fit); "smem_reserve_kb" (0): shared memory per SM the persistent conv CTAs leave
  * free (<= 22) so that one TMEM-free streaming CTA of another stream -- the L-BFGS history passes -- can be resident beside
- * them.  Unknown names return non-zero. */
+ * them; "pool_idx" (1): the NST driver routes the max-pool + ReLU backward through the index bytes the fused conv epilogues
+ * emit and does not store untapped pre-pool activations (0: stores them and re-reads them in the backward); "head_ctas" (5):
+ * resident CTAs per SM the conv1_1 head is compiled for (5 or 8).  Unknown names return non-zero. */
 int isx_set_option(const char* name, int value);   /* on the calling thread's current context */
 int isx_get_option(const char* name, int* value);
 int isx_prof_enable(int on);

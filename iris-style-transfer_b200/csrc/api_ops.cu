@@ -93,6 +93,18 @@ extern "C" int isx_conv3x3_bias_relu_pool_fwd(const isx_bf16* in, const isx_bf16
   return conv_tc(a, S(stream));
 }
 
+extern "C" int isx_conv3x3_bias_relu_pool_idx_fwd(const isx_bf16* in, const isx_bf16* w_fwd, const float* bias, isx_bf16* out,
+                                                  isx_bf16* pool_out, uint8_t* pool_idx, int skip_out, int B, int H, int W,
+                                                  int Cin, int Cout, int tile_cfg, isx_stream stream) {
+  ISX_REQUIRE(in && w_fwd && out && pool_out && pool_idx && H >= 2 && W >= 2, "isx_conv3x3_bias_relu_pool_idx_fwd: bad arguments");
+  ConvArgs a;
+  a.in = P(in); a.weight = P(w_fwd); a.out = P(out); a.pool_out = P(pool_out); a.pool_idx = pool_idx; a.skip_out = skip_out != 0;
+  a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ntaps = 9;
+  a.bias = bias; a.relu = 1;
+  decode_tile_cfg(tile_cfg, &a);
+  return conv_tc(a, S(stream));
+}
+
 extern "C" int isx_conv3x3_dgrad(const isx_bf16* dy, const isx_bf16* w_dgrad, isx_bf16* dx, int B, int H, int W,
                                  int Cin, int Cout, const isx_bf16* relu_act, const isx_bf16* add_grad,
                                  const float* aff_a, const float* aff_b, int tile_cfg, isx_stream stream) {
@@ -125,6 +137,18 @@ extern "C" int isx_maxpool2x2_bwd(const isx_bf16* dy, const isx_bf16* act, isx_b
                                   isx_stream stream) {
   ISX_REQUIRE(dy && act && dx, "isx_maxpool2x2_bwd: null pointer");
   return maxpool_bwd(P(dy), P(act), P(dx), B, H, W, C, S(stream));
+}
+
+extern "C" int isx_maxpool2x2_fwd_idx(const isx_bf16* in, isx_bf16* out, uint8_t* idx, int B, int H, int W, int C,
+                                      isx_stream stream) {
+  ISX_REQUIRE(in && idx, "isx_maxpool2x2_fwd_idx: null pointer");
+  return maxpool_fwd_idx(P(in), P(out), idx, B, H, W, C, S(stream));
+}
+
+extern "C" int isx_maxpool2x2_bwd_idx(const isx_bf16* dy, const uint8_t* idx, isx_bf16* dx, int B, int H, int W, int C,
+                                      isx_stream stream) {
+  ISX_REQUIRE(dy && idx && dx, "isx_maxpool2x2_bwd_idx: null pointer");
+  return maxpool_bwd_idx(P(dy), idx, P(dx), B, H, W, C, S(stream));
 }
 
 extern "C" int64_t isx_gram_workspace_bytes(int B, int HW, int C) {
@@ -251,6 +275,8 @@ extern "C" int isx_set_option(const char* name, int value) {
   if (strcmp(name, "halo2_stages") == 0) { isx_ctx()->opt_halo2_stages = value; return 0; }
   if (strcmp(name, "c64_slots") == 0) { isx_ctx()->opt_c64_slots = value; return 0; }
   if (strcmp(name, "smem_reserve_kb") == 0) { isx_ctx()->opt_smem_reserve_kb = value; return 0; }
+  if (strcmp(name, "head_ctas") == 0) { isx_ctx()->opt_head_ctas = value; return 0; }
+  if (strcmp(name, "pool_idx") == 0) { isx_ctx()->opt_pool_idx = value; return 0; }
   ISX_REQUIRE(false, "isx_set_option: unknown option '%s'", name);
 }
 
@@ -263,5 +289,7 @@ extern "C" int isx_get_option(const char* name, int* value) {
   if (strcmp(name, "halo2_stages") == 0) { *value = c->opt_halo2_stages; return 0; }
   if (strcmp(name, "c64_slots") == 0) { *value = c->opt_c64_slots; return 0; }
   if (strcmp(name, "smem_reserve_kb") == 0) { *value = c->opt_smem_reserve_kb; return 0; }
+  if (strcmp(name, "head_ctas") == 0) { *value = c->opt_head_ctas; return 0; }
+  if (strcmp(name, "pool_idx") == 0) { *value = c->opt_pool_idx; return 0; }
   ISX_REQUIRE(false, "isx_get_option: unknown option '%s'", name);
 }

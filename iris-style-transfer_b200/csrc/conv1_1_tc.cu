@@ -26,6 +26,9 @@ int pack_w0_fwd(const float* w, __nv_bfloat16* wp, cudaStream_t s) {
   return 0;
 }
 
+static constexpr int kC11Bias = 16384 + 8192 + 64;   // shared-memory offsets behind the two operand tiles and the barriers
+static constexpr int kC11Patch = kC11Bias + 256;
+
 struct C11Params {
   const float* x;
   const float* mask;
@@ -38,25 +41,30 @@ struct C11Params {
 
 // TW (power of two, TH = 128 / TW) is a template parameter: the patch index arithmetic (i % PW, i / (PW*PH), tid % TW)
 // then compiles to multiply-shift instead of ~15 integer divisions per thread and tile.
-template <int TW>
-__global__ void __launch_bounds__(128)
+template <int TW, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 conv1_1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO, const C11Params p) {
   constexpr int TH = 128 / TW;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // Everything lives in DYNAMIC shared memory declared 1024-byte aligned (no static arrays in front of it, no alignment
+  // slack): 27 KB + the 1 KB the system reserves per CTA lets eight CTAs share an SM's 227 KB.
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;                 // 128 rows x 128 B
   uint8_t* sB = smem + 16384;         // 64 rows x 128 B
   uint8_t* sO = sA;                   // output staging aliases the A tile (free once the MMA has completed)
   uint64_t* w_bar = reinterpret_cast<uint64_t*>(smem + 16384 + 8192);
   uint64_t* mma_bar = w_bar + 1;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mma_bar + 1);
-  __shared__ float s_bias[64];
-  __shared__ uint32_t s_patch[3 * (TW + 2) * (TH + 2)];
+  float* s_bias = reinterpret_cast<float*>(smem + kC11Bias);
+  uint32_t* s_patch = reinterpret_cast<uint32_t*>(smem + kC11Patch);   // 3 * (TW + 2) * (TH + 2) words
   const int tid = threadIdx.x, warp = tid >> 5;
   const float mean[3] = {0.485f, 0.456f, 0.406f};
   const float stdv[3] = {0.229f, 0.224f, 0.225f};
 
   if (tid == 0) {
+    if (smem_u32(smem) & 1023u) {
+      printf("isx: conv1_1 head: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmO);
     mbar_init(w_bar, 1);
@@ -229,16 +237,23 @@ int conv1_1_fwd_tc(const float* x, int xc, const float* mask, int mask_b, const 
     uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
     if (isx_make_tmap_bf16(&tmO, out, 4, dims, str, box, true)) return 3;
   }
-  const size_t smem_bytes = 1024 + 16384 + 8192 + 64;
-  // Latency-bound kernel (per tile: patch -> smem, row build, MMA round trip, TMEM read, TMA store): ~5 CTAs are resident
-  // per SM (90 registers x 128 threads, 64 TMEM columns each).  Measured grid sweep at 640x400 (us/image): 148 x 5 12.0,
-  // x 6 15.4 (partial second wave), x 10 11.9, x 32 11.8 -> many short CTAs make the static tile split insensitive to
-  // wave quantisation.
+  const size_t smem_bytes = kC11Patch + 4 * 3 * (p.TW + 2) * (p.TH + 2);
+  // Latency-bound kernel (per tile: patch -> smem, row build, MMA round trip, TMEM read, TMA store): what hides the chain
+  // is the number of resident CTAs.  Compiled for 8 per SM (64 registers, 28 KB of shared memory and 64 TMEM columns each;
+  // "head_ctas" = 5 selects the 93-register build that fits five).  Measured grid sweep at 640x400 (us/image, five resident):
+  // 148 x 5 12.0, x 6 15.4 (partial second wave), x 10 11.9, x 32 11.8 -> many short CTAs make the static tile split
+  // insensitive to wave quantisation.
   const int grid = std::min(p.n_tiles, kNumSMs * 32);
+  const bool dense = isx_ctx()->opt_head_ctas >= 8;
 #define ISX_C11_CASE(TW_)                                                                                                   \
   case TW_:                                                                                                                 \
-    ISX_CHECK_CUDA(cudaFuncSetAttribute(conv1_1_tc_kernel<TW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); \
-    conv1_1_tc_kernel<TW_><<<grid, 128, smem_bytes, s>>>(tmW, tmO, p);                                                      \
+    if (dense) {                                                                                                            \
+      ISX_CHECK_CUDA(cudaFuncSetAttribute(conv1_1_tc_kernel<TW_, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); \
+      conv1_1_tc_kernel<TW_, 8><<<grid, 128, smem_bytes, s>>>(tmW, tmO, p);                                                 \
+    } else {                                                                                                                \
+      ISX_CHECK_CUDA(cudaFuncSetAttribute(conv1_1_tc_kernel<TW_, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); \
+      conv1_1_tc_kernel<TW_, 5><<<grid, 128, smem_bytes, s>>>(tmW, tmO, p);                                                 \
+    }                                                                                                                       \
     break;
   switch (p.TW) {
     ISX_C11_CASE(128) ISX_C11_CASE(64) ISX_C11_CASE(32) ISX_C11_CASE(16) ISX_C11_CASE(8) ISX_C11_CASE(4) ISX_C11_CASE(2)

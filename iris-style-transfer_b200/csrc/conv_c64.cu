@@ -41,6 +41,8 @@ struct C64Params {
   int xc;
   const float* in_mask;
   int mask_b;
+  uint8_t* pool_idx;
+  int skip_out;
 };
 
 // smem carve-up (all offsets multiples of 1024)
@@ -342,7 +344,7 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // staging slot (gc+1)&1 is written by the next tile: its TMA stores must have finished reading shared memory
         if (threadIdx.x == 64) tma_store_wait_read<0>();
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (threadIdx.x == 64) {
+        if (threadIdx.x == 64 && !p.skip_out) {
           tma_store_4d(&tmO, stg, 0, x0, y0, b);
           tma_store_commit();
         }
@@ -353,14 +355,17 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int px = pr & 3, py = pr >> 2;  // pooled tile is 4 x 8
           const int r00 = (2 * py) * 8 + 2 * px;
           const int rr[4] = {r00, r00 + 1, r00 + 8, r00 + 9};
-          uint4 m4 = *reinterpret_cast<const uint4*>(stg + rr[0] * 128 + ((chunk ^ (rr[0] & 7)) * 16));
+          uint4 u4[4];
 #pragma unroll
-          for (int k = 1; k < 4; ++k) {
-            const uint4 u = *reinterpret_cast<const uint4*>(stg + rr[k] * 128 + ((chunk ^ (rr[k] & 7)) * 16));
-            __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&m4);
-            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) a2[e] = __hmax2(a2[e], b2[e]);
+          for (int k = 0; k < 4; ++k) u4[k] = *reinterpret_cast<const uint4*>(stg + rr[k] * 128 + ((chunk ^ (rr[k] & 7)) * 16));
+          uint4 m4;
+          uint2 codes;
+          pool4_codes(u4, m4, codes);
+          if (p.pool_idx != nullptr) {  // routing bytes of the max-pool + ReLU backward, straight to global memory
+            const int xp = (x0 >> 1) + px, yp = (y0 >> 1) + py;
+            if (xp < (p.W >> 1) && yp < (p.H >> 1))
+              *reinterpret_cast<uint2*>(p.pool_idx + ((static_cast<size_t>(b) * (p.H >> 1) + yp) * (p.W >> 1) + xp) * p.Cout +
+                                        chunk * 8) = codes;
           }
           *reinterpret_cast<uint4*>(pst + pr * 128 + ((chunk ^ (pr & 7)) * 16)) = m4;
           fence_proxy_async_smem();
@@ -398,6 +403,8 @@ static int launch_c64(const ConvArgs& a, cudaStream_t stream) {
   p.use_gram = (EPI == 0 && a.gram_act != nullptr) ? 1 : 0;
   ISX_REQUIRE(!p.use_gram || a.gram_act == a.mask_act, "conv_c64: the fused Gram operand must be the ReLU-mask activation");
   p.fuse_pool = (EPI == 0 && a.pool_out != nullptr && a.H >= 2 && a.W >= 2) ? 1 : 0;
+  p.pool_idx = p.fuse_pool ? a.pool_idx : nullptr;
+  p.skip_out = (p.fuse_pool && a.pool_idx != nullptr && a.skip_out) ? 1 : 0;
   p.dx_nchw = a.dx_nchw; p.xc = a.xc; p.in_mask = a.in_mask; p.mask_b = a.mask_b;
   int hs = isx_ctx()->opt_c64_slots > 0 ? isx_ctx()->opt_c64_slots : 4;
   C64Layout L = c64_layout<BN, EPI>(hs, p.use_mask, p.use_gram, p.fuse_pool);

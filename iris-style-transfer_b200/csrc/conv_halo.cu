@@ -37,6 +37,8 @@ struct HaloParams {
   const __nv_bfloat16* add_buf;
   const float* aff_a;
   const float* aff_b;
+  uint8_t* pool_idx;
+  int skip_out;
 };
 
 struct HaloLayout {
@@ -361,7 +363,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const bool inside = xs < p.W && ys < p.H;  // a tile of the pair may lie entirely outside the image
         if (leader) {
-          if (inside) {
+          if (inside && !p.skip_out) {
             tma_store_4d(&tmO, stg, n0 + nh * 64, xs, ys, b);
             tma_store_commit();
           }
@@ -378,14 +380,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int px = pr & 3, py = pr >> 2;  // pooled tile is 4 x 8
           const int r00 = (2 * py) * 8 + 2 * px;
           const int rr[4] = {r00, r00 + 1, r00 + 8, r00 + 9};
-          uint4 m4 = *reinterpret_cast<const uint4*>(stg + rr[0] * 128 + ((chunk ^ (rr[0] & 7)) * 16));
+          uint4 u4[4];
 #pragma unroll
-          for (int k = 1; k < 4; ++k) {
-            const uint4 u = *reinterpret_cast<const uint4*>(stg + rr[k] * 128 + ((chunk ^ (rr[k] & 7)) * 16));
-            __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&m4);
-            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) a2[e] = __hmax2(a2[e], b2[e]);
+          for (int k = 0; k < 4; ++k) u4[k] = *reinterpret_cast<const uint4*>(stg + rr[k] * 128 + ((chunk ^ (rr[k] & 7)) * 16));
+          uint4 m4;
+          uint2 codes;
+          pool4_codes(u4, m4, codes);
+          if (p.pool_idx != nullptr) {  // routing bytes of the max-pool + ReLU backward, straight to global memory
+            const int xp = (xs >> 1) + px, yp = (ys >> 1) + py;
+            if (xp < (p.W >> 1) && yp < (p.H >> 1))
+              *reinterpret_cast<uint2*>(p.pool_idx + ((static_cast<size_t>(b) * (p.H >> 1) + yp) * (p.W >> 1) + xp) * p.Cout +
+                                        n0 + nh * 64 + chunk * 8) = codes;
           }
           *reinterpret_cast<uint4*>(pst + pr * 128 + ((chunk ^ (pr & 7)) * 16)) = m4;
           fence_proxy_async_smem();
@@ -427,6 +432,8 @@ static int launch_halo(const ConvArgs& a, cudaStream_t stream) {
   p.relu = a.relu; p.bias = a.bias; p.add_buf = a.add_buf; p.aff_a = a.aff_a; p.aff_b = a.aff_b;
   p.use_mask = a.mask_act != nullptr ? 1 : 0;
   p.fuse_pool = (a.pool_out != nullptr && a.H >= 2 && a.W >= 2) ? 1 : 0;
+  p.pool_idx = p.fuse_pool ? a.pool_idx : nullptr;
+  p.skip_out = (p.fuse_pool && a.pool_idx != nullptr && a.skip_out) ? 1 : 0;
   int ws = isx_ctx()->opt_halo2_stages > 0 ? std::min(isx_ctx()->opt_halo2_stages, 8) : 6;
   HaloLayout L = halo_layout<BN>(ws, p.use_mask, p.fuse_pool);
   // "smem_reserve_kb" (<= 22): leave that much of the SM's shared memory free, so that one TMEM-free streaming CTA (the

@@ -38,6 +38,8 @@ struct ConvParams {
   const float* aff_a;        // [B,Cout] or null: out += aff_a + aff_b * act   (BN-statistics tap gradient)
   const float* aff_b;
   int fuse_pool;             // epilogue also emits the 2x2 max-pooled tile (TW, TH even) through tmP
+  uint8_t* pool_idx;         // with fuse_pool: routing bytes of the max-pool + ReLU backward [B,H/2,W/2,Cout] or null
+  int skip_out;              // with fuse_pool + pool_idx: the full-resolution tile is not stored
   // EPI == 1 (image-gradient tail, BN = 16): dx fp32 NCHW [B,xc,H,W] = acc[c] * mask / std[c]
   float* dx_nchw;
   int xc;
@@ -310,8 +312,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
         if (threadIdx.x == 64) {
-          tma_store_4d(&tmO, stg, n0 + g * 64, x0[mt], y0[mt], b0[mt]);
-          tma_store_commit();
+          if (!p.skip_out) {
+            tma_store_4d(&tmO, stg, n0 + g * 64, x0[mt], y0[mt], b0[mt]);
+            tma_store_commit();
+          }
           if (use_mask && gi + 2 < NG) issue_mask_load(gi + 2);  // scratch slot (gi & 1) has been read by everyone
         }
         if (p.fuse_pool) {
@@ -325,14 +329,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int px = pr % twp, py = (pr / twp) % thp, pb = pr / (twp * thp);
             const int r00 = (pb * p.TH + 2 * py) * p.TW + 2 * px;
             const int rr[4] = {r00, r00 + 1, r00 + p.TW, r00 + p.TW + 1};
-            uint4 m4 = *reinterpret_cast<const uint4*>(stg + rr[0] * 128 + ((chunk ^ (rr[0] & 7)) * 16));
+            uint4 u4[4];
 #pragma unroll
-            for (int k = 1; k < 4; ++k) {
-              const uint4 u = *reinterpret_cast<const uint4*>(stg + rr[k] * 128 + ((chunk ^ (rr[k] & 7)) * 16));
-              __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&m4);
-              const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) a2[e] = __hmax2(a2[e], b2[e]);
+            for (int k = 0; k < 4; ++k) u4[k] = *reinterpret_cast<const uint4*>(stg + rr[k] * 128 + ((chunk ^ (rr[k] & 7)) * 16));
+            uint4 m4;
+            uint2 codes;
+            pool4_codes(u4, m4, codes);
+            if (p.pool_idx != nullptr) {  // routing bytes of the max-pool + ReLU backward, straight to global memory
+              const int xp = (x0[mt] >> 1) + px, yp = (y0[mt] >> 1) + py, bp = b0[mt] + pb;
+              if (xp < (p.W >> 1) && yp < (p.H >> 1) && bp < p.B)
+                *reinterpret_cast<uint2*>(p.pool_idx + ((static_cast<size_t>(bp) * (p.H >> 1) + yp) * (p.W >> 1) + xp) * p.Cout +
+                                          n0 + g * 64 + chunk * 8) = codes;
             }
             *reinterpret_cast<uint4*>(pst + pr * 128 + ((chunk ^ (pr & 7)) * 16)) = m4;
           }
@@ -397,6 +404,8 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
   const bool fuse_pool = EPI == 0 && a.pool_out != nullptr && p.TW % 2 == 0 && p.TH % 2 == 0 &&
                          a.H >= 2 && a.W >= 2;
   p.fuse_pool = fuse_pool ? 1 : 0;
+  p.pool_idx = fuse_pool ? a.pool_idx : nullptr;
+  p.skip_out = (fuse_pool && a.pool_idx != nullptr && a.skip_out) ? 1 : 0;
   const int epi_bytes = (MT * (BN / 64) + (a.mask_act ? 2 : 0)) * kATileBytes + (fuse_pool ? MT * (BN / 64) * 4096 : 0);
   int stages;
   size_t ring_bytes;
@@ -463,8 +472,10 @@ static int launch_conv(const ConvArgs& a, int stages_override, cudaStream_t stre
   kern<<<(unsigned)grid, kConvThreads, smem_bytes, stream>>>(tmA, tmB, tmO, tmM, tmA2, tmB2, tmP, p);
   isx_prof_end(ISX_PROF_CONV, stream);
   ISX_LAUNCH_CHECK();
-  if (a.pool_out != nullptr && !fuse_pool)  // patch shape not poolable in the epilogue: separate kernel
+  if (a.pool_out != nullptr && !fuse_pool) {  // patch shape not poolable in the epilogue: separate kernel
+    if (a.pool_idx != nullptr) return maxpool_fwd_idx(a.out, a.pool_out, a.pool_idx, a.B, a.H, a.W, a.Cout, stream);
     return maxpool_fwd(a.out, a.pool_out, a.B, a.H, a.W, a.Cout, stream);
+  }
   return 0;
 }
 

@@ -281,6 +281,89 @@ int maxpool_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* act, __nv_bfloat16
   return 0;
 }
 
+// The same pool with the routing codes of its backward (pool4_codes: first-maximum position 0..3, 4 = blocked by the ReLU)
+// stored as one byte per pooled element -- what the conv epilogues emit when they fuse the pool.  The backward then reads
+// the pooled gradient and the codes (3 B per pooled element) instead of the four pre-pool activations (8 B).
+__global__ void maxpool_fwd_idx_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                       uint8_t* __restrict__ idx, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
+  const long n = static_cast<long>(B) * Ho * Wo * C8;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c8 = i % C8;
+    const int xo = (i / C8) % Wo;
+    const int yo = (i / (static_cast<long>(C8) * Wo)) % Ho;
+    const int b = i / (static_cast<long>(C8) * Wo * Ho);
+    const __nv_bfloat16* p = in + ((static_cast<long>(b) * H + 2 * yo) * W + 2 * xo) * C + c8 * 8;
+    uint4 u[4];
+    u[0] = __ldg(reinterpret_cast<const uint4*>(p));
+    u[1] = __ldg(reinterpret_cast<const uint4*>(p + C));
+    u[2] = __ldg(reinterpret_cast<const uint4*>(p + static_cast<long>(W) * C));
+    u[3] = __ldg(reinterpret_cast<const uint4*>(p + static_cast<long>(W) * C + C));
+    uint4 m4;
+    uint2 codes;
+    pool4_codes(u, m4, codes);
+    const long o = ((static_cast<long>(b) * Ho + yo) * Wo + xo) * C + c8 * 8;
+    if (out != nullptr) *reinterpret_cast<uint4*>(out + o) = m4;
+    *reinterpret_cast<uint2*>(idx + o) = codes;
+  }
+}
+
+int maxpool_fwd_idx(const __nv_bfloat16* in, __nv_bfloat16* out, uint8_t* idx, int B, int H, int W, int C, cudaStream_t s) {
+  ISX_REQUIRE(C % 8 == 0 && H >= 2 && W >= 2, "maxpool: bad shape H=%d W=%d C=%d", H, W, C);
+  const long n = static_cast<long>(B) * (H / 2) * (W / 2) * (C / 8);
+  const int blocks = static_cast<int>(std::min<long>((n + 255) / 256, static_cast<long>(isx_num_sms()) * 16));
+  maxpool_fwd_idx_kernel<<<blocks, 256, 0, s>>>(in, out, idx, B, H, W, C);
+  ISX_LAUNCH_CHECK();
+  return 0;
+}
+
+// dx[pre-pool position k] = (code == k) ? dy[pooled] : 0
+__global__ void maxpool_bwd_idx_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
+                                       __nv_bfloat16* __restrict__ dx, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
+  const long n = static_cast<long>(B) * Ho * Wo * C8;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c8 = i % C8;
+    const int xo = (i / C8) % Wo;
+    const int yo = (i / (static_cast<long>(C8) * Wo)) % Ho;
+    const int b = i / (static_cast<long>(C8) * Wo * Ho);
+    const long po = ((static_cast<long>(b) * Ho + yo) * Wo + xo) * C + c8 * 8;
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(dy + po));
+    const uint2 cd = __ldg(reinterpret_cast<const uint2*>(idx + po));
+    const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+    // codes of elements (2e, 2e+1) as 16-bit lanes: byte 2e of the code word pair -> low half, byte 2e+1 -> high half
+    const uint32_t c16[4] = {__byte_perm(cd.x, 0u, 0x4140), __byte_perm(cd.x, 0u, 0x4342), __byte_perm(cd.y, 0u, 0x4140),
+                             __byte_perm(cd.y, 0u, 0x4342)};
+    const long base = ((static_cast<long>(b) * H + 2 * yo) * W + 2 * xo) * C + c8 * 8;
+    const long offs[4] = {0, C, static_cast<long>(W) * C, static_cast<long>(W) * C + C};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t d = c16[e] ^ (static_cast<uint32_t>(k) * 0x00010001u);  // a 16-bit lane is zero where code == k
+        const uint32_t keep = ((d & 0x0000FFFFu) ? 0u : 0x0000FFFFu) | ((d & 0xFFFF0000u) ? 0u : 0xFFFF0000u);
+        o[e] = gw[e] & keep;
+      }
+      *reinterpret_cast<uint4*>(dx + base + offs[k]) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+int maxpool_bwd_idx(const __nv_bfloat16* dy, const uint8_t* idx, __nv_bfloat16* dx, int B, int H, int W, int C,
+                    cudaStream_t s) {
+  ISX_REQUIRE(C % 8 == 0 && H >= 2 && W >= 2, "maxpool_bwd: bad shape H=%d W=%d C=%d", H, W, C);
+  if ((H & 1) || (W & 1))  // the last row / column belongs to no window: gradient 0
+    ISX_CHECK_CUDA(cudaMemsetAsync(dx, 0, static_cast<size_t>(B) * H * W * C * 2, s));
+  const long n = static_cast<long>(B) * (H / 2) * (W / 2) * (C / 8);
+  const int blocks = static_cast<int>(std::min<long>((n + 255) / 256, static_cast<long>(isx_num_sms()) * 16));
+  maxpool_bwd_idx_kernel<<<blocks, 256, 0, s>>>(dy, idx, dx, B, H, W, C);
+  ISX_LAUNCH_CHECK();
+  return 0;
+}
+
 // Row G' (mask-weighted Gram, SURVEY.md note N5): Fm = F * m_l (Gram input), Fm2 = F * m_l^2 (its backward operand:
 // m * ((F*m) . D) == (F*m^2) . D because m is a per-pixel scalar).  F bf16 [B,HW,C], m fp32 [mask_b,HW].
 __global__ void mask_features_kernel(const __nv_bfloat16* __restrict__ f, const float* __restrict__ m, int mask_b,

@@ -46,6 +46,9 @@ struct IsxContext {
   int opt_c64_slots = 0;             // "c64_slots": halo ring depth override
   int opt_halo2_stages = 0;          // "halo2_stages": weight ring depth override
   int opt_smem_reserve_kb = 0;       // "smem_reserve_kb": shared memory the persistent conv CTAs leave free per SM
+  int opt_head_ctas = 5;             // "head_ctas": resident CTAs per SM the conv1_1 head is compiled for (5 or 8)
+  int opt_pool_idx = 1;              // "pool_idx": the NST driver routes the max-pool backward through index bytes (0: re-reads
+                                     // the pre-pool activations, which the forward then always stores)
   unsigned long long launches = 0;   // kernels launched through this context
   IsxProfiler* prof = nullptr;
 };
@@ -282,6 +285,31 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(h);
 }
+// 2x2 max-pool of four chunks of eight post-ReLU bf16 values (window scan order (0,0),(0,1),(1,0),(1,1)): the maxima and, per
+// element, the ROUTING CODE of the fused max-pool + ReLU backward -- 0..3 = position of the FIRST maximum (ATen's
+// `val > maxval` rule), 4 = blocked (maximum <= 0: ReLU passes nothing).  One byte per element, in element order.
+__device__ __forceinline__ void pool4_codes(const uint4 (&u)[4], uint4& m4, uint2& codes) {
+  uint32_t cw[4];
+  const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __nv_bfloat162 m = reinterpret_cast<const __nv_bfloat162*>(&u[0])[e];
+    uint32_t code = 0u;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const __nv_bfloat162 a = reinterpret_cast<const __nv_bfloat162*>(&u[k])[e];
+      const uint32_t gt = __hgt2_mask(a, m);  // 0xFFFF per half where a > m
+      m = __hmax2(m, a);
+      code = (code & ~gt) | (gt & (static_cast<uint32_t>(k) * 0x00010001u));
+    }
+    const uint32_t z = __hle2_mask(m, zero2);
+    cw[e] = (code & ~z) | (z & 0x00040004u);
+    reinterpret_cast<__nv_bfloat162*>(&m4)[e] = m;
+  }
+  codes.x = __byte_perm(cw[0], cw[1], 0x6420);
+  codes.y = __byte_perm(cw[2], cw[3], 0x6420);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

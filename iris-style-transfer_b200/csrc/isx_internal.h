@@ -16,6 +16,11 @@ struct ConvArgs {
   const float* bias = nullptr;
   int relu = 0;
   __nv_bfloat16* pool_out = nullptr;  // also write MaxPool2d(2,2)(out) [B,H/2,W/2,Cout] (fused into the epilogue when possible)
+  // with pool_out: one routing byte per pooled element for the fused max-pool + ReLU backward (pool4_codes) [B,H/2,W/2,Cout]
+  uint8_t* pool_idx = nullptr;
+  // with pool_out + pool_idx: do not store the full-resolution output at all (nobody reads it: the backward routes through
+  // pool_idx).  Honoured when the pool is fused into the epilogue; `out` must still be a valid buffer (fallback path).
+  bool skip_out = false;
   const __nv_bfloat16* mask_act = nullptr;
   const __nv_bfloat16* add_buf = nullptr;
   const float* aff_a = nullptr;

@@ -33,6 +33,7 @@ struct Layout {
   int B, H[6], W[6];
   size_t act[16];     // byte offsets of ReLU outputs
   size_t pool[5];     // byte offsets of pool outputs
+  size_t pidx[5];     // routing bytes of each pool's backward (one per pooled element, pool4_codes)
   size_t gradA, gradB, tapbuf;
   size_t cgrad[ISX_MAX_TAPS];
   size_t gram_ws, D[ISX_MAX_TAPS], sums, csum, aff_a[ISX_MAX_TAPS], aff_b[ISX_MAX_TAPS];
@@ -68,6 +69,9 @@ int make_layout(const isx_nst_config* c, Layout* L) {
     const int conv_before[5] = {1, 3, 7, 11, 15};
     if (conv_before[k] < c->n_conv)
       off += align_up(static_cast<size_t>(c->B) * L->H[k + 1] * L->W[k + 1] * kCout[conv_before[k]] * 2);
+    L->pidx[k] = off;
+    if (conv_before[k] < c->n_conv)
+      off += align_up(static_cast<size_t>(c->B) * L->H[k + 1] * L->W[k + 1] * kCout[conv_before[k]]);
   }
   auto tap_ok = [&](int id) { return id >= 0 && id < ISX_VGG19_TAPS && tap_conv(id) < c->n_conv && L->H[tap_level(id)] >= 1 && L->W[tap_level(id)] >= 1; };
   for (int t = 0; t < c->n_style; ++t) {
@@ -126,9 +130,16 @@ int content_tap_of(const isx_nst_config* c, int conv) {
   return -1;
 }
 
-// forward through conv `i` (input selection included)
+inline uint8_t* atb(const isx_nst_buffers* b, size_t off) { return reinterpret_cast<uint8_t*>(static_cast<char*>(b->workspace) + off); }
+
+// Is the ReLU output of conv `i` read by anything but the pool that follows it?  (taps only: the max-pool + ReLU backward
+// routes through the pool's index bytes, not through the pre-pool activation)
+bool conv_tapped(const isx_nst_config* c, int i) { return style_tap_of(c, i) >= 0 || content_tap_of(c, i) >= 0; }
+
+// forward through conv `i` (input selection included).  lean: a pre-pool activation that no tap reads is not written to
+// memory at all -- only its pooled map and the routing bytes are (57 MB of stores per 640x400 image).
 int run_conv_fwd(const isx_nst_config* c, const isx_nst_buffers* b, const Layout& L, int i, const float* x,
-                 bool want_pool, cudaStream_t s) {
+                 bool want_pool, cudaStream_t s, bool lean = false) {
   const int lv = kLevel[i];
   if (i == 0 && b->w0_fwd != nullptr)
     return conv1_1_fwd_tc(x, c->xc, c->mask_b ? b->input_mask : nullptr, c->mask_b,
@@ -146,6 +157,10 @@ int run_conv_fwd(const isx_nst_config* c, const isx_nst_buffers* b, const Layout
   if (want_pool) {  // MaxPool2d(2,2) of this layer's output rides the conv epilogue
     ISX_REQUIRE(L.H[lv] >= 2 && L.W[lv] >= 2, "nst: cannot pool a %dx%d map", L.H[lv], L.W[lv]);
     a.pool_out = at(b, L.pool[lv]);
+    if (isx_ctx()->opt_pool_idx) {
+      a.pool_idx = atb(b, L.pidx[lv]);
+      a.skip_out = lean && !conv_tapped(c, i);
+    }
   }
   return conv_tc(a, s);
 }
@@ -157,15 +172,16 @@ extern "C" int64_t isx_nst_workspace_bytes(const isx_nst_config* cfg) {
   return static_cast<int64_t>(L.total);
 }
 
-extern "C" int isx_nst_forward(const isx_nst_config* c, const isx_nst_buffers* b, const float* x, int with_last_pool,
+extern "C" int isx_nst_forward(const isx_nst_config* c, const isx_nst_buffers* b, const float* x, int flags,
                                isx_stream stream) {
   ISX_REQUIRE(c && b && x && b->workspace, "isx_nst_forward: null pointer");
   Layout L;
   if (int rc = make_layout(c, &L)) return rc;
   cudaStream_t s = S(stream);
+  const bool with_last_pool = (flags & ISX_FWD_LAST_POOL) != 0, lean = (flags & ISX_FWD_LEAN) != 0;
   for (int i = 0; i < c->n_conv; ++i) {
     const bool want_pool = pool_after(i) && (i + 1 < c->n_conv || with_last_pool || pool_tapped(c, pool_index(i)));
-    if (int rc = run_conv_fwd(c, b, L, i, x, want_pool && i > 0, s)) return rc;
+    if (int rc = run_conv_fwd(c, b, L, i, x, want_pool && i > 0, s, lean)) return rc;
     if (want_pool && i == 0) {  // (conv1_1 is never followed by a pool in VGG-19; kept for completeness)
       const int lv = kLevel[i];
       if (int rc = maxpool_fwd(at(b, L.act[i]), at(b, L.pool[lv]), c->B, L.H[lv], L.W[lv], kCout[i], s)) return rc;
@@ -232,6 +248,12 @@ int run_backward(const isx_nst_config* c, const isx_nst_buffers* b, const Layout
     a.mask_act = mask ? at(b, tap_off(L, id)) : nullptr;
     return conv_tc(a, s);
   };
+  // max-pool + ReLU backward of the pool after conv `conv` (level lv): through the routing bytes the forward left, or
+  // (option "pool_idx" = 0) by re-reading the pre-pool activation
+  auto pool_bwd = [&](const bf16* dy, int lv, int conv, bf16* dx) -> int {
+    if (isx_ctx()->opt_pool_idx) return maxpool_bwd_idx(dy, atb(b, L.pidx[lv]), dx, B, L.H[lv], L.W[lv], kCout[conv], s);
+    return maxpool_bwd(dy, at(b, L.act[conv]), dx, B, L.H[lv], L.W[lv], kCout[conv], s);
+  };
   // gradient w.r.t. a POOL output: out = g (may be NULL) + every source of that pool tap; no ReLU mask (the max-pool
   // backward that follows applies the ReLU mask of the pre-pool activation)
   auto pool_combine = [&](int k, const bf16* g, bf16* out) -> int {
@@ -258,11 +280,13 @@ int run_backward(const isx_nst_config* c, const isx_nst_buffers* b, const Layout
       pg = ping;
     }
     if (pg) {
-      if (int rc = maxpool_bwd(pg, at(b, L.act[i]), pong, B, L.H[lv], L.W[lv], C, s)) return rc;
+      if (int rc = pool_bwd(pg, lv, i, pong)) return rc;
       up = pong;
     }
     ISX_REQUIRE(up || t.any(), "nst backward: conv %d carries no gradient", i);
-    if (!up && t.add && !t.aa && !t.gram_D) {
+    if (up && !t.any()) {
+      gm = up;  // the max-pool backward already applied this layer's ReLU mask (its activation may not even be stored)
+    } else if (!up && t.add && !t.aa && !t.gram_D) {
       if (t.add_is_masked) {
         gm = t.add;
       } else {  // a lone gradient map must be ReLU-masked before the dgrad
@@ -314,7 +338,7 @@ int run_backward(const isx_nst_config* c, const isx_nst_buffers* b, const Layout
       if (pool_src(j))                        // taps on this pool add their gradient in place
         if (int rc = pool_combine(pool_index(j), a.out, a.out)) return rc;
       // `other` held this dgrad's input, which is consumed now
-      if (int rc = maxpool_bwd(a.out, at(b, L.act[j]), other, B, L.H[lvj], L.W[lvj], Cj, s)) return rc;
+      if (int rc = pool_bwd(a.out, lvj, j, other)) return rc;
       gm = other;
       if (t.any()) {
         const bf16* add2 = t.add;
@@ -417,7 +441,7 @@ extern "C" int isx_nst_eval(const isx_nst_config* c, const isx_nst_buffers* b, c
   // ---------------- forward + losses ----------------
   for (int i = 0; i < c->n_conv; ++i) {
     const bool want_pool = pool_after(i) && (i + 1 < c->n_conv || pool_tapped(c, pool_index(i)));
-    if (int rc = run_conv_fwd(c, b, L, i, x, want_pool, s)) return rc;
+    if (int rc = run_conv_fwd(c, b, L, i, x, want_pool, s, /*lean=*/true)) return rc;
     if (int rc = tap_losses(i)) return rc;
     if (want_pool && pool_tapped(c, pool_index(i)))
       if (int rc = tap_losses(ISX_TAP_POOL0 + pool_index(i))) return rc;

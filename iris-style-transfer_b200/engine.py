@@ -14,6 +14,7 @@ MAX_TAPS = 8
 N_CONVS = 16
 TAP_POOL0 = 16          # tap ids: 0..15 = ReLU output of conv i, 16..20 = output of pool 0..4 (include/isx.h ISX_TAP_POOL0)
 N_TAPS = 21
+FWD_LAST_POOL, FWD_LEAN = 1, 2   # include/isx.h ISX_FWD_*
 CONV_BEFORE_POOL = [1, 3, 7, 11, 15]
 
 # models/vgg/vgg.py:6-10 (torchvision vgg19.features indices)
@@ -213,11 +214,13 @@ class NstEngine:
             self.cfg.style_target_b = means[0].shape[0] if means[0].dim() == 2 else 1
 
     # ---- compute -------------------------------------------------------------------------
-    def forward(self, x: torch.Tensor, with_last_pool: bool = False):
+    def forward(self, x: torch.Tensor, with_last_pool: bool = False, lean: bool = False):
+        """lean (ISX_FWD_LEAN): pre-pool ReLU outputs that are not taps are not written to memory -- only their pooled maps and
+        the routing bytes of the pool's backward; feature_view(0, i) of such a conv is undefined afterwards."""
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
         assert tuple(x.shape) == (self.cfg.B, self.cfg.xc, self.cfg.H, self.cfg.W), (tuple(x.shape), self.cfg.B)
-        _lib.call("isx_nst_forward", ctypes.byref(self.cfg), ctypes.byref(self.bufs), x, int(with_last_pool),
-                  _lib.stream_ptr())
+        flags = (FWD_LAST_POOL if with_last_pool else 0) | (FWD_LEAN if lean else 0)
+        _lib.call("isx_nst_forward", ctypes.byref(self.cfg), ctypes.byref(self.bufs), x, flags, _lib.stream_ptr())
 
     def feature(self, kind: int, idx: int) -> torch.Tensor:
         """bf16 NHWC COPY of a stored activation: kind 0 = conv idx's ReLU output, 1 = pool idx."""

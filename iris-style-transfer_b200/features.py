@@ -32,7 +32,7 @@ def style_features_batch(vgg: VGG19, x: torch.Tensor, gram: bool = True, stats: 
     on the activations where they lie in the workspace and written straight into the rows of `out` (given or new)."""
     if not (gram or stats):
         raise ValueError("nothing to extract")
-    eng = vgg.run_forward(x, full=False)
+    eng = vgg.run_forward(x, full=False, lean=True)
     chans = [tap_channels(c) for c in vgg.style_convs]
     D = feature_dim(chans, gram, stats)
     if out is None:
@@ -134,7 +134,7 @@ def cache_classifier_inputs(vgg: VGG19, images, batch: int = 32, device=None):
     pool = torch.empty(n, 25088, device=dev, dtype=torch.bfloat16)
     for lo in range(0, n, batch):
         xb = torch.as_tensor(images[lo:lo + batch]).to(dev, torch.float32)
-        eng = vgg.run_forward(xb, full=True)
+        eng = vgg.run_forward(xb, full=True, lean=True)
         b = xb.shape[0]
         with torch.cuda.device(dev):
             eng.style_features(stats[lo:lo + b], stats=True, gram=False)

@@ -191,8 +191,10 @@ class VGG19(torch.nn.Module):
         return self._engines[key]
 
     @torch.no_grad()
-    def run_forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None, full: bool = False) -> NstEngine:
-        """Forward pass only; the activations stay in the returned engine's workspace (engine.feature_view)."""
+    def run_forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None, full: bool = False,
+                    lean: bool = False) -> NstEngine:
+        """Forward pass only; the activations stay in the returned engine's workspace (engine.feature_view).  lean: pre-pool
+        activations that are not taps are not materialised (feature extraction: nobody reads them)."""
         if x.dim() == 3:
             x = x[None]
         dev = x.device if x.is_cuda else self._device
@@ -205,7 +207,7 @@ class VGG19(torch.nn.Module):
         self._last_engine = eng
         self._fwd_version += 1
         with torch.cuda.device(dev):
-            eng.forward(x, with_last_pool=full)
+            eng.forward(x, with_last_pool=full, lean=lean)
         return eng
 
     @torch.no_grad()

@@ -95,6 +95,20 @@ def test_conv3x3_fwd_fused_pool(isx, shape, cfg):
     assert_close_bf16(out, ref.permute(0, 2, 3, 1), "conv fwd (+pool) %s cfg %d" % (shape, cfg))
     ref_pool = F.max_pool2d(out.float().permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
     assert torch.equal(pool.float(), ref_pool)
+    # the same launch with the routing bytes of the pool's backward, with and without the full-resolution store
+    ref_idx = torch.empty(B, H // 2, W // 2, Cout, device="cuda", dtype=torch.uint8)
+    isx.call("isx_maxpool2x2_fwd_idx", out, None, ref_idx, B, H, W, Cout, isx.stream_ptr())
+    for skip in (0, 1):
+        out2 = torch.full((B, H, W, Cout), 7.0, device="cuda", dtype=torch.bfloat16)
+        pool2 = torch.full((B, H // 2, W // 2, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+        idx2 = torch.full((B, H // 2, W // 2, Cout), 255, device="cuda", dtype=torch.uint8)
+        isx.call("isx_conv3x3_bias_relu_pool_idx_fwd", x, wf, bias, out2, pool2, idx2, skip, B, H, W, Cin, Cout, cfg,
+                 isx.stream_ptr())
+        torch.cuda.synchronize()
+        assert torch.equal(pool2, pool), "pooled map differs (skip_out=%d)" % skip
+        assert torch.equal(idx2, ref_idx), "routing bytes differ (skip_out=%d): %d" % (skip, int((idx2 != ref_idx).sum()))
+        untouched = bool((out2 == 7.0).all())
+        assert torch.equal(out2, out) or (skip == 1 and untouched), "full-resolution output (skip_out=%d)" % skip
 
 
 @pytest.mark.parametrize("shape", CONV_SHAPES)
@@ -473,6 +487,24 @@ def test_maxpool_fwd_bwd(isx, B, H, W, C):
     pr.backward(dy.float().permute(0, 3, 1, 2))
     ref = (ar.grad * (ar.detach() > 0)).permute(0, 2, 3, 1)
     assert torch.equal(dx.float(), ref)
+    # the same pair through routing bytes (what the fused conv epilogues emit): bit-identical results
+    out2 = torch.empty_like(out)
+    idx = torch.full((B, H // 2, W // 2, C), 255, device="cuda", dtype=torch.uint8)
+    isx.call("isx_maxpool2x2_fwd_idx", a, out2, idx, B, H, W, C, isx.stream_ptr())
+    dx2 = torch.full((B, H, W, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    isx.call("isx_maxpool2x2_bwd_idx", dy, idx, dx2, B, H, W, C, isx.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out) and int(idx.max()) <= 4
+    assert torch.equal(dx2, dx)
+    # ties and zero windows: first maximum wins, an all-zero window routes nothing
+    t = torch.zeros(1, 4, 4, 8, device="cuda", dtype=torch.bfloat16)
+    t[0, 0, 1, :] = 2.0
+    t[0, 1, 0, :] = 2.0          # window (0,0): tie between positions 1 and 2 -> 1
+    t[0, 2, 2, 0] = 1.0          # window (1,1), channel 0: position 0; other channels all zero -> 4
+    ti = torch.empty(1, 2, 2, 8, device="cuda", dtype=torch.uint8)
+    isx.call("isx_maxpool2x2_fwd_idx", t, None, ti, 1, 4, 4, 8, isx.stream_ptr())
+    torch.cuda.synchronize()
+    assert ti[0, 0, 0].tolist() == [1] * 8 and ti[0, 1, 1].tolist() == [0] + [4] * 7 and ti[0, 0, 1].tolist() == [4] * 8
 
 
 def test_content_mse(isx):
