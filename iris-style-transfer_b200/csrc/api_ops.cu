@@ -276,6 +276,8 @@ extern "C" int isx_set_option(const char* name, int value) {
   if (strcmp(name, "c64_slots") == 0) { isx_ctx()->opt_c64_slots = value; return 0; }
   if (strcmp(name, "smem_reserve_kb") == 0) { isx_ctx()->opt_smem_reserve_kb = value; return 0; }
   if (strcmp(name, "head_ctas") == 0) { isx_ctx()->opt_head_ctas = value; return 0; }
+  if (strcmp(name, "sweep64") == 0) { isx_ctx()->opt_sweep64 = value; return 0; }
+  if (strcmp(name, "sweep_dbg") == 0) { isx_ctx()->opt_sweep_dbg = value; return 0; }
   if (strcmp(name, "pool_idx") == 0) { isx_ctx()->opt_pool_idx = value; return 0; }
   ISX_REQUIRE(false, "isx_set_option: unknown option '%s'", name);
 }
@@ -290,6 +292,8 @@ extern "C" int isx_get_option(const char* name, int* value) {
   if (strcmp(name, "c64_slots") == 0) { *value = c->opt_c64_slots; return 0; }
   if (strcmp(name, "smem_reserve_kb") == 0) { *value = c->opt_smem_reserve_kb; return 0; }
   if (strcmp(name, "head_ctas") == 0) { *value = c->opt_head_ctas; return 0; }
+  if (strcmp(name, "sweep64") == 0) { *value = c->opt_sweep64; return 0; }
+  if (strcmp(name, "sweep_dbg") == 0) { *value = c->opt_sweep_dbg; return 0; }
   if (strcmp(name, "pool_idx") == 0) { *value = c->opt_pool_idx; return 0; }
   ISX_REQUIRE(false, "isx_get_option: unknown option '%s'", name);
 }

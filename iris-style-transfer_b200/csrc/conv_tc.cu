@@ -494,6 +494,14 @@ int conv_tc(const ConvArgs& a_in, cudaStream_t stream) {
   if (a.dx_nchw != nullptr && isx_ctx()->opt_tail_n > 0 && isx_ctx()->opt_c64 < 2 && a.force_bn == 0 &&
       a.Cin == 64 && a.Cout == 16 && a.ntaps == 9)
     return conv1_1_tail_n(a.in, a.weight, a.in_mask, a.mask_b, a.dx_nchw, a.xc, a.B, a.H, a.W, stream);
+  if (isx_ctx()->opt_sweep64 > 0 && a.force_bn == 0 && conv_sweep_applicable(a)) {
+    // strips of 128 pixels along the better-fitting image axis, every CTA sweeps an equal share of them: worth it when the
+    // strips are mostly real pixels (the kernel is ~1.5x faster per processed pixel than conv_c64) and every SM gets a few
+    // hundred of them (a CTA's share starts and ends with two slower edge strips)
+    const long strips = static_cast<long>(a.B) * ((std::max(a.H, a.W) + 127) / 128) * std::min(a.H, a.W);
+    if (isx_ctx()->opt_sweep64 >= 2 || (conv_sweep_efficiency(a) >= 0.85 && strips >= 64L * kNumSMs && std::min(a.H, a.W) >= 16))
+      return conv_sweep(a, stream);
+  }
   if (isx_ctx()->opt_c64 > 0 && a.force_bn == 0 && conv_c64_applicable(a) &&
       (isx_ctx()->opt_c64 >= 2 || (a.dx_nchw == nullptr && static_cast<long>(a.B) * ((a.H + 15) / 16) * ((a.W + 7) / 8) >= kNumSMs)))
     return conv_c64(a, stream);

@@ -38,6 +38,10 @@ struct ConvArgs {
 int conv_tc(const ConvArgs& a, cudaStream_t stream);
 bool conv_c64_applicable(const ConvArgs& a);
 int conv_c64(const ConvArgs& a, cudaStream_t stream);
+// Cin = Cout = 64 as a sweep with the sweep-axis taps stacked in N (conv_sweep.cu)
+bool conv_sweep_applicable(const ConvArgs& a);
+double conv_sweep_efficiency(const ConvArgs& a);
+int conv_sweep(const ConvArgs& a, cudaStream_t stream);
 // image-gradient tail with the taps in N (conv1_1_tail.cu)
 int conv1_1_tail_n(const __nv_bfloat16* dy, const __nv_bfloat16* wd, const float* mask, int mask_b, float* dx, int xc,
                    int B, int H, int W, cudaStream_t stream);

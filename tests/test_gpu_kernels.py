@@ -197,6 +197,62 @@ def test_conv_c64_tail(isx, c64_forced, xc, use_mask):
     test_conv1_1_fwd_dgrad(isx, xc, use_mask)
 
 
+# ---- the tap-stacked sweep kernel (conv_sweep.cu): 128-pixel strips, N = 192 MMAs into a ring of eight TMEM accumulators ----
+SWEEP_SHAPES = [
+    (2, 20, 24, 64, 64),      # one partly filled strip along x, one short segment
+    (3, 13, 9, 64, 64),       # ragged, odd sizes
+    (2, 41, 37, 64, 64),      # odd sizes: the fused pool drops the last row / column, strips along y
+    (1, 256, 40, 64, 64),     # strips along y (two full strips), sweep along x
+    (2, 128, 230, 64, 64),    # strips along y, two sweep segments (116 + 114): the accumulator ring wraps many times
+    (4, 160, 200, 64, 64),    # strips along x (200 = 128 + 72), two segments of 80 rows, several jobs per CTA
+    (1, 300, 128, 64, 64),    # strips along x exactly 128 wide, three segments
+]
+
+
+@pytest.fixture
+def sweep_forced(isx):
+    lib = isx.load()
+    assert lib.isx_set_option(b"sweep64", 2) == 0
+    yield
+    assert lib.isx_set_option(b"sweep64", 0) == 0
+
+
+@pytest.mark.parametrize("shape", SWEEP_SHAPES)
+def test_conv_sweep_fwd_and_pool(isx, sweep_forced, shape):
+    test_conv3x3_fwd(isx, shape, 0)
+    test_conv3x3_fwd_fused_pool(isx, shape, 0)
+
+
+@pytest.mark.parametrize("shape", SWEEP_SHAPES)
+@pytest.mark.parametrize("mode", ["plain", "mask", "mask_add", "mask_affine", "gram"])
+def test_conv_sweep_dgrad(isx, sweep_forced, shape, mode):
+    if mode == "gram":
+        test_conv3x3_dgrad_fused_gram(isx, shape)
+    else:
+        test_conv3x3_dgrad(isx, shape, mode)
+
+
+def test_conv_sweep_matches_c64_bitwise(isx):
+    """Same K order per output element (nine taps x four 16-channel steps, fp32 accumulation in TMEM) is not guaranteed between
+    the two kernels, but both must agree to one bf16 rounding; and the sweep kernel must be deterministic run to run."""
+    B, H, W = 2, 256, 120
+    x = nhwc_bf16(B, H, W, 64, 5, relu=True)
+    w = torch.randn(64, 64, 3, 3, device="cuda") * (2.0 / (9 * 64)) ** 0.5
+    bias = torch.randn(64, device="cuda") * 0.1
+    wf, _ = pack(isx, w)
+    lib = isx.load()
+    outs = []
+    for opt in (0, 2, 2):
+        assert lib.isx_set_option(b"sweep64", opt) == 0
+        o = torch.empty(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
+        isx.call("isx_conv3x3_bias_relu_fwd", x, wf, bias, o, B, H, W, 64, 64, 1, 0, isx.stream_ptr())
+        outs.append(o)
+    assert lib.isx_set_option(b"sweep64", 0) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(outs[1], outs[2])
+    assert_close_bf16(outs[1], outs[0].float(), "sweep vs c64")
+
+
 # ---- the halo-patch pair kernel (conv_halo.cu): persistent CTAs, 16x16 / 8x32 pixel pairs, streamed weight slabs ------
 HALO_SHAPES = [
     (2, 20, 24, 64, 64),       # BN = 64, fewer items than SMs
