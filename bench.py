@@ -433,7 +433,7 @@ def main():
     ap.add_argument("--smem-reserve-kb", type=int, default=0, help="shared memory per SM the persistent conv CTAs leave free")
     ap.add_argument("--history-bf16", action="store_true", help="opt-in: store the L-BFGS (s, y) history in bf16")
     ap.add_argument("--feature-images", type=int, default=512, help="images per GPU of the feature-extraction leg")
-    ap.add_argument("--feature-batch", type=int, default=32, help="images per forward pass of the feature-extraction leg")
+    ap.add_argument("--feature-batch", type=int, default=64, help="images per forward pass of the feature-extraction leg")
     ap.add_argument("--opt", action="append", default=[], help="name=value: libisx kernel-selection option (isx_set_option), repeatable")
     ap.add_argument("--e2e-evals", type=int, default=300, help="evaluations of the end-to-end job (BASELINE config[1]: 300)")
     args = ap.parse_args()

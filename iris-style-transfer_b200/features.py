@@ -53,7 +53,7 @@ def feature_dim(channels: Sequence[int], gram: bool = True, stats: bool = True) 
 
 
 @torch.no_grad()
-def extract_features_sharded(vgg: VGG19, images, batch: int = 32, gram: bool = True, stats: bool = True,
+def extract_features_sharded(vgg: VGG19, images, batch: int = 64, gram: bool = True, stats: bool = True,
                              device=None, gather_chunk: int = 128) -> torch.Tensor:
     """`images`: indexable [n,1|3,H,W] (host or device).  Each rank extracts its contiguous shard in batches of `batch`,
     every batch writing its rows in place into the final matrix; complete chunks of `gather_chunk` rows are all-gathered
