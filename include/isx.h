@@ -30,6 +30,17 @@ int isx_version(void);
 /* fails unless `device` is an sm_100 part: there is no fallback path */
 int isx_device_check(int device);
 
+/* ---- peer memory over NVLink (one process per GPU of one box) ---------------------------------------------------------
+ * isx_ipc_export: 64-byte handle of the cudaMalloc allocation that contains `ptr` + the byte offset of `ptr` inside it;
+ * isx_ipc_open (in ANOTHER process of the box): maps that allocation into the caller's address space with peer access
+ * enabled and returns its base; isx_ipc_close unmaps it.  Used by sharding.PeerRows: every rank pushes its feature rows
+ * straight into every other rank's matrix (BASELINE config 3) with copy-engine copies instead of an all-gather kernel. */
+int isx_ipc_export(const void* ptr, void* handle64, int64_t* offset);
+int isx_ipc_open(const void* handle64, void** base_out);
+int isx_ipc_close(void* base);
+/* device-to-device copy on `stream` (cudaMemcpyAsync: copy engines); dst may be peer memory mapped with isx_ipc_open */
+int isx_copy_d2d_async(void* dst, const void* src, int64_t bytes, isx_stream stream);
+
 /* ---- handles ---------------------------------------------------------------------------------
  * The library keeps NO process-global mutable state.  Kernel-selection options (isx_set_option), the launch counter, the
  * CUDA-event profiler and the device's SM count (grid sizing) live in a context.  isx_create makes one for `device`,

@@ -28,6 +28,55 @@ extern "C" int isx_device_check(int device) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Peer memory (BASELINE config 3: the feature rows of every rank land in every rank's matrix).  A rank exports the
+// cudaMalloc allocation behind its row matrix as a 64-byte IPC handle, the other ranks of the box map it into their own
+// address space (peer access over NVLink / NVSwitch enabled lazily by the driver) and PUSH their rows into it with plain
+// device-to-device copies -- copy engines, no SM, no collective kernel competing with the persistent conv CTAs.
+// ---------------------------------------------------------------------------------------------
+extern "C" int isx_ipc_export(const void* ptr, void* handle64, int64_t* offset) {
+  ISX_REQUIRE(ptr && handle64 && offset, "isx_ipc_export: null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  // the handle names the whole allocation: report where `ptr` lies inside it
+  typedef CUresult (*RangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  static RangeFn range = nullptr;
+  if (!range) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &qres);
+    ISX_REQUIRE(e == cudaSuccess && qres == cudaDriverEntryPointSuccess && f, "isx_ipc_export: cuMemGetAddressRange unavailable");
+    range = reinterpret_cast<RangeFn>(f);
+  }
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  ISX_REQUIRE(range(&base, &size, reinterpret_cast<CUdeviceptr>(ptr)) == CUDA_SUCCESS, "isx_ipc_export: %p is not a device allocation", ptr);
+  cudaIpcMemHandle_t h;
+  ISX_CHECK_CUDA(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+  memcpy(handle64, &h, 64);
+  *offset = static_cast<int64_t>(reinterpret_cast<CUdeviceptr>(ptr) - base);
+  return 0;
+}
+
+extern "C" int isx_ipc_open(const void* handle64, void** base_out) {
+  ISX_REQUIRE(handle64 && base_out, "isx_ipc_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  ISX_CHECK_CUDA(cudaIpcOpenMemHandle(base_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+extern "C" int isx_copy_d2d_async(void* dst, const void* src, int64_t bytes, isx_stream stream) {
+  ISX_REQUIRE(dst && src && bytes >= 0, "isx_copy_d2d_async: bad arguments");
+  ISX_CHECK_CUDA(cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+extern "C" int isx_ipc_close(void* base) {
+  ISX_REQUIRE(base, "isx_ipc_close: null pointer");
+  ISX_CHECK_CUDA(cudaIpcCloseMemHandle(base));
+  return 0;
+}
+
 // cuTensorMapEncodeTiled is fetched through the runtime so that libisx.so does not link libcuda
 // (the library must load -- symbols only -- on a box without a driver for the CPU test tier).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -54,16 +54,18 @@ def feature_dim(channels: Sequence[int], gram: bool = True, stats: bool = True) 
 
 @torch.no_grad()
 def extract_features_sharded(vgg: VGG19, images, batch: int = 64, gram: bool = True, stats: bool = True,
-                             device=None, gather_chunk: int = 128) -> torch.Tensor:
+                             device=None, gather_chunk: int = 128, peer: bool = True) -> torch.Tensor:
     """`images`: indexable [n,1|3,H,W] (host or device).  Each rank extracts its contiguous shard in batches of `batch`,
     every batch writing its rows in place into the final matrix; complete chunks of `gather_chunk` rows are all-gathered
-    on a side stream while later batches compute (sharding.RowGatherer); every rank returns the full [n, D] matrix."""
-    from .sharding import RowGatherer
+    on a side stream while later batches compute (sharding.RowGatherer) -- or, on a CUDA box (peer=True), every batch of rows
+    is pushed straight into the other ranks' matrices over NVLink by the copy engines (sharding.PeerRows; the returned matrix
+    is then a cached buffer, valid until the next extraction of the same shape); every rank returns the full [n, D] matrix."""
+    from .sharding import make_row_exchange
 
     n = len(images)
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     chans = [tap_channels(c) for c in vgg.style_convs]
-    rows = RowGatherer(n, feature_dim(chans, gram, stats), dev, chunk_rows=gather_chunk)
+    rows = make_row_exchange(n, feature_dim(chans, gram, stats), dev, chunk_rows=gather_chunk, peer=peer)
     lo, hi = rows.lo, rows.hi
     # Host -> device copies run on a side stream, one batch ahead of the kernels, into two device buffers that are
     # allocated once (a fresh allocation per batch on a second stream makes the caching allocator fall back to
