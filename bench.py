@@ -356,7 +356,7 @@ def nst_leg(args, dev, vgg, c_dev, s_dev, BN_loss, independent, K, Wm, world, ra
 
 def feature_leg(dev, vgg, taps5, n_per_gpu, world, batch=32):
     """BASELINE config[2]: style features (mean/std + Gram upper triangles of the style taps) of synthetic eyes for the
-    iris classifier, image list sharded contiguously over the ranks, rows all-gathered over NCCL."""
+    iris classifier, image list sharded contiguously over the ranks, rows exchanged over NVLink (sharding.PeerRows)."""
     import torch
     import torch.distributed as dist
 
@@ -408,7 +408,7 @@ def feature_leg(dev, vgg, taps5, n_per_gpu, world, batch=32):
            "value": rate, "unit": "images/s", "n_images": n_total, "feature_dim": int(rows.shape[1]),
            "all_gather_bytes": int(rows.numel() * 4), "flops_per_image": fl,
            "model_tflops_per_gpu": rate * fl / 1e12 / world,
-           "note": "host (pinned) -> device copies of the frames inside the timed region; rows all-gathered over NCCL"}
+           "note": "host (pinned) -> device copies of the frames inside the timed region; rows pushed into every rank over NVLink peer memory (copy engines; NCCL all-gather fallback)"}
     del rows
     torch.cuda.empty_cache()
     return out
