@@ -431,7 +431,7 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int e = 0; e < 32; ++e) bias_r[e] = p.bias != nullptr ? __ldg(p.bias + n + e) : 0.f;
     uint32_t g = 0, at = 0;   // running output-strip / activation-strip counters
     bool f_ready = false;     // slot_full of strip g already seen (probed while the previous strip was in flight)
-    long long et[2] = {0, 0};
+    long long et[6] = {0, 0, 0, 0, 0, 0};
     long long estrips = 0;
     const bool eprof = (p.dbg & 8) && blockIdx.x == 0 && leader;
     SweepWalk walk(p);
@@ -453,6 +453,8 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + slot * 64 + n + (static_cast<uint32_t>(q * 32) << 16), v);
         tmem_ld_wait();
+        long long e2 = 0, e3 = 0, e4 = 0;
+        if (eprof) e2 = clock64();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&slot_empty[slot]);   // accumulator read: the ring slot goes back to the MMA warp
@@ -524,9 +526,11 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           *reinterpret_cast<uint4*>(rowp + chunk * 16) = o;
         }
         fence_proxy_async_smem();
+        if (eprof) e3 = clock64();
         // the other staging slot is rewritten by the next strip: the TMA stores that read it must be done with it
         if (leader) tma_store_wait_read<0>();
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (eprof) e4 = clock64();
         if (leader && !p.skip_out) {
           tma_store_4d(&tmO, stg, 0, J.u0, vo, J.b);
           tma_store_commit();
@@ -572,13 +576,14 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_store_commit();
           }
         }
-        if (eprof) { et[0] += e1 - e0; et[1] += clock64() - e1; ++estrips; }
+        if (eprof) { et[0] += e1 - e0; et[1] += clock64() - e1; et[2] += e2 - e1; et[3] += e3 - e2; et[4] += e4 - e3; ++estrips; }
       }
     }
     if (leader) tma_store_wait_all<0>();
     if (eprof && estrips > 0)
-      printf("sweep epilogue leader, %lld strips: slot_full wait %lld, drain + math + stage + store %lld cycles per strip\n", estrips,
-             et[0] / estrips, et[1] / estrips);
+      printf("sweep epilogue leader, %lld strips: slot_full wait %lld, drain + math + stage + store %lld (tmem_ld %lld, probe + math + staging %lld, "
+             "store-read wait + barrier %lld) cycles per strip\n", estrips, et[0] / estrips, et[1] / estrips, et[2] / estrips, et[3] / estrips,
+             et[4] / estrips);
     tc_fence_before();
   }
   __syncthreads();

@@ -790,3 +790,49 @@ def test_cpu_device_is_refused(mods):
     with pytest.raises(Exception):
         mods["pipelines"].nst(rand_img(1, (1, 3, 32, 32)), rand_img(2, (1, 3, 32, 32)), vgg=mods["vgg"],
                               use_tqdm=False, device="cpu")
+
+
+def test_lean_forward_and_pool_routing_bytes(mods):
+    """ISX_FWD_LEAN: pre-pool ReLU outputs that are not taps are not stored, the max-pool backward runs through the routing
+    bytes the fused conv epilogues emit.  Style features, the autograd gradient and one closure evaluation must be bit-identical
+    to the path that stores every activation and re-reads it in the backward (option pool_idx = 0), even when the workspace
+    holds poison where the skipped activations would be."""
+    import ctypes
+
+    E, lib = mods["engine"], mods["lib"]
+    dev = torch.device("cuda:0")
+    net = iris_b200_vgg(mods, content=["relu4_2"], style=["relu1_1", "relu2_1", "relu3_1", "relu4_1"])
+    B, H, W = 2, 96, 80
+    x = rand_img(301, (B, 3, H, W)).to(dev)
+    res = {}
+    for mode in ("stored", "lean"):
+        assert lib.load().isx_set_option(b"pool_idx", 0 if mode == "stored" else 1) == 0
+        eng = E.NstEngine(net.packed(dev), B, H, W, 3, net.content_convs, net.style_convs, style_mode=0, c_weight=1.0, s_weight=1e6)
+        eng.workspace.view(torch.int16).fill_(0x7fc0)        # bf16 NaN everywhere: a read of a skipped activation shows
+        eng.forward(x, lean=(mode == "lean"))
+        feats = torch.empty(B, 2 * 960 + sum(c * (c + 1) // 2 for c in (64, 128, 256, 512)), device=dev)
+        eng.style_features(feats)
+        gin = {t: torch.ones_like(eng.tap_view(t)) * 0.01 for t in net.style_convs}   # autograd-style backward from the taps
+        g1 = torch.empty(B, 3, H, W, device=dev)
+        eng.backward(gin, None, g1)
+        # one closure evaluation (always lean inside isx_nst_eval when pool_idx = 1)
+        eng.set_content_targets([eng.tap(i) for i in net.content_convs])
+        eng.set_gram_targets([E.gram_of(eng.tap(i)) * 0.5 for i in net.style_convs])
+        eng.workspace.view(torch.int16).fill_(0x7fc0)
+        g2 = torch.empty(B, 3, H, W, device=dev)
+        eng.eval(x, g2)
+        torch.cuda.synchronize()
+        res[mode] = (feats.clone(), g1.clone(), g2.clone(), eng.loss_s.clone())
+    assert lib.load().isx_set_option(b"pool_idx", 1) == 0
+    for a, b, what in zip(res["stored"], res["lean"], ("style features", "autograd gradient", "closure gradient", "style loss")):
+        assert bool(torch.isfinite(b).all()), what
+        if what == "style loss":   # a double accumulated with atomics over several blocks: the order is not fixed
+            assert torch.allclose(a, b, rtol=1e-12, atol=0.0), what
+        else:
+            assert torch.equal(a, b), what
+
+
+def iris_b200_vgg(mods, content, style):
+    import iris_b200
+
+    return iris_b200.VGG19(content_layers=content, style_layers=style, weights=mods["weights"])
