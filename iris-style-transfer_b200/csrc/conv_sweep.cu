@@ -43,6 +43,7 @@ static constexpr int kSwPatch = 17 * 1024;    // one strip patch: 130 rows x 128
 static constexpr int kSwPatchBytes = 130 * 128;
 static constexpr int kSwTile = 128 * 128;     // a 128-row x 64-channel bf16 tile
 static constexpr int kSwWBytes = 9 * 64 * 128;  // nine 64 x 64 weight slabs
+static constexpr int kSwMaxCtas = 160;          // persistent CTAs (one per SM; B200: 148)
 
 struct SweepParams {
   int B, H, W;
@@ -50,6 +51,11 @@ struct SweepParams {
   int u_is_y;          // 1: strips run along y (u = y, v = x); 0: along x
   int u_tiles;         // strip positions per image
   long total_cols;     // B * u_tiles * V output strips in all
+  // cut points of the CTAs' shares, computed by the host: share c = [cut c, cut c+1), a cut = (image, strip position, even v).
+  // Kernel PARAMETERS on purpose: loop bounds read from the constant bank with a uniform index keep the whole issue loop in
+  // uniform registers (with bounds derived by 64-bit divisions in the kernel, ptxas keeps the descriptor words in vector
+  // registers and wraps every tcgen05.mma in two more instructions).
+  int cut_b[kSwMaxCtas + 1], cut_t[kSwMaxCtas + 1], cut_v[kSwMaxCtas + 1];
   int patch_slots;
   int relu, fuse_pool, use_mask, use_gram, skip_out;
   const float* bias;
@@ -85,30 +91,27 @@ struct SweepJob {
   int b, u0, vs, ve, vin0, vin1;
 };
 struct SweepWalk {
-  long f, f_end;
-  int V, u_tiles;
-  __device__ static long cut(const SweepParams& p, long k, long G) {
-    if (k >= G) return p.total_cols;
-    long f = k * p.total_cols / G;
-    const long sw = f / p.V;
-    const long v = (f - sw * p.V) & ~1L;
-    return sw * p.V + v;
-  }
+  int b, t, v, b_end, t_end, v_end, V, u_tiles;
   __device__ SweepWalk(const SweepParams& p) : V(p.V), u_tiles(p.u_tiles) {
-    f = cut(p, blockIdx.x, gridDim.x);
-    f_end = cut(p, blockIdx.x + 1, gridDim.x);
+    const int c = blockIdx.x;
+    b = p.cut_b[c]; t = p.cut_t[c]; v = p.cut_v[c];
+    b_end = p.cut_b[c + 1]; t_end = p.cut_t[c + 1]; v_end = p.cut_v[c + 1];
   }
   __device__ bool next(SweepJob& J) {
-    if (f >= f_end) return false;
-    const long sw = f / V;
-    J.vs = static_cast<int>(f - sw * V);
-    const long left = f_end - f;
-    J.ve = static_cast<int>(left < V - J.vs ? J.vs + left : V) - 1;
-    J.b = static_cast<int>(sw / u_tiles);
-    J.u0 = static_cast<int>(sw - static_cast<long>(J.b) * u_tiles) * 128;
+    const bool last = b == b_end && t == t_end;
+    if (last && v >= v_end) return false;
+    J.vs = v;
+    J.ve = (last ? v_end : V) - 1;
+    J.b = b;
+    J.u0 = t * 128;
     J.vin0 = max(J.vs - 1, 0);          // first / last input strip that contributes to the run
     J.vin1 = min(J.ve + 1, V - 1);
-    f += J.ve - J.vs + 1;
+    if (last) {
+      v = v_end;
+    } else {
+      v = 0;
+      if (++t == u_tiles) { t = 0; ++b; }
+    }
     return true;
   }
 };
@@ -117,8 +120,10 @@ struct SweepWalk {
 // ring slot S: every TMEM address, instruction descriptor and accumulate flag is a compile-time constant, the shared-memory
 // descriptors are the strip's base words plus immediates.  Twelve (ku, k) steps; the window (S, S+1, S+2) is one N = 192 MMA
 // unless it wraps around the ring (S = 6, 7: two MMAs); the first step gives the new slot j = 2 its own MMA with accumulate = 0.
+// uz: a runtime value that is always zero, derived from a kernel parameter -- added to the constant TMEM addresses so that
+// they are formed on the uniform datapath (a literal goes through a vector register and an R2UR per MMA).
 template <int S, bool SMALL = false>
-__device__ __forceinline__ void sweep_interior(uint32_t a_lo, uint32_t w_lo, uint32_t hi) {
+__device__ __forceinline__ void sweep_interior(uint32_t a_lo, uint32_t w_lo, uint32_t hi, uint32_t uz) {
   constexpr uint32_t I64 = umma_idesc_bf16(128, SMALL ? 16 : 64, false, false);
   constexpr uint32_t I128 = umma_idesc_bf16(128, SMALL ? 16 : 128, false, false);
   constexpr uint32_t I192 = umma_idesc_bf16(128, SMALL ? 16 : 192, false, false);
@@ -131,20 +136,20 @@ __device__ __forceinline__ void sweep_interior(uint32_t a_lo, uint32_t w_lo, uin
       const uint32_t b = w_lo + ((ku * 3 * 8192 + k * 32) >> 4);
       if (ku == 0 && k == 0) {
         if (S <= 6) {
-          umma_bf16_lohi(S * 64, a, hi, b, hi, I128, 1u);
+          umma_bf16_lohi(S * 64 + uz, a, hi, b, hi, I128, 1u);
         } else {
-          umma_bf16_lohi(448, a, hi, b, hi, I64, 1u);
-          umma_bf16_lohi(0, a, hi, b + J1, hi, I64, 1u);
+          umma_bf16_lohi(448 + uz, a, hi, b, hi, I64, 1u);
+          umma_bf16_lohi(uz, a, hi, b + J1, hi, I64, 1u);
         }
-        umma_bf16_lohi(((S + 2) & 7) * 64, a, hi, b + J2, hi, I64, 0u);
+        umma_bf16_lohi(((S + 2) & 7) * 64 + uz, a, hi, b + J2, hi, I64, 0u);
       } else if (S <= 5) {
-        umma_bf16_lohi(S * 64, a, hi, b, hi, I192, 1u);
+        umma_bf16_lohi(S * 64 + uz, a, hi, b, hi, I192, 1u);
       } else if (S == 6) {
-        umma_bf16_lohi(384, a, hi, b, hi, I128, 1u);
-        umma_bf16_lohi(0, a, hi, b + J2, hi, I64, 1u);
+        umma_bf16_lohi(384 + uz, a, hi, b, hi, I128, 1u);
+        umma_bf16_lohi(uz, a, hi, b + J2, hi, I64, 1u);
       } else {
-        umma_bf16_lohi(448, a, hi, b, hi, I64, 1u);
-        umma_bf16_lohi(0, a, hi, b + J1, hi, I128, 1u);
+        umma_bf16_lohi(448 + uz, a, hi, b, hi, I64, 1u);
+        umma_bf16_lohi(uz, a, hi, b + J1, hi, I128, 1u);
       }
     }
   }
@@ -186,6 +191,44 @@ __device__ __forceinline__ void sweep_gram(uint32_t a2, uint32_t b2, uint32_t hi
 #pragma unroll
   for (int k = 0; k < 4; ++k) umma_bf16_lohi(S * 64, a2 + 2 * k, hi, b2 + 2 * k, hi, I64, 1u);
 }
+// State of the MMA-issuing thread that survives from strip to strip.
+struct SweepIssue {
+  uint32_t ps, pph;        // patch ring slot / phase
+  uint32_t as, aph;        // activation ring slot / phase (fused Gram backward)
+  uint32_t a_lo;           // descriptor low word of patch slot ps
+  bool p_ready, s_ready;   // probes issued during the previous strip: next patch landed / next first-touch slot drained
+  uint32_t s_probed;       // running number of the output strip whose slot_empty was probed
+};
+// One interior strip whose output j = 0 sits in ring slot S, inside a run of eight strips that starts ring-aligned (S = 0):
+// every barrier index, TMEM address and instruction descriptor is a compile-time constant; q = parity bit of the ring round.
+template <int S>
+__device__ __forceinline__ void sweep_fast_strip(SweepIssue& m, uint32_t q, uint32_t g_first, int PS, uint32_t a_lo0, uint32_t w_lo,
+                                                 uint32_t hi, uint64_t* patch_full, uint64_t* patch_empty, uint64_t* slot_full,
+                                                 uint64_t* slot_empty, uint64_t* act_full, bool use_gram, uint32_t act_lo0, uint32_t d_lo) {
+  // first touch of output j = 2 (running number g_first + S + 2)
+  if (!(m.s_ready && m.s_probed == g_first + S + 2)) mbar_wait(&slot_empty[(S + 2) & 7], q ^ (S >= 6 ? 1u : 0u) ^ 1u);
+  if (!m.p_ready) mbar_wait(&patch_full[m.ps], m.pph);
+  tc_fence_after();
+  {
+    const uint32_t ps_n = m.ps + 1 == static_cast<uint32_t>(PS) ? 0 : m.ps + 1;
+    m.p_ready = mbar_try_wait(&patch_full[ps_n], ps_n == 0 ? m.pph ^ 1 : m.pph);
+    m.s_probed = g_first + S + 3;
+    m.s_ready = mbar_try_wait(&slot_empty[(S + 3) & 7], q ^ (S >= 5 ? 1u : 0u) ^ 1u);
+  }
+  sweep_interior<S>(m.a_lo, w_lo, hi, 0u);
+  umma_commit(&patch_empty[m.ps]);
+  m.a_lo += kSwPatch >> 4;
+  if (++m.ps == static_cast<uint32_t>(PS)) { m.ps = 0; m.pph ^= 1; m.a_lo = a_lo0; }
+  if (use_gram) {  // output j = 0 is complete: + act . D_b
+    mbar_wait(&act_full[m.as], m.aph);
+    tc_fence_after();
+    sweep_gram<S>(act_lo0 + m.as * (kSwTile >> 4), d_lo, hi);
+    m.as ^= 1;
+    if (m.as == 0) m.aph ^= 1;
+  }
+  umma_commit(&slot_full[S]);
+}
+
 #define ISX_SWEEP_SWITCH(slot, CALL)                 \
   switch (slot) {                                    \
     case 0: CALL(0); break; case 1: CALL(1); break;  \
@@ -302,12 +345,14 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t a_lo0 = static_cast<uint32_t>(da0);
       const uint32_t act_lo0 = static_cast<uint32_t>(umma_desc_sw128(smem_u32(smem + L.act), 16, 1024));
       const uint32_t d_lo0 = static_cast<uint32_t>(umma_desc_sw128(smem_u32(smem + L.d), 16, 1024));
-      uint32_t ps = 0, pph = 0, as = 0, aph = 0, ds = 0, dph = 0, a_lo = a_lo0;
+      const uint32_t uz = p.B < 0 ? 64u : 0u;   // always 0, but only the hardware knows
+      uint32_t ps = 0, pph = 0, as = 0, aph = 0, a_lo = a_lo0;
+      bool p_ready = false, s_ready = false;
+      uint32_t s_probed = 0xffffffffu;
+      uint32_t ds = 0, dph = 0;
       uint32_t g0 = 0;           // running number of the job's first output strip
       // An mbarrier probe costs 150-270 cycles even when its phase completed long ago: the probes of the NEXT strip's
       // barriers (its patch, the ring slot it touches first) are issued before this strip's MMAs and consumed afterwards.
-      bool p_ready = false, s_ready = false;
-      uint32_t s_probed = 0xffffffffu;   // running number of the output strip whose slot_empty was probed
       long long tt[4] = {0, 0, 0, 0};
       long long nstrips = 0;
       const bool prof = (p.dbg & 8) && blockIdx.x == 0;
@@ -320,6 +365,40 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int ja = max(0, J.vs - vin + 1), jb = min(2, J.ve - vin + 1);   // valid outputs vo = vin - 1 + j
           const uint32_t gj0 = g0 + static_cast<uint32_t>(vin - 1 - J.vs);      // running number of output j = 0 (may be "-1")
           const bool first_in = vin == J.vin0;
+          // steady state: eight interior strips in a row, starting ring-aligned -> straight-line code with constant slots
+          if ((gj0 & 7) == 0 && !first_in && vin - 1 >= J.vs && vin + 8 <= J.ve && p.dbg == 0) {
+            const uint32_t q = (gj0 >> 3) & 1;
+            const uint32_t d_lo = d_lo0 + ds * (8192 >> 4);
+#define ISX_SWEEP_FAST(S_)                                                                                                   \
+  {                                                                                                                          \
+    if (!(s_ready && s_probed == gj0 + S_ + 2)) mbar_wait(&slot_empty[(S_ + 2) & 7], q ^ (S_ >= 6 ? 1u : 0u) ^ 1u);           \
+    if (!p_ready) mbar_wait(&patch_full[ps], pph);                                                                           \
+    tc_fence_after();                                                                                                        \
+    {                                                                                                                        \
+      const uint32_t ps_n = ps + 1 == static_cast<uint32_t>(PS) ? 0 : ps + 1;                                                \
+      p_ready = mbar_try_wait(&patch_full[ps_n], ps_n == 0 ? pph ^ 1 : pph);                                                 \
+      s_probed = gj0 + S_ + 3;                                                                                               \
+      s_ready = mbar_try_wait(&slot_empty[(S_ + 3) & 7], q ^ (S_ >= 5 ? 1u : 0u) ^ 1u);                                       \
+    }                                                                                                                        \
+    sweep_interior<S_>(a_lo, w_lo, hi, uz);                                                                                      \
+    umma_commit(&patch_empty[ps]);                                                                                           \
+    a_lo += kSwPatch >> 4;                                                                                                   \
+    if (++ps == static_cast<uint32_t>(PS)) { ps = 0; pph ^= 1; a_lo = a_lo0; }                                               \
+    if (p.use_gram) {                                                                                                        \
+      mbar_wait(&act_full[as], aph);                                                                                         \
+      tc_fence_after();                                                                                                      \
+      sweep_gram<S_>(act_lo0 + as * (kSwTile >> 4), d_lo, hi);                                                               \
+      as ^= 1;                                                                                                               \
+      if (as == 0) aph ^= 1;                                                                                                 \
+    }                                                                                                                        \
+    umma_commit(&slot_full[S_]);                                                                                             \
+  }
+            ISX_SWEEP_FAST(0); ISX_SWEEP_FAST(1); ISX_SWEEP_FAST(2); ISX_SWEEP_FAST(3);
+            ISX_SWEEP_FAST(4); ISX_SWEEP_FAST(5); ISX_SWEEP_FAST(6); ISX_SWEEP_FAST(7);
+#undef ISX_SWEEP_FAST
+            vin += 7;
+            continue;
+          }
           const bool interior = !first_in && ja == 0 && jb == 2;
           long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
           if (prof) c0 = clock64();
@@ -340,13 +419,13 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (prof) c2 = clock64();
           if (no_mma) {
           } else if (interior && (p.dbg & 4)) {   // diagnostics: the same instruction stream with N = 16 (wrong results)
-#define ISX_SWEEP_CALL(S_) sweep_interior<S_, true>(a_lo, w_lo, hi)
+#define ISX_SWEEP_CALL(S_) sweep_interior<S_, true>(a_lo, w_lo, hi, uz)
             ISX_SWEEP_SWITCH(gj0 & 7, ISX_SWEEP_CALL)
 #undef ISX_SWEEP_CALL
           } else if (interior && (p.dbg & 16)) {
             sweep_interior_rt(a_lo, w_lo, hi, gj0 & 7);
           } else if (interior) {
-#define ISX_SWEEP_CALL(S_) sweep_interior<S_>(a_lo, w_lo, hi)
+#define ISX_SWEEP_CALL(S_) sweep_interior<S_>(a_lo, w_lo, hi, uz)
             ISX_SWEEP_SWITCH(gj0 & 7, ISX_SWEEP_CALL)
 #undef ISX_SWEEP_CALL
           } else {
@@ -667,7 +746,15 @@ int conv_sweep(const ConvArgs& a, cudaStream_t stream) {
   }
   ISX_CHECK_CUDA(cudaFuncSetAttribute(conv_sweep64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   // every CTA gets an equal contiguous share of the output strips; tiny launches: at least ~16 strips per CTA
-  const long grid = std::max<long>(1, std::min<long>(p.total_cols / 16, kNumSMs));
+  const long grid = std::max<long>(1, std::min<long>(p.total_cols / 16, std::min<long>(kNumSMs, kSwMaxCtas)));
+  for (long k = 0; k <= grid; ++k) {
+    long f = k >= grid ? p.total_cols : k * p.total_cols / grid;
+    long sw = f / p.V;
+    const long v = k >= grid ? 0 : ((f - sw * p.V) & ~1L);    // even v: the pooling pairs of strips stay in one share
+    p.cut_b[k] = static_cast<int>(sw / p.u_tiles);
+    p.cut_t[k] = static_cast<int>(sw % p.u_tiles);
+    p.cut_v[k] = static_cast<int>(v);
+  }
   isx_prof_begin(ISX_PROF_CONV, 2.0 * (9 * 64 + (p.use_gram ? 64 : 0)) * 64 * static_cast<double>(a.B) * a.H * a.W, stream);
   conv_sweep64_kernel<<<(unsigned)grid, kSwThreads, smem_bytes, stream>>>(tmA, tmW, tmO, tmM, tmD, tmP, p);
   isx_prof_end(ISX_PROF_CONV, stream);
