@@ -357,9 +357,9 @@ unsigned long long isx_launch_count(void);
  * free (<= 22) so that one TMEM-free streaming CTA of another stream -- the L-BFGS history passes -- can be resident beside
  * them; "pool_idx" (1): the NST driver routes the max-pool + ReLU backward through the index bytes the fused conv epilogues
  * emit and does not store untapped pre-pool activations (0: stores them and re-reads them in the backward); "head_ctas" (5):
- * resident CTAs per SM the conv1_1 head is compiled for (5 or 8); "sweep64" (0): experimental tap-stacked
- * sweep kernel for the 64 -> 64 layers (conv_sweep.cu; 0 never, 1 when its 128-pixel strips fit the image, 2 on every
- * applicable call), "sweep_dbg": its diagnostics.  Unknown names return non-zero. */
+ * resident CTAs per SM the conv1_1 head is compiled for (5 or 8); "sweep64" (1): tap-stacked sweep kernel for
+ * the 64 -> 64 layers (conv_sweep.cu; 0 never, 1 the forward launches whose 128-pixel strips fit the image, 2 every applicable
+ * call), "sweep_dbg": its diagnostics.  Unknown names return non-zero. */
 int isx_set_option(const char* name, int value);   /* on the calling thread's current context */
 int isx_get_option(const char* name, int* value);
 int isx_prof_enable(int on);

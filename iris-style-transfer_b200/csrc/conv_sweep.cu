@@ -23,13 +23,15 @@
 //     shared memory and stored by TMA; fused 2x2 max-pool (two consecutive strips) with the routing bytes of its backward;
 //     the dgrad's ReLU-mask activation strip doubles as the A operand of the fused Gram backward (x D_b, N = 64).
 //
-// STATUS (round 2, profiles/r02_conv_sweep_experiment.txt): correct (tests/test_gpu_kernels.py::test_conv_sweep_*), but NOT
-// faster than conv_c64 on the B200, so it is opt-in (option "sweep64").  clock64 timeline of one CTA at 64 x 640 x 400: the
-// issuing thread needs ~80 cycles per tcgen05.mma (14 SASS instructions each: ELECT / R2UR.BROADCAST waterfall around the
-// descriptor words) x 16 MMAs per strip (12 + the first-touch and ring-wrap splits) + ~650 cycles of barrier probes and
-// commits = 1 950 cycles per 128 pixels against 1 152 of tensor work; and with the MMAs running the epilogue slows from 1 100 to
-// 2 000 cycles per strip -- operands (120 KB per strip), patch, staging tile and TMA store together come close to the 128 B/clk
-// of shared-memory bandwidth.  Forward 17.2-22.9 us/image against 17.9-18.4 for conv_c64, dgrad 27 against 21.
+// STATUS (round 2, profiles/r02_conv_sweep_experiment.txt, profiles/r02_ab_sweep64.txt): the FORWARD launches run here by default
+// (option "sweep64" = 1): 14.0-14.8 us per 640x400 image against 17.5-18.1 for conv_c64 (1 340 TFLOP/s), 15.7-17.4 against
+// 18.6-19.7 with the fused pool; feature extraction 7 759 -> 8 017 images/s.  The dgrad launches (ReLU-mask strip, fused Gram block)
+// are still slower than conv_c64 (25-28 against 21-24 us) and stay there.  Two things made the forward win: (i) the cut points of
+// the CTAs' shares are KERNEL PARAMETERS -- with loop bounds that come out of in-kernel divisions ptxas keeps the descriptor words
+// in vector registers and wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST loop (14 SASS instructions per MMA, ~80 cycles);
+// with uniform bounds and the eight-strip straight-line steady state it is 10 --, (ii) probes of the next strip's barriers are
+// issued before the current strip's MMAs.  What bounds it now is shared-memory bandwidth: operands (120 KB per strip), patch,
+// staging tile and TMA store come to ~190 KB per 128 pixels at 128 B/clk.
 #include <algorithm>
 
 #include "isx_common.cuh"

@@ -172,8 +172,10 @@ def c64_forced(isx):
     tile per SM, which the default heuristic leaves to the generic kernel)."""
     lib = isx.load()
     assert lib.isx_set_option(b"c64", 2) == 0
+    assert lib.isx_set_option(b"sweep64", 0) == 0
     yield
     assert lib.isx_set_option(b"c64", 1) == 0
+    assert lib.isx_set_option(b"sweep64", 1) == 0
 
 
 @pytest.mark.parametrize("shape", C64_SHAPES)
@@ -214,7 +216,7 @@ def sweep_forced(isx):
     lib = isx.load()
     assert lib.isx_set_option(b"sweep64", 2) == 0
     yield
-    assert lib.isx_set_option(b"sweep64", 0) == 0
+    assert lib.isx_set_option(b"sweep64", 1) == 0
 
 
 @pytest.mark.parametrize("shape", SWEEP_SHAPES)
@@ -247,7 +249,7 @@ def test_conv_sweep_matches_c64_bitwise(isx):
         o = torch.empty(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
         isx.call("isx_conv3x3_bias_relu_fwd", x, wf, bias, o, B, H, W, 64, 64, 1, 0, isx.stream_ptr())
         outs.append(o)
-    assert lib.isx_set_option(b"sweep64", 0) == 0
+    assert lib.isx_set_option(b"sweep64", 1) == 0
     torch.cuda.synchronize()
     assert torch.equal(outs[1], outs[2])
     assert_close_bf16(outs[1], outs[0].float(), "sweep vs c64")
@@ -270,9 +272,11 @@ def halo2_forced(isx):
     lib = isx.load()
     assert lib.isx_set_option(b"halo2", 2) == 0
     assert lib.isx_set_option(b"c64", 0) == 0
+    assert lib.isx_set_option(b"sweep64", 0) == 0
     yield
     assert lib.isx_set_option(b"halo2", 1) == 0
     assert lib.isx_set_option(b"c64", 1) == 0
+    assert lib.isx_set_option(b"sweep64", 1) == 0
 
 
 @pytest.mark.parametrize("shape", HALO_SHAPES)
