@@ -77,8 +77,11 @@ __host__ __device__ inline SweepLayout sweep_layout(int patch_slots, int use_mas
   L.w = off; off += kSwWBytes;
   L.d = off; off += use_gram ? 2 * 8192 : 0;
   L.patch = off; off += patch_slots * kSwPatch;
-  L.act = off; off += use_mask ? 2 * kSwTile : 0;
-  L.stg = off; off += 2 * kSwTile;
+  // dgrad: FOUR ReLU-mask strips in flight (with two, the next strip's activation is requested only ~1.5 strip times before it
+  // is needed -- less than a DRAM round trip: the epilogue then waited ~1 400 cycles per strip for it); the result is written
+  // IN PLACE over the mask strip it was computed from, so the dgrad needs no staging tiles
+  L.act = off; off += use_mask ? 4 * kSwTile : 0;
+  L.stg = off; off += use_mask ? 0 : 2 * kSwTile;
   L.pstg = off; off += fuse_pool ? 2 * 8192 : 0;
   L.bars = off; off += 1024;
   L.total = off;
@@ -193,44 +196,6 @@ __device__ __forceinline__ void sweep_gram(uint32_t a2, uint32_t b2, uint32_t hi
 #pragma unroll
   for (int k = 0; k < 4; ++k) umma_bf16_lohi(S * 64, a2 + 2 * k, hi, b2 + 2 * k, hi, I64, 1u);
 }
-// State of the MMA-issuing thread that survives from strip to strip.
-struct SweepIssue {
-  uint32_t ps, pph;        // patch ring slot / phase
-  uint32_t as, aph;        // activation ring slot / phase (fused Gram backward)
-  uint32_t a_lo;           // descriptor low word of patch slot ps
-  bool p_ready, s_ready;   // probes issued during the previous strip: next patch landed / next first-touch slot drained
-  uint32_t s_probed;       // running number of the output strip whose slot_empty was probed
-};
-// One interior strip whose output j = 0 sits in ring slot S, inside a run of eight strips that starts ring-aligned (S = 0):
-// every barrier index, TMEM address and instruction descriptor is a compile-time constant; q = parity bit of the ring round.
-template <int S>
-__device__ __forceinline__ void sweep_fast_strip(SweepIssue& m, uint32_t q, uint32_t g_first, int PS, uint32_t a_lo0, uint32_t w_lo,
-                                                 uint32_t hi, uint64_t* patch_full, uint64_t* patch_empty, uint64_t* slot_full,
-                                                 uint64_t* slot_empty, uint64_t* act_full, bool use_gram, uint32_t act_lo0, uint32_t d_lo) {
-  // first touch of output j = 2 (running number g_first + S + 2)
-  if (!(m.s_ready && m.s_probed == g_first + S + 2)) mbar_wait(&slot_empty[(S + 2) & 7], q ^ (S >= 6 ? 1u : 0u) ^ 1u);
-  if (!m.p_ready) mbar_wait(&patch_full[m.ps], m.pph);
-  tc_fence_after();
-  {
-    const uint32_t ps_n = m.ps + 1 == static_cast<uint32_t>(PS) ? 0 : m.ps + 1;
-    m.p_ready = mbar_try_wait(&patch_full[ps_n], ps_n == 0 ? m.pph ^ 1 : m.pph);
-    m.s_probed = g_first + S + 3;
-    m.s_ready = mbar_try_wait(&slot_empty[(S + 3) & 7], q ^ (S >= 5 ? 1u : 0u) ^ 1u);
-  }
-  sweep_interior<S>(m.a_lo, w_lo, hi, 0u);
-  umma_commit(&patch_empty[m.ps]);
-  m.a_lo += kSwPatch >> 4;
-  if (++m.ps == static_cast<uint32_t>(PS)) { m.ps = 0; m.pph ^= 1; m.a_lo = a_lo0; }
-  if (use_gram) {  // output j = 0 is complete: + act . D_b
-    mbar_wait(&act_full[m.as], m.aph);
-    tc_fence_after();
-    sweep_gram<S>(act_lo0 + m.as * (kSwTile >> 4), d_lo, hi);
-    m.as ^= 1;
-    if (m.as == 0) m.aph ^= 1;
-  }
-  umma_commit(&slot_full[S]);
-}
-
 #define ISX_SWEEP_SWITCH(slot, CALL)                 \
   switch (slot) {                                    \
     case 0: CALL(0); break; case 1: CALL(1); break;  \
@@ -251,13 +216,13 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* w_full = bars;               // [1]
   uint64_t* patch_full = bars + 1;       // [8]
   uint64_t* patch_empty = bars + 9;      // [8]
-  uint64_t* act_full = bars + 17;        // [2]
-  uint64_t* act_empty = bars + 19;       // [2]
-  uint64_t* d_full = bars + 21;          // [2]
-  uint64_t* d_empty = bars + 23;         // [2]
-  uint64_t* slot_full = bars + 25;       // [8]
-  uint64_t* slot_empty = bars + 33;      // [8]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 41);
+  uint64_t* act_full = bars + 17;        // [4]
+  uint64_t* act_empty = bars + 21;       // [4]
+  uint64_t* d_full = bars + 25;          // [2]
+  uint64_t* d_empty = bars + 27;         // [2]
+  uint64_t* slot_full = bars + 29;       // [8]
+  uint64_t* slot_empty = bars + 37;      // [8]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 45);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -276,9 +241,11 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&slot_full[i], 1);
       mbar_init(&slot_empty[i], 8);   // one arrival per epilogue warp
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&act_full[i], 1);
-      mbar_init(&act_empty[i], 8);
+      mbar_init(&act_empty[i], 1);    // the epilogue leader, once the TMA store of the result written over the strip has read it
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&d_full[i], 1);
       mbar_init(&d_empty[i], 1);
     }
@@ -302,12 +269,15 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tma_load_2d(smem + L.w + (ku * 3 + (2 - ks)) * 8192, &tmW, w_full, 0, (ky * 3 + kx) * 64);
         }
       uint32_t ps = 0, pph = 0, as = 0, aph = 0, ds = 0, dph = 0;
+      const bool pprof = (p.dbg & 8) && blockIdx.x == 0;
+      long long pw_patch = 0, pw_act = 0, pn = 0;
       auto load_act = [&](int u0, int vo, int b) {
+        const long long t0 = pprof ? clock64() : 0;
         mbar_wait(&act_empty[as], aph ^ 1);
+        if (pprof) pw_act += clock64() - t0;
         mbar_arrive_expect_tx(&act_full[as], kSwTile);
         tma_load_4d(smem + L.act + as * kSwTile, &tmM, &act_full[as], 0, u0, vo, b);
-        as ^= 1;
-        if (as == 0) aph ^= 1;
+        if (++as == 4) { as = 0; aph ^= 1; }
       };
       SweepWalk walk(p);
       SweepJob J;
@@ -320,7 +290,9 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (ds == 0) dph ^= 1;
         }
         for (int vin = J.vin0; vin <= J.vin1; ++vin) {
+          const long long t0 = pprof ? clock64() : 0;
           mbar_wait(&patch_empty[ps], pph ^ 1);
+          if (pprof) { pw_patch += clock64() - t0; ++pn; }
           mbar_arrive_expect_tx(&patch_full[ps], kSwPatchBytes);
           tma_load_4d(smem + L.patch + ps * kSwPatch, &tmA, &patch_full[ps], 0, J.u0 - 1, vin, J.b);
           if (++ps == static_cast<uint32_t>(PS)) { ps = 0; pph ^= 1; }
@@ -330,6 +302,7 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
+      if (pprof && pn > 0) printf("sweep producer, %lld strips: patch_empty wait %lld, act_empty wait %lld cycles per strip\n", pn, pw_patch / pn, pw_act / pn);
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ===========================================
@@ -356,7 +329,7 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // An mbarrier probe costs 150-270 cycles even when its phase completed long ago: the probes of the NEXT strip's
       // barriers (its patch, the ring slot it touches first) are issued before this strip's MMAs and consumed afterwards.
       long long tt[4] = {0, 0, 0, 0};
-      long long nstrips = 0;
+      long long nstrips = 0, tfast = 0, nfast = 0;
       const bool prof = (p.dbg & 8) && blockIdx.x == 0;
       const bool no_mma = (p.dbg & 1) != 0;
       SweepWalk walk(p);
@@ -368,7 +341,8 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t gj0 = g0 + static_cast<uint32_t>(vin - 1 - J.vs);      // running number of output j = 0 (may be "-1")
           const bool first_in = vin == J.vin0;
           // steady state: eight interior strips in a row, starting ring-aligned -> straight-line code with constant slots
-          if ((gj0 & 7) == 0 && !first_in && vin - 1 >= J.vs && vin + 8 <= J.ve && p.dbg == 0) {
+          if ((gj0 & 7) == 0 && !first_in && vin - 1 >= J.vs && vin + 8 <= J.ve && (p.dbg & ~8) == 0) {
+            const long long cb = prof ? clock64() : 0;
             const uint32_t q = (gj0 >> 3) & 1;
             const uint32_t d_lo = d_lo0 + ds * (8192 >> 4);
 #define ISX_SWEEP_FAST(S_)                                                                                                   \
@@ -390,14 +364,14 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&act_full[as], aph);                                                                                         \
       tc_fence_after();                                                                                                      \
       sweep_gram<S_>(act_lo0 + as * (kSwTile >> 4), d_lo, hi);                                                               \
-      as ^= 1;                                                                                                               \
-      if (as == 0) aph ^= 1;                                                                                                 \
+      if (++as == 4) { as = 0; aph ^= 1; }                                                                                   \
     }                                                                                                                        \
     umma_commit(&slot_full[S_]);                                                                                             \
   }
             ISX_SWEEP_FAST(0); ISX_SWEEP_FAST(1); ISX_SWEEP_FAST(2); ISX_SWEEP_FAST(3);
             ISX_SWEEP_FAST(4); ISX_SWEEP_FAST(5); ISX_SWEEP_FAST(6); ISX_SWEEP_FAST(7);
 #undef ISX_SWEEP_FAST
+            if (prof) { tfast += clock64() - cb; nfast += 8; }
             vin += 7;
             continue;
           }
@@ -480,8 +454,7 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 ISX_SWEEP_SWITCH(g & 7, ISX_SWEEP_CALL)
 #undef ISX_SWEEP_CALL
               }
-              as ^= 1;
-              if (as == 0) aph ^= 1;
+              if (++as == 4) { as = 0; aph ^= 1; }
             }
             umma_commit(&slot_full[g & 7]);
           }
@@ -496,6 +469,7 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         g0 += static_cast<uint32_t>(J.ve - J.vs + 1);
       }
+      if (prof && nfast > 0) printf("sweep MMA thread, fast path: %lld strips, %lld cycles per strip\n", nfast, tfast / nfast);
       if (prof && nstrips > 0)
         printf("sweep MMA thread, %lld strips: slot_empty wait %lld, patch_full wait + probes %lld, issue %lld, commits %lld cycles per strip\n",
                nstrips, tt[0] / nstrips, tt[1] / nstrips, tt[2] / nstrips, tt[3] / nstrips);
@@ -511,6 +485,7 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
     for (int e = 0; e < 32; ++e) bias_r[e] = p.bias != nullptr ? __ldg(p.bias + n + e) : 0.f;
     uint32_t g = 0, at = 0;   // running output-strip / activation-strip counters
+    uint32_t act_held = 0xffffffffu;   // leader: mask strip whose in-place result is still being read by its TMA store
     bool f_ready = false;     // slot_full of strip g already seen (probed while the previous strip was in flight)
     long long et[6] = {0, 0, 0, 0, 0, 0};
     long long estrips = 0;
@@ -525,7 +500,8 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int px = p.u_is_y ? vo : u, py = p.u_is_y ? u : vo;
         const size_t pix = valid ? ((static_cast<size_t>(J.b) * p.H + py) * p.W + px) * 64 : 0;
         const uint32_t ss = static_cast<uint32_t>(vo) & 1;   // staging slot: even / odd sweep coordinate
-        uint8_t* stg = smem + L.stg + ss * kSwTile;
+        const uint32_t as = at & 3;                          // dgrad: mask strip of this output, overwritten in place by the result
+        uint8_t* stg = p.use_mask ? smem + L.act + as * kSwTile : smem + L.stg + ss * kSwTile;
         long long e0 = 0, e1 = 0;
         if (eprof) e0 = clock64();
         if (!f_ready) mbar_wait(&slot_full[slot], (g >> 3) & 1);
@@ -542,10 +518,9 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         f_ready = mbar_try_wait(&slot_full[(g + 1) & 7], ((g + 1) >> 3) & 1);   // consumed at the top of the next strip
         if (p.dbg & 2) {
           if (p.use_mask) {
-            const uint32_t as = at & 1;
-            mbar_wait(&act_full[as], (at >> 1) & 1);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&act_empty[as]);
+            mbar_wait(&act_full[as], (at >> 2) & 1);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (leader) mbar_arrive(&act_empty[as]);
             ++at;
           }
           continue;
@@ -564,31 +539,35 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             t = unpack_bf16x2(w4.w); f[e + 6] += t.x; f[e + 7] += t.y;
           }
         }
+        // ReLU mask of the layer below as packed select masks (0xFFFF per bf16 whose activation is > 0): applied to the packed
+        // output words -- one HSETP2 + one AND per two channels instead of two unpacks and two selects
+        uint32_t keep[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) keep[e] = 0xffffffffu;
         if (p.use_mask) {
-          const uint32_t as = at & 1;
-          mbar_wait(&act_full[as], (at >> 1) & 1);
-          const uint8_t* mrow = smem + L.act + as * kSwTile + row * 128;
+          mbar_wait(&act_full[as], (at >> 2) & 1);
+          const uint8_t* mrow = stg + row * 128;   // read before this thread overwrites the same 16-byte chunks below
+          const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
           for (int e = 0; e < 32; e += 8) {
             const int chunk = (hsel * 4 + (e >> 3)) ^ (row & 7);
             const uint4 w4 = *reinterpret_cast<const uint4*>(mrow + chunk * 16);
-            float a[8];
-            float2 t;
-            t = unpack_bf16x2(w4.x); a[0] = t.x; a[1] = t.y;
-            t = unpack_bf16x2(w4.y); a[2] = t.x; a[3] = t.y;
-            t = unpack_bf16x2(w4.z); a[4] = t.x; a[5] = t.y;
-            t = unpack_bf16x2(w4.w); a[6] = t.x; a[7] = t.y;
+            const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) keep[(e >> 1) + i] = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&ww[i]), zero2);
             if (p.aff_a != nullptr && valid) {
+              float a[8];
+              float2 t;
+              t = unpack_bf16x2(w4.x); a[0] = t.x; a[1] = t.y;
+              t = unpack_bf16x2(w4.y); a[2] = t.x; a[3] = t.y;
+              t = unpack_bf16x2(w4.z); a[4] = t.x; a[5] = t.y;
+              t = unpack_bf16x2(w4.w); a[6] = t.x; a[7] = t.y;
               const float* pa = p.aff_a + static_cast<size_t>(J.b) * 64 + n + e;
               const float* pb = p.aff_b + static_cast<size_t>(J.b) * 64 + n + e;
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[e + j] += __ldg(pa + j) + __ldg(pb + j) * a[j];
             }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[e + j] = a[j] > 0.f ? f[e + j] : 0.f;
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&act_empty[as]);
           ++at;
         }
         if (p.relu) {
@@ -599,23 +578,27 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 o;
-          o.x = pack_bf16x2(f[c * 8 + 0], f[c * 8 + 1]);
-          o.y = pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]);
-          o.z = pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]);
-          o.w = pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]);
+          o.x = pack_bf16x2(f[c * 8 + 0], f[c * 8 + 1]) & keep[c * 4 + 0];
+          o.y = pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]) & keep[c * 4 + 1];
+          o.z = pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]) & keep[c * 4 + 2];
+          o.w = pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]) & keep[c * 4 + 3];
           const int chunk = (hsel * 4 + c) ^ (row & 7);
           *reinterpret_cast<uint4*>(rowp + chunk * 16) = o;
         }
         fence_proxy_async_smem();
         if (eprof) e3 = clock64();
         // the other staging slot is rewritten by the next strip: the TMA stores that read it must be done with it
-        if (leader) tma_store_wait_read<0>();
+        if (leader) {
+          tma_store_wait_read<0>();
+          if (act_held != 0xffffffffu) { mbar_arrive(&act_empty[act_held]); act_held = 0xffffffffu; }   // its store has read it
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (eprof) e4 = clock64();
         if (leader && !p.skip_out) {
           tma_store_4d(&tmO, stg, 0, J.u0, vo, J.b);
           tma_store_commit();
         }
+        if (leader && p.use_mask) act_held = as;
         if (p.fuse_pool && (vo & 1)) {
           // 2x2 max-pool of strips vo - 1 (staging slot 0) and vo (slot 1): 64 pooled pixels x 64 channels, 2 items per thread
           const uint8_t* s0 = smem + L.stg;
@@ -660,7 +643,10 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (eprof) { et[0] += e1 - e0; et[1] += clock64() - e1; et[2] += e2 - e1; et[3] += e3 - e2; et[4] += e4 - e3; ++estrips; }
       }
     }
-    if (leader) tma_store_wait_all<0>();
+    if (leader) {
+      tma_store_wait_all<0>();
+      if (act_held != 0xffffffffu) mbar_arrive(&act_empty[act_held]);
+    }
     if (eprof && estrips > 0)
       printf("sweep epilogue leader, %lld strips: slot_full wait %lld, drain + math + stage + store %lld (tmem_ld %lld, probe + math + staging %lld, "
              "store-read wait + barrier %lld) cycles per strip\n", estrips, et[0] / estrips, et[1] / estrips, et[2] / estrips, et[3] / estrips,

@@ -499,11 +499,11 @@ int conv_tc(const ConvArgs& a_in, cudaStream_t stream) {
     // strips are mostly real pixels (the kernel is ~1.5x faster per processed pixel than conv_c64) and every SM gets a few
     // hundred of them (a CTA's share starts and ends with two slower edge strips)
     const long strips = static_cast<long>(a.B) * ((std::max(a.H, a.W) + 127) / 128) * std::min(a.H, a.W);
-    // measured (profiles/r02_conv_sweep_experiment.txt): the FORWARD launches win (14.0 vs 17.5-18.1 us/image plain, 15.7-17.4 vs
-    // 18.6-19.7 with the fused pool); the dgrad launches (ReLU-mask strip, fused Gram block) are still slower than conv_c64
-    const bool forward = a.mask_act == nullptr && a.add_buf == nullptr;
+    // measured (profiles/r02_conv_sweep_experiment.txt), us per 640x400 image: forward 14.0-14.8 against 17.5-18.1 for conv_c64,
+    // with the fused pool 15.7-17.4 against 18.6-19.7, dgrad + mask 19.9-20.1 against 21.5-22.0, dgrad + mask + Gram 21.9-22.2
+    // against 23.5-25.6
     if (isx_ctx()->opt_sweep64 >= 2 ||
-        (forward && conv_sweep_efficiency(a) >= 0.85 && strips >= 64L * kNumSMs && std::min(a.H, a.W) >= 16))
+        (conv_sweep_efficiency(a) >= 0.85 && strips >= 64L * kNumSMs && std::min(a.H, a.W) >= 16))
       return conv_sweep(a, stream);
   }
   if (isx_ctx()->opt_c64 > 0 && a.force_bn == 0 && conv_c64_applicable(a) &&
