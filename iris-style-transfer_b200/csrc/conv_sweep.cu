@@ -322,7 +322,7 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t d_lo0 = static_cast<uint32_t>(umma_desc_sw128(smem_u32(smem + L.d), 16, 1024));
       const uint32_t uz = p.B < 0 ? 64u : 0u;   // always 0, but only the hardware knows
       uint32_t ps = 0, pph = 0, as = 0, aph = 0, a_lo = a_lo0;
-      bool p_ready = false, s_ready = false;
+      bool p_ready = false, s_ready = false, a_ready = false;
       uint32_t s_probed = 0xffffffffu;
       uint32_t ds = 0, dph = 0;
       uint32_t g0 = 0;           // running number of the job's first output strip
@@ -355,13 +355,14 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       p_ready = mbar_try_wait(&patch_full[ps_n], ps_n == 0 ? pph ^ 1 : pph);                                                 \
       s_probed = gj0 + S_ + 3;                                                                                               \
       s_ready = mbar_try_wait(&slot_empty[(S_ + 3) & 7], q ^ (S_ >= 5 ? 1u : 0u) ^ 1u);                                       \
+      if (p.use_gram) a_ready = mbar_try_wait(&act_full[as], aph);                                                           \
     }                                                                                                                        \
     sweep_interior<S_>(a_lo, w_lo, hi, uz);                                                                                      \
     umma_commit(&patch_empty[ps]);                                                                                           \
     a_lo += kSwPatch >> 4;                                                                                                   \
     if (++ps == static_cast<uint32_t>(PS)) { ps = 0; pph ^= 1; a_lo = a_lo0; }                                               \
     if (p.use_gram) {                                                                                                        \
-      mbar_wait(&act_full[as], aph);                                                                                         \
+      if (!a_ready) mbar_wait(&act_full[as], aph);                                                                           \
       tc_fence_after();                                                                                                      \
       sweep_gram<S_>(act_lo0 + as * (kSwTile >> 4), d_lo, hi);                                                               \
       if (++as == 4) { as = 0; aph ^= 1; }                                                                                   \
@@ -487,6 +488,7 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t g = 0, at = 0;   // running output-strip / activation-strip counters
     uint32_t act_held = 0xffffffffu;   // leader: mask strip whose in-place result is still being read by its TMA store
     bool f_ready = false;     // slot_full of strip g already seen (probed while the previous strip was in flight)
+    bool m_ready = false;     // likewise the ReLU-mask strip of strip g (dgrad)
     long long et[6] = {0, 0, 0, 0, 0, 0};
     long long estrips = 0;
     const bool eprof = (p.dbg & 8) && blockIdx.x == 0 && leader;
@@ -516,6 +518,8 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(&slot_empty[slot]);   // accumulator read: the ring slot goes back to the MMA warp
         f_ready = mbar_try_wait(&slot_full[(g + 1) & 7], ((g + 1) >> 3) & 1);   // consumed at the top of the next strip
+        const bool m_now = m_ready;
+        if (p.use_mask) m_ready = mbar_try_wait(&act_full[(at + 1) & 3], ((at + 1) >> 2) & 1);
         if (p.dbg & 2) {
           if (p.use_mask) {
             mbar_wait(&act_full[as], (at >> 2) & 1);
@@ -545,7 +549,7 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int e = 0; e < 16; ++e) keep[e] = 0xffffffffu;
         if (p.use_mask) {
-          mbar_wait(&act_full[as], (at >> 2) & 1);
+          if (!m_now) mbar_wait(&act_full[as], (at >> 2) & 1);
           const uint8_t* mrow = stg + row * 128;   // read before this thread overwrites the same 16-byte chunks below
           const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
