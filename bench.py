@@ -628,7 +628,9 @@ def main():
         tr = json.load(open(os.path.join(ROOT, "profiles", "r02_conv_traffic.json")))
         if tr.get("batch") == B and tr.get("config") == cfgname:
             traffic = tr["dram_bytes_per_conv_launch"]
-            traffic_src = "ncu --set full capture of this command committed as profiles/r02_conv_traffic.json"
+            traffic_src = ("ncu capture of this command (dram__bytes_read.sum + dram__bytes_write.sum per launch, "
+                           "profiles/r02_ncu_launches_bench_b64.csv), averaged over the conv launches of one evaluation: "
+                           "profiles/r02_conv_traffic.json")
     except Exception:
         pass
     conv_n, conv_ms, conv_flops = prof[0], prof[1], prof[2]
