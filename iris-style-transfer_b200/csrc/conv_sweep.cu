@@ -489,6 +489,10 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t act_held = 0xffffffffu;   // leader: mask strip whose in-place result is still being read by its TMA store
     bool f_ready = false;     // slot_full of strip g already seen (probed while the previous strip was in flight)
     bool m_ready = false;     // likewise the ReLU-mask strip of strip g (dgrad)
+    const bool regpool = p.fuse_pool && p.skip_out && !p.use_mask;   // pool in registers, nothing else to store
+    uint32_t prevw[16];       // regpool: the even strip of the current pair, packed bf16x2
+#pragma unroll
+    for (int e = 0; e < 16; ++e) prevw[e] = 0u;
     long long et[6] = {0, 0, 0, 0, 0, 0};
     long long estrips = 0;
     const bool eprof = (p.dbg & 8) && blockIdx.x == 0 && leader;
@@ -577,6 +581,67 @@ conv_sweep64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (p.relu) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) f[e] = fmaxf(f[e], 0.f);
+        }
+        if (regpool) {
+          // Forward with the fused pool and NO full-resolution store (NST evaluation, lean feature forward): the 2x2 windows are
+          // pooled IN REGISTERS.  The two strips of a window are consecutive strips of the same thread (the even one is kept in
+          // prevw), its two rows are the lanes l and l ^ 1 of one warp.  No staging tile, no barrier on even strips, 32 KB less
+          // shared-memory traffic per pair of strips -- the kernel's bound.
+          uint32_t w[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) w[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+          if ((vo & 1) == 0) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) prevw[e] = w[e];
+            if (eprof) { et[0] += e1 - e0; et[1] += clock64() - e1; ++estrips; }
+            continue;
+          }
+          const bool odd = (lane & 1) != 0;   // this lane pools words 8..15 of its 16, the even lane of the pair words 0..7
+          uint32_t r0p[8], r1p[8], r0c[8], r1c[8];   // rows r0 (even lane) / r1 (odd lane) x strips prev / cur, this lane's 8 words
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t my_p = odd ? prevw[8 + i] : prevw[i], send_p = odd ? prevw[i] : prevw[8 + i];
+            const uint32_t my_c = odd ? w[8 + i] : w[i], send_c = odd ? w[i] : w[8 + i];
+            const uint32_t got_p = __shfl_xor_sync(0xffffffffu, send_p, 1);
+            const uint32_t got_c = __shfl_xor_sync(0xffffffffu, send_c, 1);
+            r0p[i] = odd ? got_p : my_p; r1p[i] = odd ? my_p : got_p;
+            r0c[i] = odd ? got_c : my_c; r1c[i] = odd ? my_c : got_c;
+          }
+          uint8_t* pst = smem + L.pstg + ((static_cast<uint32_t>(vo) >> 1) & 1) * 8192;
+          const int pr = row >> 1;
+          const int up = (J.u0 >> 1) + pr, vp = vo >> 1;
+          const int xp = p.u_is_y ? vp : up, yp = p.u_is_y ? up : vp;
+          const bool pvalid = xp < (p.W >> 1) && yp < (p.H >> 1);
+          uint32_t cw[4];
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            uint4 u4[4];
+            // window scan order (dy, dx): u = y -> (r0,prev) (r0,cur) (r1,prev) (r1,cur); u = x -> (prev,r0) (prev,r1) (cur,r0) (cur,r1)
+            u4[0] = make_uint4(r0p[4 * h2], r0p[4 * h2 + 1], r0p[4 * h2 + 2], r0p[4 * h2 + 3]);
+            u4[3] = make_uint4(r1c[4 * h2], r1c[4 * h2 + 1], r1c[4 * h2 + 2], r1c[4 * h2 + 3]);
+            const uint4 a = make_uint4(r0c[4 * h2], r0c[4 * h2 + 1], r0c[4 * h2 + 2], r0c[4 * h2 + 3]);
+            const uint4 bq = make_uint4(r1p[4 * h2], r1p[4 * h2 + 1], r1p[4 * h2 + 2], r1p[4 * h2 + 3]);
+            u4[1] = p.u_is_y ? a : bq;
+            u4[2] = p.u_is_y ? bq : a;
+            uint4 m4;
+            uint2 codes;
+            pool4_codes(u4, m4, codes);
+            cw[2 * h2] = codes.x; cw[2 * h2 + 1] = codes.y;
+            const int chunk = hsel * 4 + (odd ? 2 : 0) + h2;   // 16-byte chunk (8 channels) of the pooled row
+            *reinterpret_cast<uint4*>(pst + pr * 128 + ((chunk ^ (pr & 7)) * 16)) = m4;
+          }
+          if (p.pool_idx != nullptr && pvalid)
+            *reinterpret_cast<uint4*>(p.pool_idx + ((static_cast<size_t>(J.b) * (p.H >> 1) + yp) * (p.W >> 1) + xp) * 64 + hsel * 32 +
+                                      (odd ? 16 : 0)) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+          fence_proxy_async_smem();
+          if (leader) tma_store_wait_read<0>();   // the pooled tile written two pairs ago has been read by its store
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (leader) {
+            tma_store_4d(&tmP, pst, 0, J.u0 >> 1, vo >> 1, J.b);
+            tma_store_commit();
+          }
+          if (eprof) { et[0] += e1 - e0; et[1] += clock64() - e1; ++estrips; }
+          continue;
         }
         uint8_t* rowp = stg + row * 128;
 #pragma unroll

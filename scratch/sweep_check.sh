@@ -1,4 +1,3 @@
 #!/bin/bash
 timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "sweep" 2>&1 | tail -2
-timeout 200 python scratch/sweep_dbg3.py 2>&1 | grep -v "25 strips" | tail -8
-timeout 300 python scratch/sweep_timing.py 2>&1 | head -4
+timeout 200 python scratch/sweep_dbg4.py 2>&1 | tail -8
