@@ -101,3 +101,48 @@ def synthetic_iris_crops(seeds, size: int = 224):
         img = np.where(m, tex, 0.0).astype(np.float32)
         out.append(np.repeat(img[None], 3, axis=0))
     return np.stack(out)
+
+
+def synthetic_label_map(seed: int, h: int = 400, w: int = 640, speck: float = 0.0, drop=()):
+    """Label map int64 [h,w] in {0,1,2,3} as a segmenter would emit it for an OpenEDS2020-shaped frame (the input of
+    `extract_eye_landmarks`, gaze_estimators.py:108): the synthetic eye's labels, optionally with a fraction `speck` of
+    the pixels relabelled at random (stray components, holes, ragged borders) and with the classes in `drop` erased."""
+    _, lab = synthetic_eye(seed, h, w)
+    lab = lab[0].copy()
+    rng = np.random.default_rng(7000003 + seed)
+    if speck > 0:
+        hit = rng.random((h, w)) < speck
+        lab[hit] = rng.integers(0, 4, size=int(hit.sum()))
+    for c in drop:
+        lab[lab == c] = 0
+    return lab
+
+
+def landmark_cases():
+    """(name, label map [400,640]) pairs: clean eyes, speckled eyes, missing classes, an empty map."""
+    cases = []
+    for seed in (11, 12, 13):
+        cases.append(("clean%d" % seed, synthetic_label_map(seed)))
+    for seed, speck in ((21, 0.002), (22, 0.02), (23, 0.2)):
+        cases.append(("speck%d" % seed, synthetic_label_map(seed, speck=speck)))
+    cases.append(("nopupil", synthetic_label_map(31, drop=(3,))))
+    cases.append(("nosclera", synthetic_label_map(32, speck=0.001, drop=(1,))))
+    cases.append(("irisonly", synthetic_label_map(33, drop=(1, 3))))
+    cases.append(("empty", np.zeros((400, 640), dtype=np.int64)))
+    return cases
+
+
+def gaze_head_case(in_dim, hidden=64, out_dim=3, batch=37, seed=0):
+    """Seeded weights (torch's (out, in) layout) and inputs of a gaze head."""
+    rng = np.random.default_rng(9000 + seed + in_dim)
+
+    def u(shape, fan_in):
+        b = 1.0 / np.sqrt(fan_in)
+        return rng.uniform(-b, b, size=shape).astype(np.float32)
+
+    params = [u((hidden, in_dim), in_dim), u((hidden,), in_dim), u((hidden, hidden), hidden), u((hidden,), hidden),
+              u((out_dim, hidden), hidden), u((out_dim,), hidden)]
+    x = rng.standard_normal((batch, in_dim)).astype(np.float32)
+    if in_dim == 19:   # landmark-sized magnitudes (pixel coordinates, angles)
+        x = (np.abs(x) * 100).astype(np.float32)
+    return params, x
