@@ -344,6 +344,27 @@ int isx_linear_fwd(const isx_bf16* Xp, const isx_bf16* Wp, isx_bf16* outT, int M
 int isx_transpose_pack(const isx_bf16* srcT, int N, int Mpad, int M, isx_bf16* dst, isx_stream stream);
 int isx_transpose_out(const isx_bf16* srcT, int N, int Mpad, int M, float* dst, isx_stream stream);
 
+/* ---- downstream evaluator features (models/gaze_estimators/gaze_estimators.py) --------------------------------------------
+ * isx_eye_landmarks = extract_eye_landmarks (gaze_estimators.py:108-178; call sites data_preprocessing.py:412,
+ * gaze_estimators.py:49,291) for a BATCH of label maps in one call, without the reference's per-image `.cpu().numpy()` round
+ * trip: cv2.findContours(RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) -> max(contourArea) -> cv2.fitEllipse for the pupil (label 3) and
+ * the iris (label 2) (:55-83), np.where min / max for the sclera (label 1) (:85-106), the derived ratios (:139-152).
+ * seg [B,H,W], seg_dtype 0 = int64, 1 = uint8, 2 = int32 (compared after `.astype(np.uint8)` like :127); landmarks fp32
+ * [B,19] in the order of :154-174, absent quantities 0 (:176); info int32 [B,8] (may be NULL) = {pupil: points of the chosen
+ * contour, external contours, flags; iris: the same three; sclera present; 0}.  flags bit 0: the chosen contour has exactly
+ * five points or a rank-deficient system -- there cv2.fitEllipse leaves the general algorithm (fitEllipseDirect / a
+ * pseudo-random perturbation) and this library does not follow it: it solves the unperturbed system; bit 1: the contour has
+ * more than max_points points (nothing fitted: call again with a larger workspace).  The reference asserts H, W = 400, 640;
+ * any frame whose three padded bit planes fit in shared memory is accepted (3 * (H+2) * ceil((W+2)/32) * 4 <= 200 KB). */
+int64_t isx_eye_landmarks_workspace_bytes(int B, int H, int W, int max_points);
+int isx_eye_landmarks(const void* seg, int seg_dtype, int B, int H, int W, double epsilon, int max_points, void* workspace,
+                      float* landmarks, int32_t* info, isx_stream stream);
+/* GazeEstimator1.model / GazeEstimator2.model in eval mode + the row normalisation (gaze_estimators.py:24-32,51-53 and
+ * :196-204,221-223): out[B,out_dim] = y / ||y||_2, y = W3 relu(W2 relu(W1 x + b1) + b2) + b3; fp32, torch.nn.Linear layouts
+ * (W1 [hidden,in_dim], W2 [hidden,hidden], W3 [out_dim,hidden]); x fp32 rows with stride ld_x. */
+int isx_gaze_head_fwd(const float* x, int64_t ld_x, int B, int in_dim, int hidden, int out_dim, const float* W1, const float* b1,
+                      const float* W2, const float* b2, const float* W3, const float* b3, float* out, isx_stream stream);
+
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------
  * isx_launch_count: kernels launched by this library since load.  isx_prof_enable(1) brackets every launch
  * of the tensor-core conv (family 0), Gram (1) and L-BFGS pass (2) kernels with CUDA events on the launching

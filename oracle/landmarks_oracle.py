@@ -115,12 +115,11 @@ def contour_area(pts: np.ndarray) -> float:
 
 
 def is_degenerate(pts: np.ndarray) -> bool:
-    """True where cv2.fitEllipse leaves the algorithm restated below: (i) for EXACTLY five points it switches to
-    fitEllipseDirect (the ellipse-constrained eigenvector fit); (ii) when the five-parameter system is rank deficient
-    (sigma_max * FLT_EPSILON > sigma_min: collinear specks) fitEllipseNoDirect perturbs the points with an mt19937 stream
-    before it solves.  Both only happen when the LARGEST component of a class is a speck of a handful of pixels -- never
-    for a pupil or an iris.  Neither this restatement nor the CUDA kernel follows OpenCV there (they solve the
-    unperturbed general system); tests skip such point sets and the kernel reports them (info flag bit 0)."""
+    """True where the CUDA kernel does not claim cv2.fitEllipse's result (info flag bit 0): (i) for EXACTLY five points cv2
+    switches to fitEllipseDirect (the ellipse-constrained eigenvector fit); (ii) when the five-parameter system is rank
+    deficient (sigma_max * FLT_EPSILON > sigma_min: collinear specks) fitEllipseNoDirect perturbs the points with an
+    mt19937 stream before it solves; (iii) see below.  All three only happen when the LARGEST component of a class is a
+    speck of a handful of pixels -- never for a pupil or an iris.  Tests skip such point sets."""
     p = np.asarray(pts, dtype=np.float32).reshape(-1, 2)
     if len(p) == 5:
         return True
@@ -130,7 +129,17 @@ def is_degenerate(pts: np.ndarray) -> bool:
     d *= 100.0 / max(s, float(np.finfo(np.float32).eps))
     A = np.stack([-d[:, 0] ** 2, -d[:, 1] ** 2, -d[:, 0] * d[:, 1], d[:, 0], d[:, 1]], axis=1)
     w = np.linalg.svd(A, compute_uv=False)
-    return bool(w[0] * float(np.finfo(np.float32).eps) > w[-1])
+    if w[0] * float(np.finfo(np.float32).eps) > w[-1]:
+        return True
+    # (iii) the refit with the centre fixed is EXACTLY rank deficient (a speck symmetric about its fitted centre: two columns
+    # coincide).  cv2's answer is then the minimum-norm solution its SVD back-substitution picks -- `fit_ellipse` below
+    # reproduces that through lstsq, the CUDA kernel (normal equations) does not and reports the contour instead.
+    gfp = np.linalg.lstsq(A, np.full(len(p), 10000.0), rcond=None)[0]
+    A2 = np.array([[2 * gfp[0], gfp[2]], [gfp[2], 2 * gfp[1]]])
+    r = np.linalg.lstsq(A2, np.array([gfp[3], gfp[4]]), rcond=None)[0]
+    A3 = np.stack([(d[:, 0] - r[0]) ** 2, (d[:, 1] - r[1]) ** 2, (d[:, 0] - r[0]) * (d[:, 1] - r[1])], axis=1)
+    w3 = np.linalg.svd(A3, compute_uv=False)
+    return bool(w3[-1] < 1e-10 * w3[0])
 
 
 def fit_ellipse(pts: np.ndarray):
