@@ -179,6 +179,23 @@ def cpu_reference_rate(steps, warmup, threads=None):
 def run_reference(args, rank):
     if rank != 0:
         return
+    if args.config == "landmarks":      # row f4: the reference's own per-frame OpenCV path on one host thread
+        import numpy as np
+
+        sys.path.insert(0, os.path.join(ROOT, "iris-style-transfer_b200"))
+        import synthetic
+
+        labs = np.stack([synthetic.synthetic_label_map(i, speck=0.002 * (i % 4)) for i in range(32)])
+        rate, n = cv2_landmark_rate(labs, seconds=10.0)
+        print(json.dumps({"impl": "reference", "metric": "eye-landmark frames/sec @400x640 label maps (extract_eye_landmarks + GazeEstimator1)",
+                          "value": rate, "unit": "frames/s", "n_gpus": args.gpus, "steps": n, "warmup": 1, "ms_per_step": 1e3 / rate,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 / f64", "data": "synthetic",
+                          "config": {"workload": "row f4: synthetic 400x640 label maps, 0-0.6 % stray pixels, one frame per step", "name": "landmarks"},
+                          "cpu_baseline": {"value": rate, "unit": "frames/s", "cores": 1, "kind": "reference",
+                                           "sample": "%d frames through cv2.findContours / contourArea / fitEllipse + np.where" % n},
+                          "e2e": {"value": rate, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}),
+              flush=True)
+        return
     steps = max(1, args.steps)
     rate, done, dt, threads = cpu_reference_rate(steps, args.warmup)
     line = {
@@ -332,8 +349,8 @@ def nst_leg(args, dev, vgg, c_dev, s_dev, BN_loss, independent, K, Wm, world, ra
         barrier()
         ms = e0.elapsed_time(e1)
         launches = int(lib.isx_launch_count() - launches0)
-        prof = (ctypes.c_double * 9)()
-        _lib.call("isx_prof_collect", prof, 9)
+        prof = (ctypes.c_double * 12)()
+        _lib.call("isx_prof_collect", prof, 12)
         lib.isx_prof_enable(0)
         clocks = sampler.stop() if rank == 0 else None
         pairs1 = torch.cat([j.history_counts() for j in subjobs])
@@ -414,6 +431,137 @@ def feature_leg(dev, vgg, taps5, n_per_gpu, world, batch=32):
     return out
 
 
+def measured_peaks():
+    """HBM peak for the roofline legs: the driver-written MEASURED_PEAKS.json, else the profiling guide's fallback."""
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        if pk.get("hbm_gbs"):
+            return {"hbm_gbs": float(pk["hbm_gbs"]), "source": "MEASURED_PEAKS.json hbm_gbs (of measured)"}
+    except Exception:
+        pass
+    return {"hbm_gbs": 6650.0, "source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+def cv2_landmark_rate(labs, seconds=8.0):
+    """The reference's own CPU path for row f4: per frame the three OpenCV calls per class + np.where that
+    gaze_estimators.py:55-178 executes (cv2 is the third-party library the reference calls), one host thread like the
+    reference's per-frame Python loop.  Returns (frames/s, frames timed)."""
+    import cv2
+    import numpy as np
+
+    def one(seg):
+        s8 = seg.astype(np.uint8)
+        for cls in (3, 2):
+            cs, _ = cv2.findContours((s8 == cls).astype(np.uint8), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+            if cs:
+                c = max(cs, key=cv2.contourArea)
+                if len(c) >= 5:
+                    cv2.fitEllipse(c)
+        ys, xs = np.where((s8 == 1) > 0)
+        return (xs.min(), xs.max(), ys.min(), ys.max()) if len(xs) else None
+
+    one(labs[0])
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        one(labs[n % len(labs)])
+        n += 1
+    return n / (time.perf_counter() - t0), n
+
+
+def landmarks_leg(args, dev, lib, world, rank, local):
+    """`--config landmarks`: 128 OpenEDS2020-shaped 400x640 label maps per GPU and step -> 19 eye
+    landmarks (extract_eye_landmarks) -> GazeEstimator1 gaze vectors.  A quarter of the maps each carry 0 / 0.2 / 0.4 / 0.6 %
+    randomly relabelled pixels (up to ~450 stray contours per class)."""
+    import ctypes
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import iris_b200
+    from iris_b200 import _lib
+
+    B = args.batch or 128
+    K, Wm = args.steps, args.warmup
+    labs = np.stack([iris_b200.synthetic.synthetic_label_map(100000 * rank + i, speck=0.002 * (i % 4)) for i in range(B)])
+    seg_h = torch.from_numpy(labs).pin_memory()
+    seg = seg_h.to(dev)
+    net = iris_b200.GazeEstimator1(extract_feature=True).to(dev)
+    out_h = torch.empty(B, 3).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(Wm):
+        net(seg)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.isx_prof_enable(1)
+    launches0 = lib.isx_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for e0, e1 in ev:
+        flush.zero_()                       # 256 MB written between steps: the label maps (262 MB) come from HBM
+        e0.record()
+        g = net(seg)
+        e1.record()
+    barrier()
+    launches = int(lib.isx_launch_count() - launches0)
+    prof = (ctypes.c_double * 12)()
+    _lib.call("isx_prof_collect", prof, 12)
+    lib.isx_prof_enable(0)
+    ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    # end to end: pinned host label maps -> device -> landmarks -> gaze vectors -> pinned host
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        g = net(seg_h.to(dev, non_blocking=True))
+        out_h.copy_(g, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms, dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, dt = float(t[0]), float(t[1])
+    if rank != 0:
+        return None
+    from oracle import landmarks_oracle as L                      # checker only: the timed results against the oracle
+    lm = iris_b200.extract_eye_landmarks_batch(seg[:4]).cpu().numpy()
+    err = float(max(np.abs(lm[i] - L.extract_eye_landmarks(labs[i])).max() for i in range(4)))
+    peaks = measured_peaks()
+    plane_ms, plane_bytes = prof[3 * 3 + 1], prof[3 * 3 + 2]
+    achieved = plane_bytes / (plane_ms / 1e3) / 1e9 if plane_ms > 0 else None
+    line = {"metric": "eye-landmark frames/sec @400x640 label maps (extract_eye_landmarks + GazeEstimator1)",
+            "value": world * B * K / (ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 labels / int32 contours / f64 fit",
+            "data": "synthetic",
+            "config": {"workload": "row f4: %d synthetic OpenEDS2020-shaped 400x640 int64 label maps per GPU and step, 0-0.6 %% stray "
+                                   "pixels, -> 19 landmarks -> GazeEstimator1 (19-64-64-3)" % B, "name": "landmarks", "batch_per_gpu": B,
+                       "l2": "256 MB written between steps; the maps of one step are 262 MB"},
+            "e2e": {"value": world * B * K / dt, "unit": "frames/s", "h2d_bytes_per_step": int(seg_h.numel() * 8),
+                    "d2h_bytes_per_step": int(out_h.numel() * 4)},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"kernel": "lm_planes_kernel (labels -> pupil / iris bit planes + sclera bounding box)", "bound": "hbm",
+                         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": None,
+                         "peak_source": peaks["source"], "share_of_step": plane_ms / ms if ms > 0 else None,
+                         "note": "the rest of a step is lm_contour_kernel: one CTA per frame and class following borders out of "
+                                 "shared memory -- latency-bound serial index work, no roofline applies"},
+            "sanity": {"max_abs_diff_vs_oracle_first4": err}}
+    if not args.no_cpu_baseline:
+        rate, n = cv2_landmark_rate(labs)
+        line["cpu_baseline"] = {"value": rate, "unit": "frames/s", "cores": 1, "kind": "reference",
+                                "sample": "%d frames of the same batch through cv2.findContours / contourArea / fitEllipse + np.where "
+                                          "(what gaze_estimators.py:55-178 executes per frame), one thread like the reference's loop" % n}
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -421,7 +569,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="isx", choices=["isx", "reference"])
     ap.add_argument("--config", default="nst640", choices=["nst640", "nst640_5tap", "masked_gram", "nst224", "nst1024",
-                                                           "feat4", "feat5", "frames2020"])
+                                                           "feat4", "feat5", "frames2020", "landmarks"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-library", action="store_true")
@@ -490,6 +638,12 @@ def main():
                     "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                     "config": {"workload": "BASELINE config[2]: %d synthetic 640x400 eyes per GPU -> style features, sharded, "
                                            "all-gathered" % args.feature_images}, "detail": feat}
+            print(json.dumps(line), flush=True)
+        finish()
+        return
+    if cfgname == "landmarks":
+        line = landmarks_leg(args, dev, lib, world, rank, local)
+        if rank == 0:
             print(json.dumps(line), flush=True)
         finish()
         return

@@ -367,9 +367,9 @@ int isx_gaze_head_fwd(const float* x, int64_t ld_x, int B, int in_dim, int hidde
 
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------
  * isx_launch_count: kernels launched by this library since load.  isx_prof_enable(1) brackets every launch
- * of the tensor-core conv (family 0), Gram (1) and L-BFGS pass (2) kernels with CUDA events on the launching
- * stream; after a device sync isx_prof_collect fills out[3*family + {0,1,2}] = {launches, total ms,
- * total algorithmic work (FLOPs for 0/1, bytes for 2)}. */
+ * of the tensor-core conv (family 0), Gram (1), L-BFGS pass (2) and landmark bit-plane (3) kernels with CUDA events on the
+ * launching stream; after a device sync isx_prof_collect fills out[3*family + {0,1,2}] = {launches, total ms,
+ * total algorithmic work (FLOPs for 0/1, bytes for 2/3)}; n_out >= 12. */
 unsigned long long isx_launch_count(void);
 /* kernel-selection knobs (tests, experiments; defaults in parentheses): "c64" (1) resident-weight kernel for the 64->64
  * layers, "halo2" (1) halo-patch pair kernel for the mid layers, "tail_n" (1) taps-in-N image-gradient tail -- 0 sends

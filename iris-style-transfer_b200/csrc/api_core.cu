@@ -141,7 +141,7 @@ struct IsxProfiler {
   size_t pool_next = 0;
   cudaEvent_t open[ISX_PROF_FAMILIES];
   double open_work[ISX_PROF_FAMILIES];
-  bool is_open[ISX_PROF_FAMILIES] = {false, false, false};
+  bool is_open[ISX_PROF_FAMILIES] = {};
   cudaEvent_t event() {
     if (pool_next == pool.size()) {
       cudaEvent_t e;

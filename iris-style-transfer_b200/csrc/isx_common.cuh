@@ -68,7 +68,7 @@ inline int isx_num_sms() { return isx_ctx()->num_sms; }
 // optional CUDA-event timing of one kernel family on the launching stream (bench.py roofline leg)
 void isx_prof_begin(int family, double work, cudaStream_t s);
 void isx_prof_end(int family, cudaStream_t s);
-enum { ISX_PROF_CONV = 0, ISX_PROF_GRAM = 1, ISX_PROF_LBFGS = 2, ISX_PROF_FAMILIES = 3 };
+enum { ISX_PROF_CONV = 0, ISX_PROF_GRAM = 1, ISX_PROF_LBFGS = 2, ISX_PROF_PLANES = 3, ISX_PROF_FAMILIES = 4 };
 
 // Encode a tiled bf16 tensor map (rank <= 5).  dims/strides innermost first; strides in BYTES
 // for dims 1..rank-1 (dim 0 is contiguous).  swizzle128: CU_TENSOR_MAP_SWIZZLE_128B else NONE.

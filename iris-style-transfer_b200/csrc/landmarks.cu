@@ -31,8 +31,9 @@ using namespace isx_lm;
 inline cudaStream_t S(isx_stream s) { return static_cast<cudaStream_t>(s); }
 inline size_t lm_align(size_t n) { return (n + 255) & ~static_cast<size_t>(255); }
 
-constexpr int kLmThreads = 256;
-constexpr int kLmPlaneBlocks = 8;   // blocks per frame of the plane kernel
+constexpr int kLmThreads = 256;          // plane kernel
+constexpr int kLmContourThreads = 128;   // contour kernel: 228 registers per thread (the double-double fit) -> 128 threads so
+                                         // that two CTAs fit on an SM (ncu: 256 threads = one CTA per SM, 1.7 waves for 256 CTAs)
 
 struct LmResult {   // per (frame, class)
   float box[5];     // cx, cy, width, height, angle
@@ -47,44 +48,45 @@ __global__ void lm_init_kernel(int32_t* sclera, int B) {
   if (b < B) { sclera[b * 4 + 0] = INT_MAX; sclera[b * 4 + 1] = -1; sclera[b * 4 + 2] = INT_MAX; sclera[b * 4 + 3] = -1; }
 }
 
-// planes[b][cls][y][w]: bit x & 31 of word x >> 5 is (uint8)label == (cls == 0 ? 3 : 2); sclera[b] = {xmin, xmax, ymin, ymax}
+// planes[b][cls][y][w]: bit x & 31 of word x >> 5 is (uint8)label == (cls == 0 ? 3 : 2); sclera[b] = {xmin, xmax, ymin, ymax}.
+// A warp owns whole rows: lane l reads pixel 32 w + l of word w (one 256-byte request per warp and word, U requests in
+// flight), three ballots turn the 32 labels into the bits of the pupil / iris word and into the sclera's column range -- the
+// ballots are warp-uniform, so the bounding box needs no reduction.  No division, ~15 instructions per 256 bytes (the first
+// version indexed a flat word list: two integer divisions per word, 52 instructions, 67 % of the issue slots, 3.1 TB/s).
 template <typename T>
 __global__ void __launch_bounds__(kLmThreads)
 lm_planes_kernel(const T* __restrict__ seg, uint32_t* __restrict__ planes, int32_t* __restrict__ sclera, int H, int W, int Wu) {
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int warps = gridDim.x * (kLmThreads / 32);
-  const int words = H * Wu;
   const T* img = seg + static_cast<size_t>(b) * H * W;
-  uint32_t* p3 = planes + static_cast<size_t>(b) * 2 * words;
-  uint32_t* p2 = p3 + words;
+  uint32_t* p3 = planes + static_cast<size_t>(b) * 2 * H * Wu;
+  uint32_t* p2 = p3 + static_cast<size_t>(H) * Wu;
   int xmin = INT_MAX, xmax = -1, ymin = INT_MAX, ymax = -1;
-  constexpr int U = 4;   // words per warp in flight
-  for (int w0 = (blockIdx.x * (kLmThreads / 32) + (threadIdx.x >> 5)) * U; w0 < words; w0 += warps * U) {
-    unsigned v[U];
+  constexpr int U = 10;   // 256-byte requests in flight per warp (half a 640-pixel row)
+  for (int y = blockIdx.x * (kLmThreads / 32) + (threadIdx.x >> 5); y < H; y += warps) {
+    const T* row = img + static_cast<size_t>(y) * W;
+    bool any = false;
+    for (int w0 = 0; w0 < Wu; w0 += U) {
+      unsigned v[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int wd = w0 + u;
-      const int y = wd / Wu, x = (wd - y * Wu) * 32 + lane;
-      v[u] = (wd < words && x < W) ? (static_cast<unsigned>(img[static_cast<size_t>(y) * W + x]) & 255u) : 0u;   // astype(np.uint8)
-    }
+      for (int u = 0; u < U; ++u) {
+        const int x = (w0 + u) * 32 + lane;
+        v[u] = x < W ? (static_cast<unsigned>(row[x]) & 255u) : 0u;   // astype(np.uint8); words past the row read as background
+      }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int wd = w0 + u;
-      const unsigned b3 = __ballot_sync(0xffffffffu, v[u] == 3u), b2 = __ballot_sync(0xffffffffu, v[u] == 2u);
-      if (wd < words && lane == 0) { p3[wd] = b3; p2[wd] = b2; }
-      if (v[u] == 1u) {
-        const int y = wd / Wu, x = (wd - y * Wu) * 32 + lane;
-        xmin = min(xmin, x); xmax = max(xmax, x); ymin = min(ymin, y); ymax = max(ymax, y);
+      for (int u = 0; u < U; ++u) {
+        const unsigned b3 = __ballot_sync(0xffffffffu, v[u] == 3u), b2 = __ballot_sync(0xffffffffu, v[u] == 2u);
+        const unsigned b1 = __ballot_sync(0xffffffffu, v[u] == 1u);
+        if (w0 + u < Wu && lane == 0) { p3[y * Wu + w0 + u] = b3; p2[y * Wu + w0 + u] = b2; }
+        if (b1) {
+          xmin = min(xmin, (w0 + u) * 32 + __ffs(static_cast<int>(b1)) - 1);
+          xmax = max(xmax, (w0 + u) * 32 + 31 - __clz(static_cast<int>(b1)));
+          any = true;
+        }
       }
     }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
-    ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
-    xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
-    ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    if (any) { ymin = min(ymin, y); ymax = y; }   // rows ascend
   }
   if (lane == 0 && xmax >= 0) {
     atomicMin(&sclera[b * 4 + 0], xmin); atomicMax(&sclera[b * 4 + 1], xmax);
@@ -94,7 +96,7 @@ lm_planes_kernel(const T* __restrict__ seg, uint32_t* __restrict__ planes, int32
 
 // sum of K doubles per thread over the block; the totals are returned to every thread in v[]
 template <int K>
-__device__ void lm_block_sum(double* v, double* red /* [kLmThreads / 32][K] shared */) {
+__device__ void lm_block_sum(double* v, double* red /* [kLmContourThreads / 32][K] shared */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -108,7 +110,7 @@ __device__ void lm_block_sum(double* v, double* red /* [kLmThreads / 32][K] shar
   for (int k = 0; k < K; ++k) {
     double x = 0;
 #pragma unroll
-    for (int w = 0; w < kLmThreads / 32; ++w) x += red[w * K + k];
+    for (int w = 0; w < kLmContourThreads / 32; ++w) x += red[w * K + k];
     v[k] = x;
   }
   __syncthreads();
@@ -116,7 +118,7 @@ __device__ void lm_block_sum(double* v, double* red /* [kLmThreads / 32][K] shar
 
 // the same for double-double accumulators
 template <int K>
-__device__ void lm_block_sum_dd(dd* v, dd* red /* [kLmThreads / 32][K] shared */) {
+__device__ void lm_block_sum_dd(dd* v, dd* red /* [kLmContourThreads / 32][K] shared */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -135,13 +137,13 @@ __device__ void lm_block_sum_dd(dd* v, dd* red /* [kLmThreads / 32][K] shared */
   for (int k = 0; k < K; ++k) {
     dd x = red[k];
 #pragma unroll
-    for (int w = 1; w < kLmThreads / 32; ++w) x = dd_add(x, red[w * K + k]);
+    for (int w = 1; w < kLmContourThreads / 32; ++w) x = dd_add(x, red[w * K + k]);
     v[k] = x;
   }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kLmThreads)
+__global__ void __launch_bounds__(kLmContourThreads, 2)
 lm_contour_kernel(const uint32_t* __restrict__ planes, uint32_t* __restrict__ points, LmResult* __restrict__ results, int H, int W,
                   int Wu, int Ww, int cap) {
   extern __shared__ uint32_t lm_smem[];
@@ -151,13 +153,13 @@ lm_contour_kernel(const uint32_t* __restrict__ planes, uint32_t* __restrict__ po
   uint32_t* M = F + pw;
   uint32_t* N = M + pw;
   __shared__ int s_best_n, s_best_buf, s_ncont;
-  __shared__ dd s_red_dd[(kLmThreads / 32) * kLmSums1];
+  __shared__ dd s_red_dd[(kLmContourThreads / 32) * kLmSums1];
   double* s_red = reinterpret_cast<double*>(s_red_dd);
   __shared__ double s_bcast[8];
 
   // ---- the class's bit plane with its one-pixel zero frame: bit (x + 1) of row (y + 1) ----
   const uint32_t* G = planes + (static_cast<size_t>(b) * 2 + cls) * H * Wu;
-  for (int i = tid; i < pw; i += kLmThreads) {
+  for (int i = tid; i < pw; i += kLmContourThreads) {
     const int yp = i / Ww, w = i - yp * Ww;
     uint32_t f = 0;
     if (yp >= 1 && yp <= H) {
@@ -175,7 +177,7 @@ lm_contour_kernel(const uint32_t* __restrict__ planes, uint32_t* __restrict__ po
   // border, and only the rows the trace touched (start row .. y_max: a trace marks nothing else, rows above the start are
   // done) are rescanned, one row per lane.
   int* cand = reinterpret_cast<int*>(N + pw);
-  for (int y = tid; y < rows; y += kLmThreads) cand[y] = (y >= 1 && y <= H) ? lm_row_first_start(F, M, N, Ww, y, 0) : -1;
+  for (int y = tid; y < rows; y += kLmContourThreads) cand[y] = (y >= 1 && y <= H) ? lm_row_first_start(F, M, N, Ww, y, 0) : -1;
   __syncthreads();
   uint32_t* buf0 = points + (static_cast<size_t>(b) * 2 + cls) * 2 * cap;
   if (tid < 32) {
@@ -223,12 +225,12 @@ lm_contour_kernel(const uint32_t* __restrict__ planes, uint32_t* __restrict__ po
     const uint32_t* pts = buf0 + static_cast<size_t>(s_best_buf) * cap;   // written by thread 0 of this block
     double v[2];
     v[0] = 0; v[1] = 0;
-    for (int i = tid; i < n; i += kLmThreads) { const uint32_t p = pts[i]; v[0] += p & 0xFFFFu; v[1] += p >> 16; }
+    for (int i = tid; i < n; i += kLmContourThreads) { const uint32_t p = pts[i]; v[0] += p & 0xFFFFu; v[1] += p >> 16; }
     lm_block_sum<2>(v, s_red);
     // Point2f c += p; c /= n  (integer-valued float sums below 2^24 are exact in any order)
     const float cx = __fdiv_rn(static_cast<float>(v[0]), static_cast<float>(n)), cy = __fdiv_rn(static_cast<float>(v[1]), static_cast<float>(n));
     v[0] = 0;
-    for (int i = tid; i < n; i += kLmThreads) {
+    for (int i = tid; i < n; i += kLmContourThreads) {
       const uint32_t p = pts[i];
       const float dx = __fsub_rn(static_cast<float>(p & 0xFFFFu), cx), dy = __fsub_rn(static_cast<float>(p >> 16), cy);
       v[0] += static_cast<double>(__fadd_rn(fabsf(dx), fabsf(dy)));
@@ -238,7 +240,7 @@ lm_contour_kernel(const uint32_t* __restrict__ planes, uint32_t* __restrict__ po
     dd a[kLmSums1];
 #pragma unroll
     for (int k = 0; k < kLmSums1; ++k) a[k] = dd_make(0.0);
-    for (int i = tid; i < n; i += kLmThreads) {
+    for (int i = tid; i < n; i += kLmContourThreads) {
       const uint32_t p = pts[i];
       const float dx = __fsub_rn(static_cast<float>(p & 0xFFFFu), cx), dy = __fsub_rn(static_cast<float>(p >> 16), cy);
       lm_acc1(dx * scale, dy * scale, a);
@@ -258,7 +260,7 @@ lm_contour_kernel(const uint32_t* __restrict__ planes, uint32_t* __restrict__ po
 #pragma unroll
     for (int k = 0; k < kLmSums2; ++k) a[k] = dd_make(0.0);
     if (ok1) {
-      for (int i = tid; i < n; i += kLmThreads) {
+      for (int i = tid; i < n; i += kLmContourThreads) {
         const uint32_t p = pts[i];
         const float dx = __fsub_rn(static_cast<float>(p & 0xFFFFu), cx), dy = __fsub_rn(static_cast<float>(p >> 16), cy);
         lm_acc2(dx * scale, dy * scale, rx, ry, a);
@@ -403,13 +405,24 @@ extern "C" int isx_eye_landmarks(const void* seg, int seg_dtype, int B, int H, i
   uint32_t* points = reinterpret_cast<uint32_t*>(ws + L.points);
   lm_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(sclera, B);
   ISX_LAUNCH_CHECK();
-  const dim3 pg(kLmPlaneBlocks, B);
+  // one resident wave: blocks per frame = what fits on the device at once / B, at least one, at most one warp per row
+  int per_sm = 1;
+  if (seg_dtype == 0) ISX_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_planes_kernel<long long>, kLmThreads, 0));
+  else if (seg_dtype == 1) ISX_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_planes_kernel<uint8_t>, kLmThreads, 0));
+  else ISX_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_planes_kernel<int>, kLmThreads, 0));
+  const int cap_blocks = std::max(1, isx_num_sms() * std::max(1, per_sm));
+  const int bx = std::max(1, std::min(cap_blocks / B, (H + kLmThreads / 32 - 1) / (kLmThreads / 32)));
+  const dim3 pg(bx, B);
+  const double label_bytes = seg_dtype == 0 ? 8.0 : seg_dtype == 1 ? 1.0 : 4.0;
+  isx_prof_begin(ISX_PROF_PLANES, static_cast<double>(B) * H * (W * label_bytes + 2.0 * L.Wu * 4), s);   // labels in, two bit planes out
   if (seg_dtype == 0) lm_planes_kernel<long long><<<pg, kLmThreads, 0, s>>>(static_cast<const long long*>(seg), planes, sclera, H, W, L.Wu);
   else if (seg_dtype == 1) lm_planes_kernel<uint8_t><<<pg, kLmThreads, 0, s>>>(static_cast<const uint8_t*>(seg), planes, sclera, H, W, L.Wu);
   else lm_planes_kernel<int><<<pg, kLmThreads, 0, s>>>(static_cast<const int*>(seg), planes, sclera, H, W, L.Wu);
+  isx_prof_end(ISX_PROF_PLANES, s);
   ISX_LAUNCH_CHECK();
   ISX_CHECK_CUDA(cudaFuncSetAttribute(lm_contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  lm_contour_kernel<<<dim3(2, B), kLmThreads, smem, s>>>(planes, points, results, H, W, L.Wu, L.Ww, max_points);
+  ISX_CHECK_CUDA(cudaFuncSetAttribute(lm_contour_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  lm_contour_kernel<<<dim3(2, B), kLmContourThreads, smem, s>>>(planes, points, results, H, W, L.Wu, L.Ww, max_points);
   ISX_LAUNCH_CHECK();
   lm_finalize_kernel<<<(B + 127) / 128, 128, 0, s>>>(results, sclera, epsilon, landmarks, info, B);
   ISX_LAUNCH_CHECK();
