@@ -24,7 +24,8 @@ own library calls (torchvision VGG-19 through cuDNN, torch.optim.LBFGS) on the s
 mask-weighted Gram via c_mask / s_mask) | nst224 (64 iris crops 224x224, default BN loss, the batch as one problem:
 what the reference's drivers call) | nst1024 (BASELINE config[4]: 1024x1024 RGB, Gram loss) | feat4 / feat5
 (BASELINE config[2]: style-feature extraction only, 4 / 5 taps) | frames2020 (BASELINE config[3]: OpenEDS2020-shaped
-400x640 frames end to end: mask -> crop -> resize -> NST -> composite).
+400x640 frames end to end: mask -> crop -> resize -> NST -> composite) | landmarks (400x640 label maps
+-> 19 eye landmarks -> GazeEstimator1; frames/s, roofline of the bit-plane kernel, cv2 on one host core beside it).
 """
 import argparse
 import json
