@@ -157,3 +157,19 @@ def test_specks_and_ill_conditioned_contours_equal_cv2(host, shape):
             assert min(da, 180.0 - da) < 2e-2
             n += 1
     assert n > 4
+
+
+def test_core_under_asan(tmp_path):
+    """The plane / neighbour / trace index arithmetic under AddressSanitizer + UBSan (compute-sanitizer's stand-in: the GPU
+    pool does not offer it): 600 random masks with widths around the word boundaries and foreground on the frame edge."""
+    exe = str(tmp_path / "lm_asan")
+    csrc = os.path.join(ROOT, "iris-style-transfer_b200", "csrc")
+    r = subprocess.run(["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-x", "c++", "-I", csrc,
+                        os.path.join(ROOT, "tests", "landmarks_core_host.cpp"), os.path.join(ROOT, "tests", "landmarks_core_asan_main.cpp"),
+                        "-o", exe], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("g++ -fsanitize=address,undefined not usable here: %s" % r.stderr[-300:])
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0")
+    env.pop("LD_PRELOAD", None)
+    run = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=300)
+    assert run.returncode == 0 and "asan driver ok" in run.stdout, (run.stdout[-500:], run.stderr[-2000:])
