@@ -365,6 +365,16 @@ int isx_eye_landmarks(const void* seg, int seg_dtype, int B, int H, int W, doubl
 int isx_gaze_head_fwd(const float* x, int64_t ld_x, int B, int in_dim, int hidden, int out_dim, const float* W1, const float* b1,
                       const float* W2, const float* b2, const float* W3, const float* b3, float* out, isx_stream stream);
 
+/* ---- evaluation metrics of the drivers ------------------------------------------------------------------------------------
+ * isx_seg_iou = utils.cal_IoUs (utils.py:163-194; iris_style_transfer_openeds2019.py:156, data_preprocessing.py:168): preds,
+ * targets int64 [B,HW] label maps -> iou fp32 [B,num_class] = intersection / (union + eps) per image and class, miou fp32 [B] =
+ * their mean; one pass over the two maps (the reference makes ~30).  counts: uint32 [B,num_class,2] scratch (zeroed here).
+ * Bit-identical to the reference (exact counts, the same fp32 division); num_class <= 8.
+ * isx_angular_distance = utils.angular_distance (utils.py:216-240): rows v1, v2 fp32 [n,d] -> acos(clamp(<v1,v2>)) and degrees. */
+int isx_seg_iou(const int64_t* preds, const int64_t* targets, int B, int64_t HW, int num_class, float eps, uint32_t* counts,
+                float* iou, float* miou, isx_stream stream);
+int isx_angular_distance(const float* v1, const float* v2, int n, int d, float* radian, float* degree, isx_stream stream);
+
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------
  * isx_launch_count: kernels launched by this library since load.  isx_prof_enable(1) brackets every launch
  * of the tensor-core conv (family 0), Gram (1), L-BFGS pass (2) and landmark bit-plane (3) kernels with CUDA events on the

@@ -8,8 +8,8 @@ from . import synthetic  # noqa: F401
 try:  # torch-dependent surface (the ctypes layer and the synthetic generators import without torch)
     from .pipelines import (composite_irises, crop_resize_irises, iris_masks_and_bboxes, mask_and_crop_iris,  # noqa: F401
                             nst)
-    from .utils import (ContentLoss_L2, GramMatrix, StyleLoss_BN, StyleLoss_Gram, crop_image,  # noqa: F401
-                        style_features)
+    from .utils import (ContentLoss_L2, GramMatrix, StyleLoss_BN, StyleLoss_Gram, angular_distance, cal_IoUs,  # noqa: F401
+                        crop_image, style_features)
     from .vgg import VGG19, random_vgg19_weights  # noqa: F401
     from .frames import stylize_frames  # noqa: F401
     from .ritnet import RITnet  # noqa: F401

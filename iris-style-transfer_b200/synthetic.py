@@ -146,3 +146,27 @@ def gaze_head_case(in_dim, hidden=64, out_dim=3, batch=37, seed=0):
     if in_dim == 19:   # landmark-sized magnitudes (pixel coordinates, angles)
         x = (np.abs(x) * 100).astype(np.float32)
     return params, x
+
+
+def iou_case(shape=(640, 400), seeds=(61, 62, 63, 64, 65)):
+    """(preds, targets) int64 [b,h,w] for cal_IoUs: targets = synthetic label maps, preds = the same maps with 0 / 0.5 / 5 %
+    of the pixels relabelled, one with a class missing, one all background (an empty union: iou = 0 / eps = 0)."""
+    h, w = shape
+    t = np.stack([synthetic_label_map(s, h, w) for s in seeds])
+    p = np.stack([synthetic_label_map(seeds[0], h, w), synthetic_label_map(seeds[1], h, w, speck=0.005),
+                  synthetic_label_map(seeds[2], h, w, speck=0.05), synthetic_label_map(seeds[3], h, w, drop=(3,)),
+                  np.zeros((h, w), dtype=np.int64)])
+    t[4][t[4] == 3] = 0          # class 3 absent from both maps of the last pair
+    return p, t
+
+
+def gaze_vector_case(n=257, seed=0):
+    """Two sets of unit vectors (n, 3) for angular_distance, incl. identical and opposite rows (dot = +-1 up to rounding)."""
+    rng = np.random.default_rng(31337 + seed)
+    a = rng.standard_normal((n, 3)).astype(np.float32)
+    b = rng.standard_normal((n, 3)).astype(np.float32)
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    b[0] = a[0]
+    b[1] = -a[1]
+    return a, b

@@ -234,3 +234,39 @@ def crop_image(image: torch.Tensor, return_idx: bool = False):
     if return_idx:
         return x_min, y_min, x_max, y_max
     return img3[:, x_min: x_max + 1, y_min: y_max + 1]
+
+
+def cal_IoUs(preds: torch.Tensor, targets: torch.Tensor, num_class: int = 4, eps: float = 1e-6, device="cuda:0"):
+    """utils.py:163-194: IoU per image and class and their mean for label maps of shape (b, h, w).  One fused pass over the
+    two maps (`isx_seg_iou`: ballots + popc, exact counts) instead of the reference's ~30 elementwise passes; returns
+    (iou_per_class: list of num_class tensors [b], miou [b]) on the device, bit-identical to the reference."""
+    if preds.shape != targets.shape:      # the reference broadcasts (data_preprocessing.py:168 passes (1,h,w) vs (1,h,w))
+        preds, targets = torch.broadcast_tensors(preds, targets)
+    if preds.dim() != 3:
+        raise ValueError("label maps must be (b, h, w), got %s" % (tuple(preds.shape),))
+    dev = preds.device if preds.is_cuda else (targets.device if targets.is_cuda else torch.device(device))
+    p = preds.detach().to(dev, torch.int64).contiguous()
+    t = targets.detach().to(dev, torch.int64).contiguous()
+    B, H, W = p.shape
+    with torch.cuda.device(dev):
+        counts = torch.empty(B, num_class, 2, device=dev, dtype=torch.int32)
+        iou = torch.empty(B, num_class, device=dev, dtype=torch.float32)
+        miou = torch.empty(B, device=dev, dtype=torch.float32)
+        _lib.call("isx_seg_iou", p, t, B, _lib.i64(H * W), int(num_class), _lib.f32(eps), counts, iou, miou, _lib.stream_ptr())
+    return [iou[:, c] for c in range(num_class)], miou
+
+
+def angular_distance(v1: torch.Tensor, v2: torch.Tensor, device="cuda:0"):
+    """utils.py:216-240: radian and degree distance between rows of two sets of unit vectors (N, 3)."""
+    dev = v1.device if v1.is_cuda else (v2.device if v2.is_cuda else torch.device(device))
+    a = v1.detach().to(dev, torch.float32).contiguous()
+    b = v2.detach().to(dev, torch.float32).contiguous()
+    if a.shape != b.shape or a.dim() != 2:
+        raise ValueError("expected two (N, d) tensors, got %s and %s" % (tuple(v1.shape), tuple(v2.shape)))
+    n, d = a.shape
+    rad = torch.empty(n, device=dev, dtype=torch.float32)
+    deg = torch.empty(n, device=dev, dtype=torch.float32)
+    if n:
+        with torch.cuda.device(dev):
+            _lib.call("isx_angular_distance", a, b, n, d, rad, deg, _lib.stream_ptr())
+    return rad, deg
