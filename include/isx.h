@@ -390,7 +390,8 @@ unsigned long long isx_launch_count(void);
  * emit and does not store untapped pre-pool activations (0: stores them and re-reads them in the backward); "head_ctas" (5):
  * resident CTAs per SM the conv1_1 head is compiled for (5 or 8); "sweep64" (1): tap-stacked sweep kernel for
  * the 64 -> 64 layers (conv_sweep.cu; 0 never, 1 the forward launches whose 128-pixel strips fit the image, 2 every applicable
- * call), "sweep_dbg": its diagnostics.  Unknown names return non-zero. */
+ * call), "sweep_dbg": its diagnostics; "lm_planes" (0): experiment knob of the landmark bit-plane kernel (requests in flight per
+ * warp + 100 x grid size in halves of a resident wave).  Unknown names return non-zero. */
 int isx_set_option(const char* name, int value);   /* on the calling thread's current context */
 int isx_get_option(const char* name, int* value);
 int isx_prof_enable(int on);

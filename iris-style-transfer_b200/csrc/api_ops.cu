@@ -279,6 +279,7 @@ extern "C" int isx_set_option(const char* name, int value) {
   if (strcmp(name, "sweep64") == 0) { isx_ctx()->opt_sweep64 = value; return 0; }
   if (strcmp(name, "sweep_dbg") == 0) { isx_ctx()->opt_sweep_dbg = value; return 0; }
   if (strcmp(name, "pool_idx") == 0) { isx_ctx()->opt_pool_idx = value; return 0; }
+  if (strcmp(name, "lm_planes") == 0) { isx_ctx()->opt_lm_planes = value; return 0; }
   ISX_REQUIRE(false, "isx_set_option: unknown option '%s'", name);
 }
 
@@ -295,5 +296,6 @@ extern "C" int isx_get_option(const char* name, int* value) {
   if (strcmp(name, "sweep64") == 0) { *value = c->opt_sweep64; return 0; }
   if (strcmp(name, "sweep_dbg") == 0) { *value = c->opt_sweep_dbg; return 0; }
   if (strcmp(name, "pool_idx") == 0) { *value = c->opt_pool_idx; return 0; }
+  if (strcmp(name, "lm_planes") == 0) { *value = c->opt_lm_planes; return 0; }
   ISX_REQUIRE(false, "isx_get_option: unknown option '%s'", name);
 }

@@ -52,6 +52,8 @@ struct IsxContext {
   int opt_head_ctas = 5;             // "head_ctas": resident CTAs per SM the conv1_1 head is compiled for (5 or 8)
   int opt_pool_idx = 1;              // "pool_idx": the NST driver routes the max-pool backward through index bytes (0: re-reads
                                      // the pre-pool activations, which the forward then always stores)
+  int opt_lm_planes = 0;             // "lm_planes": experiment knob of the landmark bit-plane kernel: requests in flight per warp
+                                     // (5, 10, 20; 0 = default 10) + 100 x grid size in halves of a resident wave (0 = default 4)
   unsigned long long launches = 0;   // kernels launched through this context
   IsxProfiler* prof = nullptr;
 };

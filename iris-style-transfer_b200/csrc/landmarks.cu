@@ -53,7 +53,7 @@ __global__ void lm_init_kernel(int32_t* sclera, int B) {
 // flight), three ballots turn the 32 labels into the bits of the pupil / iris word and into the sclera's column range -- the
 // ballots are warp-uniform, so the bounding box needs no reduction.  No division, ~15 instructions per 256 bytes (the first
 // version indexed a flat word list: two integer divisions per word, 52 instructions, 67 % of the issue slots, 3.1 TB/s).
-template <typename T>
+template <typename T, int U>
 __global__ void __launch_bounds__(kLmThreads)
 lm_planes_kernel(const T* __restrict__ seg, uint32_t* __restrict__ planes, int32_t* __restrict__ sclera, int H, int W, int Wu) {
   const int b = blockIdx.y;
@@ -63,7 +63,6 @@ lm_planes_kernel(const T* __restrict__ seg, uint32_t* __restrict__ planes, int32
   uint32_t* p3 = planes + static_cast<size_t>(b) * 2 * H * Wu;
   uint32_t* p2 = p3 + static_cast<size_t>(H) * Wu;
   int xmin = INT_MAX, xmax = -1, ymin = INT_MAX, ymax = -1;
-  constexpr int U = 10;   // 256-byte requests in flight per warp (half a 640-pixel row)
   for (int y = blockIdx.x * (kLmThreads / 32) + (threadIdx.x >> 5); y < H; y += warps) {
     const T* row = img + static_cast<size_t>(y) * W;
     bool any = false;
@@ -405,21 +404,35 @@ extern "C" int isx_eye_landmarks(const void* seg, int seg_dtype, int B, int H, i
   uint32_t* points = reinterpret_cast<uint32_t*>(ws + L.points);
   lm_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(sclera, B);
   ISX_LAUNCH_CHECK();
-  // one resident wave: blocks per frame = what fits on the device at once / B, at least one, at most one warp per row
-  int per_sm = 1;
-  if (seg_dtype == 0) ISX_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_planes_kernel<long long>, kLmThreads, 0));
-  else if (seg_dtype == 1) ISX_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_planes_kernel<uint8_t>, kLmThreads, 0));
-  else ISX_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_planes_kernel<int>, kLmThreads, 0));
-  const int cap_blocks = std::max(1, isx_num_sms() * std::max(1, per_sm));
-  const int bx = std::max(1, std::min(cap_blocks / B, (H + kLmThreads / 32 - 1) / (kLmThreads / 32)));
-  const dim3 pg(bx, B);
-  const double label_bytes = seg_dtype == 0 ? 8.0 : seg_dtype == 1 ? 1.0 : 4.0;
-  isx_prof_begin(ISX_PROF_PLANES, static_cast<double>(B) * H * (W * label_bytes + 2.0 * L.Wu * 4), s);   // labels in, two bit planes out
-  if (seg_dtype == 0) lm_planes_kernel<long long><<<pg, kLmThreads, 0, s>>>(static_cast<const long long*>(seg), planes, sclera, H, W, L.Wu);
-  else if (seg_dtype == 1) lm_planes_kernel<uint8_t><<<pg, kLmThreads, 0, s>>>(static_cast<const uint8_t*>(seg), planes, sclera, H, W, L.Wu);
-  else lm_planes_kernel<int><<<pg, kLmThreads, 0, s>>>(static_cast<const int*>(seg), planes, sclera, H, W, L.Wu);
-  isx_prof_end(ISX_PROF_PLANES, s);
-  ISX_LAUNCH_CHECK();
+  // blocks per frame: TWO resident waves over the batch (measured with the "lm_planes" knob, 128 maps: half a wave 3.4 TB/s,
+  // one 4.1, one and a half 4.1, two 4.4; 5 / 10 / 20 requests in flight per warp make no difference), at least one block, at
+  // most one warp per row
+  const int knob = isx_ctx()->opt_lm_planes;
+  const int u_sel = knob % 100, halves = knob / 100 > 0 ? knob / 100 : 4;
+  auto launch = [&](auto kernel, const auto* segp) -> int {
+    int per_sm = 1;
+    ISX_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kLmThreads, 0));
+    const int cap_blocks = std::max(1, isx_num_sms() * std::max(1, per_sm) * halves / 2);
+    const int bx = std::max(1, std::min(cap_blocks / B, (H + kLmThreads / 32 - 1) / (kLmThreads / 32)));
+    const double label_bytes = seg_dtype == 0 ? 8.0 : seg_dtype == 1 ? 1.0 : 4.0;
+    isx_prof_begin(ISX_PROF_PLANES, static_cast<double>(B) * H * (W * label_bytes + 2.0 * L.Wu * 4), s);   // labels in, two bit planes out
+    kernel<<<dim3(bx, B), kLmThreads, 0, s>>>(segp, planes, sclera, H, W, L.Wu);
+    isx_prof_end(ISX_PROF_PLANES, s);
+    ISX_LAUNCH_CHECK();
+    return 0;
+  };
+  int rc = 0;
+  if (seg_dtype == 0) {
+    const long long* p = static_cast<const long long*>(seg);
+    if (u_sel == 5) rc = launch(lm_planes_kernel<long long, 5>, p);
+    else if (u_sel == 20) rc = launch(lm_planes_kernel<long long, 20>, p);
+    else rc = launch(lm_planes_kernel<long long, 10>, p);
+  } else if (seg_dtype == 1) {
+    rc = launch(lm_planes_kernel<uint8_t, 10>, static_cast<const uint8_t*>(seg));
+  } else {
+    rc = launch(lm_planes_kernel<int, 10>, static_cast<const int*>(seg));
+  }
+  if (rc) return rc;
   ISX_CHECK_CUDA(cudaFuncSetAttribute(lm_contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   ISX_CHECK_CUDA(cudaFuncSetAttribute(lm_contour_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   lm_contour_kernel<<<dim3(2, B), kLmContourThreads, smem, s>>>(planes, points, results, H, W, L.Wu, L.Ww, max_points);

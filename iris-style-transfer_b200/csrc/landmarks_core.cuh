@@ -40,13 +40,15 @@ ISX_HD void lm_set(uint32_t* P, int Ww, int x, int y) { P[y * Ww + (x >> 5)] |= 
 // Raster scan of ONE padded row (cvFindNextContour, mode RETR_EXTERNAL): the first pixel with x > x_after that starts an
 // outer border -- value 1 (foreground, unmarked), left neighbour 0 -- and is not rejected: OpenCV skips the start when the
 // last marked pixel met on this row (`lnbd`) carries a POSITIVE mark (the scan is inside a traced border).  -1: none.
+// x_after > 0 must be a MARKED pixel (the start of the trace that has just run): every candidate right of it finds a mark in
+// its own word or in a later one, so the words left of x_after need not be read.
 ISX_HD int lm_row_first_start(const uint32_t* F, const uint32_t* M, const uint32_t* N, int Ww, int y, int x_after) {
   const uint32_t* f = F + y * Ww;
   const uint32_t* m = M + y * Ww;
   const uint32_t* n = N + y * Ww;
   int inside = 0;          // 1: the last marked pixel so far is positive
   uint32_t prev_top = 0;   // foreground bit of the pixel left of the current word
-  for (int w = 0; w < Ww; ++w) {
+  for (int w = x_after > 0 ? (x_after >> 5) : 0; w < Ww; ++w) {
     const uint32_t fw = f[w];
     if (fw == 0) { prev_top = 0; continue; }   // no foreground: no marks either
     const uint32_t mw = m[w], nw = n[w];
@@ -99,9 +101,11 @@ ISX_HD LmTrace lm_trace(const uint32_t* F, uint32_t* M, uint32_t* N, int Ww, int
   r.y_max = y0;
   int s = 4, s_end = 4;
   uint32_t nb = lm_neighbours(F, Ww, x0, y0);
-  do {
-    s = (s - 1) & 7;
-  } while (!((nb >> s) & 1u) && s != s_end);
+  if (nb != 0) {      // OpenCV probes 3, 2, 1, 0, 7, 6, 5, 4 and stops at the first foreground neighbour (4 = west is background)
+    do {
+      s = (s - 1) & 7;
+    } while (!((nb >> s) & 1u) && s != s_end);
+  }
   if (s == s_end) {   // single-pixel domain
     lm_set(M, Ww, x0, y0);
     lm_set(N, Ww, x0, y0);
