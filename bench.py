@@ -538,6 +538,13 @@ def landmarks_leg(args, dev, lib, world, rank, local):
     peaks = measured_peaks()
     plane_ms, plane_bytes = prof[3 * 3 + 1], prof[3 * 3 + 2]
     achieved = plane_bytes / (plane_ms / 1e3) / 1e9 if plane_ms > 0 else None
+    traffic, traffic_src = None, "not measured in this run (ncu is not available inside the timed run)"
+    try:      # DRAM traffic per launch: only from an ncu capture of this round committed under profiles/
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_landmarks_traffic.json")))
+        if tr.get("batch") == B:
+            traffic, traffic_src = tr["dram_bytes_per_launch"], tr["source"]
+    except Exception:
+        pass
     line = {"metric": "eye-landmark frames/sec @400x640 label maps (extract_eye_landmarks + GazeEstimator1)",
             "value": world * B * K / (ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 labels / int32 contours / f64 fit",
@@ -550,7 +557,8 @@ def landmarks_leg(args, dev, lib, world, rank, local):
             "gpu_launches": launches, "clocks": clocks,
             "roofline": {"kernel": "lm_planes_kernel (labels -> pupil / iris bit planes + sclera bounding box)", "bound": "hbm",
                          "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": None,
+                         "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": traffic,
+                         "traffic_source": traffic_src, "algorithmic_bytes_per_launch": plane_bytes / max(prof[3 * 3], 1.0),
                          "peak_source": peaks["source"], "share_of_step": plane_ms / ms if ms > 0 else None,
                          "note": "the rest of a step is lm_contour_kernel: one CTA per frame and class following borders out of "
                                  "shared memory -- latency-bound serial index work, no roofline applies"},
