@@ -6,10 +6,11 @@
 //     lm_planes_kernel    labels (int64 / int32 / uint8) -> one BIT per pixel for the pupil and the iris class (warp ballots)
 //                         + the sclera's bounding box = the eye corners.  HBM-bound: 8 B/pixel in, 2 bits/pixel out.
 //     lm_contour_kernel   one CTA per (frame, class): the class's bit plane and two mark planes live in shared memory
-//                         (3 x 34 KB at 400x640).  All threads raster-scan the rows for the next outer-border start exactly
-//                         as OpenCV's scanner would accept it, one thread follows the border (Suzuki-Abe as OpenCV implements
-//                         it: the marks decide which later starts are external), keeps the contour of largest area, then
-//                         all threads accumulate the normal equations of OpenCV's two-stage conic fit in double.
+//                         (3 x 34 KB at 400x640).  All threads find, per row, the first outer-border start OpenCV's scanner
+//                         would accept; one warp then walks the starts in raster order, one thread follows each border
+//                         (Suzuki-Abe as OpenCV implements it: the marks decide which later starts are external) and keeps
+//                         the contour of largest area; then all threads accumulate the normal equations of OpenCV's
+//                         two-stage conic fit in double-double arithmetic.
 //     lm_finalize_kernel  the 19 landmarks per frame (the derived ones in double like the Python arithmetic).
 //   The per-pixel / per-point arithmetic is in landmarks_core.cuh, which the CPU tier compiles with g++ and pins against cv2.
 //
