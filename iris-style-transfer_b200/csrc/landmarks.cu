@@ -393,6 +393,7 @@ extern "C" int isx_eye_landmarks(const void* seg, int seg_dtype, int B, int H, i
   ISX_REQUIRE(seg && workspace && landmarks && B > 0 && H > 0 && W > 0 && max_points >= 5, "isx_eye_landmarks: bad arguments");
   ISX_REQUIRE(seg_dtype >= 0 && seg_dtype <= 2, "isx_eye_landmarks: seg_dtype %d (0 = int64, 1 = uint8, 2 = int32)", seg_dtype);
   ISX_REQUIRE(H < 32768 && W < 65535, "isx_eye_landmarks: frame %dx%d too large for 16-bit point coordinates", H, W);
+  ISX_REQUIRE(B <= 65535, "isx_eye_landmarks: at most 65535 label maps per call (got %d)", B);
   const LmLayout L = lm_layout(B, H, W, max_points);
   const size_t smem = static_cast<size_t>(3) * (H + 2) * L.Ww * 4 + static_cast<size_t>(H + 2) * 4;
   ISX_REQUIRE(smem <= 200 * 1024, "isx_eye_landmarks: the three bit planes of a %dx%d frame (%zu bytes) do not fit in shared "

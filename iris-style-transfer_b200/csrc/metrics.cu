@@ -94,7 +94,7 @@ using namespace isx;
 extern "C" int isx_seg_iou(const int64_t* preds, const int64_t* targets, int B, int64_t HW, int num_class, float eps,
                            uint32_t* counts, float* iou, float* miou, isx_stream stream) {
   ISX_REQUIRE(preds && targets && counts && iou && miou, "isx_seg_iou: null pointer");
-  ISX_REQUIRE(B > 0 && HW > 0 && HW < (1ll << 32), "isx_seg_iou: bad shape B=%d HW=%lld", B, static_cast<long long>(HW));
+  ISX_REQUIRE(B > 0 && B <= 65535 && HW > 0 && HW < (1ll << 32), "isx_seg_iou: bad shape B=%d (1..65535) HW=%lld", B, static_cast<long long>(HW));
   ISX_REQUIRE(num_class >= 1 && num_class <= kIouMaxClass, "isx_seg_iou: num_class %d (1..%d)", num_class, kIouMaxClass);
   cudaStream_t s = S(stream);
   ISX_CHECK_CUDA(cudaMemsetAsync(counts, 0, static_cast<size_t>(B) * num_class * 2 * sizeof(uint32_t), s));
