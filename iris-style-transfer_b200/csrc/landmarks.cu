@@ -94,6 +94,39 @@ lm_planes_kernel(const T* __restrict__ seg, uint32_t* __restrict__ planes, int32
   }
 }
 
+// lm_row_first_start (landmarks_core.cuh) for ONE row by a whole warp, Ww <= 32: lane w owns word w.  The two things the
+// serial scan carries from word to word -- the foreground bit left of the word and the sign of the last marked pixel so far --
+// come from a shuffle and from two ballots, so a row costs ~50 instructions instead of ~12 per word in sequence.  Used for
+// the rescan after a contour of a few rows (every stray speck: 1.8 -> 0.6 us per stray contour); all 32 lanes must call it.
+__device__ __forceinline__ int lm_row_first_start_warp(const uint32_t* F, const uint32_t* M, const uint32_t* N, int Ww, int y,
+                                                       int x_after, int lane) {
+  const bool own = lane < Ww;
+  const uint32_t fw = own ? F[y * Ww + lane] : 0u;
+  const uint32_t mw = fw ? M[y * Ww + lane] : 0u, nw = fw ? N[y * Ww + lane] : 0u;   // marks exist on foreground only
+  uint32_t prev_top = __shfl_up_sync(0xffffffffu, fw >> 31, 1);
+  if (lane == 0) prev_top = 0u;
+  uint32_t cand = fw & ~mw & ~((fw << 1) | prev_top);
+  const int lo = x_after - lane * 32;   // candidates need bit index > lo
+  if (lo >= 31) cand = 0u;
+  else if (lo >= 0) cand &= ~((2u << lo) - 1u);
+  const bool has = mw != 0u;
+  const bool pos = has && !((nw >> (31 - __clz(static_cast<int>(mw)))) & 1u);   // this word's last mark is positive
+  const unsigned bal_has = __ballot_sync(0xffffffffu, has), bal_pos = __ballot_sync(0xffffffffu, pos);
+  const unsigned below = bal_has & ((1u << lane) - 1u);
+  const int inside_in = below ? static_cast<int>((bal_pos >> (31 - __clz(static_cast<int>(below)))) & 1u) : 0;
+  int x = -1;
+  while (cand) {
+    const int k = __ffs(static_cast<int>(cand)) - 1;
+    const uint32_t left = mw & ((1u << k) - 1u);
+    const int in = left ? (((nw >> (31 - __clz(static_cast<int>(left)))) & 1u) ? 0 : 1) : inside_in;
+    if (!in) { x = lane * 32 + k; break; }
+    cand &= cand - 1u;
+  }
+  const unsigned found = __ballot_sync(0xffffffffu, x >= 0);
+  if (!found) return -1;
+  return __shfl_sync(0xffffffffu, x, __ffs(static_cast<int>(found)) - 1);
+}
+
 // sum of K doubles per thread over the block; the totals are returned to every thread in v[]
 template <int K>
 __device__ void lm_block_sum(double* v, double* red /* [kLmContourThreads / 32][K] shared */) {
@@ -205,7 +238,14 @@ lm_contour_kernel(const uint32_t* __restrict__ planes, uint32_t* __restrict__ po
       }
       y_max = __shfl_sync(0xffffffffu, y_max, 0);   // also orders lane 0's mark writes before the rescans
       __syncwarp();
-      for (int y = fy + lane; y <= y_max; y += 32) cand[y] = lm_row_first_start(F, M, N, Ww, y, y == fy ? x0 : 0);
+      if (y_max - fy < 6 && Ww <= 32) {   // a stray speck (a few rows at most): warp-wide rescans, row after row
+        for (int y = fy; y <= y_max; ++y) {
+          const int x = lm_row_first_start_warp(F, M, N, Ww, y, y == fy ? x0 : 0, lane);
+          if (lane == 0) cand[y] = x;
+        }
+      } else {
+        for (int y = fy + lane; y <= y_max; y += 32) cand[y] = lm_row_first_start(F, M, N, Ww, y, y == fy ? x0 : 0);
+      }
       __syncwarp();
       sy = fy;
     }
@@ -248,9 +288,9 @@ lm_contour_kernel(const uint32_t* __restrict__ planes, uint32_t* __restrict__ po
     lm_block_sum_dd<kLmSums1>(a, s_red_dd);
     if (tid == 0) {
       double gfp[5], rx = 0, ry = 0;
-      double piv = 1.0;
-      const bool ok = lm_solve_sym<5>(a, a + 15, gfp, &piv) && lm_centre(gfp, &rx, &ry);
-      const int f = (n == 5 || piv < kLmPivotFloor || lm_rank_deficient(a)) ? 1 : 0;
+      double piv = 1.0, det = 0.0;
+      const bool ok = lm_solve_sym<5>(a, a + 15, gfp, &piv, &det) && lm_centre(gfp, &rx, &ry);
+      const int f = (n == 5 || piv < kLmPivotFloor || (!lm_rank_surely_full(a, det) && lm_rank_deficient(a))) ? 1 : 0;
       s_bcast[0] = rx; s_bcast[1] = ry; s_bcast[2] = ok ? 1.0 : 0.0; s_bcast[3] = f;
     }
     __syncthreads();

@@ -240,25 +240,26 @@ ISX_HD void lm_acc2(double px, double py, double rx, double ry, dd* acc) {
 // keeps it above ~1e-14 (cond^2 of a near-degenerate speck), an exactly rank-deficient one -- e.g. a speck whose points are
 // symmetric about the fitted centre, so that two columns of the refit coincide -- leaves double-double noise (< 1e-28).
 // There OpenCV's answer is the minimum-norm solution its SVD back-substitution picks after dropping the zero singular value;
-// the caller flags such systems (kLmPivotFloor) instead of imitating that.
+// the caller flags such systems (kLmPivotFloor) instead of imitating that.  *det_abs = |product of the pivots| = det of the matrix.
 #define kLmPivotFloor 1e-22
 template <int NN>
-ISX_HD bool lm_solve_sym(const dd* tri, const dd* rhs, double* x, double* min_pivot) {
+ISX_HD bool lm_solve_sym(const dd* tri, const dd* rhs, double* x, double* min_pivot, double* det_abs = nullptr) {
   dd A[NN][NN + 1];
   dd xs[NN];
   int k = 0;
   for (int i = 0; i < NN; ++i)
     for (int j = i; j < NN; ++j) { A[i][j] = tri[k]; A[j][i] = tri[k]; ++k; }
   for (int i = 0; i < NN; ++i) A[i][NN] = rhs[i];
-  double dmax = 0.0;
+  double dmax = 0.0, det = 1.0;
   for (int i = 0; i < NN; ++i) dmax = fmax(dmax, fabs(A[i][i].hi));
   *min_pivot = 1.0;
   for (int c = 0; c < NN; ++c) {
     int p = c;
     for (int r = c + 1; r < NN; ++r)
       if (fabs(A[r][c].hi) > fabs(A[p][c].hi)) p = r;
-    if (A[p][c].hi == 0.0) { *min_pivot = 0.0; return false; }
+    if (A[p][c].hi == 0.0) { *min_pivot = 0.0; if (det_abs) *det_abs = 0.0; return false; }
     *min_pivot = fmin(*min_pivot, fabs(A[p][c].hi) / dmax);
+    det *= fabs(A[p][c].hi);
     if (p != c)
       for (int j = 0; j <= NN; ++j) { const dd t = A[c][j]; A[c][j] = A[p][j]; A[p][j] = t; }
     for (int r = c + 1; r < NN; ++r) {
@@ -272,7 +273,20 @@ ISX_HD bool lm_solve_sym(const dd* tri, const dd* rhs, double* x, double* min_pi
     xs[i] = dd_div(v, A[i][i]);
     x[i] = xs[i].hi;
   }
+  if (det_abs) *det_abs = det;
   return true;
+}
+
+// OpenCV's rank test can only fire when lambda_min / lambda_max < FLT_EPSILON^2 = 1.4e-14.  A rigorous lower bound that costs
+// nothing: the other four eigenvalues multiply to at most (trace / 4)^4 (AM-GM) and lambda_max <= trace, so
+// lambda_min / lambda_max >= det / ((trace / 4)^4 * trace) with det = the product of the pivots of the elimination that has
+// just run.  A pupil or an iris is at ~1e-6: the Jacobi sweeps below are needed for near-degenerate specks only.
+ISX_HD bool lm_rank_surely_full(const dd* tri, double det_abs) {
+  double tr = 0.0;
+  int k = 0;
+  for (int i = 0; i < 5; ++i) { tr += tri[k].hi; k += 5 - i; }
+  const double q = tr / 4.0;
+  return det_abs > 1e-12 * (q * q * q * q * tr);   // 70 x the threshold: rounding of det and trace cannot matter
 }
 
 // eigenvalue range of the 5 x 5 normal matrix (cyclic Jacobi): OpenCV's rank test sigma_max * FLT_EPSILON > sigma_min on

@@ -26,7 +26,7 @@ int main() {
     int info[4];
     const int cap = it % 5 == 0 ? 8 : 4096;
     std::vector<unsigned> pts(cap);
-    lm_host_ellipse_features(m.data(), H, W, cap, out, info, pts.data());
+    if (lm_host_ellipse_features(m.data(), H, W, cap, out, info, pts.data()) != 0) { printf("rank bound contradiction\n"); return 1; }
     total += info[0] + info[1];
   }
   printf("asan driver ok %ld\n", total);

@@ -13,7 +13,8 @@
 using namespace isx_lm;
 
 // mask uint8 [H,W] (nonzero = foreground) -> out[5] = cx, cy, width, height, angle; info[4] = points of the chosen contour,
-// contours found, flags (1 = rank deficient or five points, 2 = more than cap points), has_result.  pts_out (optional):
+// contours found, flags (1 = rank deficient or five points, 2 = more than cap points, 16 = the determinant bound
+// could not rule out rank deficiency), has_result.  pts_out (optional):
 // the chosen contour's points as (x | y << 16).
 extern "C" int lm_host_ellipse_features(const unsigned char* mask, int H, int W, int cap, float* out, int* info, unsigned* pts_out) {
   const int Ww = (W + 2 + 31) / 32;
@@ -62,11 +63,13 @@ extern "C" int lm_host_ellipse_features(const unsigned char* mask, int H, int W,
     const float dx = static_cast<float>(best[i] & 0xFFFF) - cx, dy = static_cast<float>(best[i] >> 16) - cy;
     lm_acc1(dx * scale, dy * scale, a1);
   }
-  if (best_n == 5 || lm_rank_deficient(a1)) info[2] |= 1;
   double gfp[5], rx = 0, ry = 0;
-  double piv = 1.0;
-  bool ok = lm_solve_sym<5>(a1, a1 + 15, gfp, &piv) && lm_centre(gfp, &rx, &ry);
-  if (piv < kLmPivotFloor) info[2] |= 1;
+  double piv = 1.0, det = 0.0;
+  bool ok = lm_solve_sym<5>(a1, a1 + 15, gfp, &piv, &det) && lm_centre(gfp, &rx, &ry);
+  const bool quick = lm_rank_surely_full(a1, det);
+  if (quick && lm_rank_deficient(a1)) return 99;   // the bound must never contradict the eigenvalues
+  info[2] |= quick ? 0 : 16;                       // diagnostic for the tests (bit 4): the Jacobi sweeps were needed
+  if (best_n == 5 || piv < kLmPivotFloor || (!quick && lm_rank_deficient(a1))) info[2] |= 1;
   dd a2[kLmSums2];
   for (int i = 0; i < kLmSums2; ++i) a2[i] = dd_make(0.0);
   double g[3];

@@ -29,8 +29,9 @@ def features(host, mask, cap=16384):
     out = np.zeros(5, np.float32)
     info = np.zeros(4, np.int32)
     pts = np.zeros(cap, np.uint32)
-    host.lm_host_ellipse_features(m.ctypes.data_as(ctypes.c_void_p), m.shape[0], m.shape[1], cap, out.ctypes.data_as(ctypes.c_void_p),
-                                  info.ctypes.data_as(ctypes.c_void_p), pts.ctypes.data_as(ctypes.c_void_p))
+    rc = host.lm_host_ellipse_features(m.ctypes.data_as(ctypes.c_void_p), m.shape[0], m.shape[1], cap, out.ctypes.data_as(ctypes.c_void_p),
+                                       info.ctypes.data_as(ctypes.c_void_p), pts.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0, "the determinant bound contradicted the eigenvalue test"
     n = int(info[0])
     p = np.stack([pts[:min(n, cap)] & 0xFFFF, pts[:min(n, cap)] >> 16], axis=1).astype(np.int32)
     return out, info, p
@@ -70,7 +71,7 @@ def test_word_boundaries_and_wide_frames(host):
 
 def test_ellipse_equals_cv2(host):
     rng = np.random.default_rng(7)
-    n = exact = 0
+    n = exact = quick = 0
     for it in range(200):
         m = np.zeros((400, 640), np.uint8)
         cv2.ellipse(m, (int(rng.integers(100, 540)), int(rng.integers(100, 300))),
@@ -95,7 +96,9 @@ def test_ellipse_equals_cv2(host):
         np.testing.assert_allclose(out, ref, rtol=2e-6, atol=2e-5)
         n += 1
         exact += int(np.array_equal(out, ref))
+        quick += int(not (info[2] & 16))
     assert n > 150 and exact > 0.9 * n      # float32-identical almost everywhere
+    assert quick == n                       # eye-sized contours: the determinant bound proves full rank, no Jacobi sweeps
 
 
 def test_point_cap_is_reported(host):
