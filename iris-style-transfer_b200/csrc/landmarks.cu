@@ -105,23 +105,12 @@ __device__ __forceinline__ int lm_row_first_start_warp(const uint32_t* F, const 
   const uint32_t mw = fw ? M[y * Ww + lane] : 0u, nw = fw ? N[y * Ww + lane] : 0u;   // marks exist on foreground only
   uint32_t prev_top = __shfl_up_sync(0xffffffffu, fw >> 31, 1);
   if (lane == 0) prev_top = 0u;
-  uint32_t cand = fw & ~mw & ~((fw << 1) | prev_top);
-  const int lo = x_after - lane * 32;   // candidates need bit index > lo
-  if (lo >= 31) cand = 0u;
-  else if (lo >= 0) cand &= ~((2u << lo) - 1u);
-  const bool has = mw != 0u;
-  const bool pos = has && !((nw >> (31 - __clz(static_cast<int>(mw)))) & 1u);   // this word's last mark is positive
-  const unsigned bal_has = __ballot_sync(0xffffffffu, has), bal_pos = __ballot_sync(0xffffffffu, pos);
-  const unsigned below = bal_has & ((1u << lane) - 1u);
+  const uint32_t cand = lm_word_candidates(fw, mw, prev_top, x_after, lane);
+  const unsigned bal_has = __ballot_sync(0xffffffffu, mw != 0u), bal_pos = __ballot_sync(0xffffffffu, lm_word_last_mark_positive(mw, nw));
+  const unsigned below = bal_has & ((1u << lane) - 1u);   // words left of this one that carry a mark
   const int inside_in = below ? static_cast<int>((bal_pos >> (31 - __clz(static_cast<int>(below)))) & 1u) : 0;
-  int x = -1;
-  while (cand) {
-    const int k = __ffs(static_cast<int>(cand)) - 1;
-    const uint32_t left = mw & ((1u << k) - 1u);
-    const int in = left ? (((nw >> (31 - __clz(static_cast<int>(left)))) & 1u) ? 0 : 1) : inside_in;
-    if (!in) { x = lane * 32 + k; break; }
-    cand &= cand - 1u;
-  }
+  const int k = lm_word_first_accepted(cand, mw, nw, inside_in);
+  const int x = k >= 0 ? lane * 32 + k : -1;
   const unsigned found = __ballot_sync(0xffffffffu, x >= 0);
   if (!found) return -1;
   return __shfl_sync(0xffffffffu, x, __ffs(static_cast<int>(found)) - 1);

@@ -70,6 +70,30 @@ ISX_HD int lm_row_first_start(const uint32_t* F, const uint32_t* M, const uint32
   return -1;
 }
 
+// ---- the same row scan split by WORD, for a warp that gives every lane one word (landmarks.cu lm_row_first_start_warp) ----
+// The serial scan carries two things from word to word: the foreground bit left of the word (`prev_top`) and whether the last
+// marked pixel so far is positive (`inside`).  Per lane: the candidate mask of its word, whether its word's last mark is
+// positive, and -- given the carried `inside` -- its first accepted candidate.  The warp combines them with one shuffle and two
+// ballots; tests/landmarks_core_host.cpp combines them with loops and checks the result against lm_row_first_start.
+ISX_HD uint32_t lm_word_candidates(uint32_t fw, uint32_t mw, uint32_t prev_top, int x_after, int w) {
+  uint32_t cand = fw & ~mw & ~((fw << 1) | prev_top);
+  const int lo = x_after - w * 32;   // candidates need bit index > lo
+  if (lo >= 31) cand = 0u;
+  else if (lo >= 0) cand &= ~((2u << lo) - 1u);
+  return cand;
+}
+ISX_HD bool lm_word_last_mark_positive(uint32_t mw, uint32_t nw) { return mw != 0u && !((nw >> (31 - lm_clz(mw))) & 1u); }
+ISX_HD int lm_word_first_accepted(uint32_t cand, uint32_t mw, uint32_t nw, int inside_in) {   // bit index, -1: none
+  while (cand) {
+    const int k = lm_ffs(cand);
+    const uint32_t left = mw & ((1u << k) - 1u);
+    const int in = left ? (((nw >> (31 - lm_clz(left))) & 1u) ? 0 : 1) : inside_in;
+    if (!in) return k;
+    cand &= cand - 1u;
+  }
+  return -1;
+}
+
 struct LmTrace {
   int n;              // points emitted (CHAIN_APPROX_SIMPLE)
   int y_max;          // last padded row the border touches (the first is the start's row: a start is the border's raster-first pixel)

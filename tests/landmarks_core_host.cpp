@@ -87,6 +87,45 @@ extern "C" int lm_host_ellipse_features(const unsigned char* mask, int H, int W,
   return 0;
 }
 
+// The warp formulation of the row scan (landmarks.cu lm_row_first_start_warp) with the shuffle and the ballots written as
+// loops over 32 "lanes", against the serial scan, on arbitrary planes: F / M / N rows of Ww <= 32 words given by the caller
+// (marks only where F is set).  Returns the number of (row, x_after) pairs on which the two disagree.
+extern "C" int lm_host_row_scan_mismatches(const uint32_t* F, const uint32_t* M, const uint32_t* N, int rows, int Ww) {
+  int bad = 0;
+  for (int y = 0; y < rows; ++y) {
+    // x_after = 0 (a fresh row) and every marked pixel of the row (the precondition of a rescan: x_after is a marked pixel)
+    std::vector<int> afters(1, 0);
+    for (int x = 1; x < Ww * 32; ++x)
+      if (lm_bit(M, Ww, x, y)) afters.push_back(x);
+    for (int x_after : afters) {
+      const int want = lm_row_first_start(F, M, N, Ww, y, x_after);
+      uint32_t fw[32], mw[32], nw[32];
+      bool has[32], pos[32];
+      int xs[32];
+      for (int lane = 0; lane < 32; ++lane) {
+        fw[lane] = lane < Ww ? F[y * Ww + lane] : 0u;
+        mw[lane] = fw[lane] ? M[y * Ww + lane] : 0u;
+        nw[lane] = fw[lane] ? N[y * Ww + lane] : 0u;
+        has[lane] = mw[lane] != 0u;
+        pos[lane] = lm_word_last_mark_positive(mw[lane], nw[lane]);
+      }
+      for (int lane = 0; lane < 32; ++lane) {
+        const uint32_t prev_top = lane == 0 ? 0u : fw[lane - 1] >> 31;               // __shfl_up_sync
+        const uint32_t cand = lm_word_candidates(fw[lane], mw[lane], prev_top, x_after, lane);
+        int inside_in = 0;                                                           // the two ballots
+        for (int l = lane - 1; l >= 0; --l)
+          if (has[l]) { inside_in = pos[l] ? 1 : 0; break; }
+        const int k = lm_word_first_accepted(cand, mw[lane], nw[lane], inside_in);
+        xs[lane] = k >= 0 ? lane * 32 + k : -1;
+      }
+      int got = -1;
+      for (int lane = 0; lane < 32 && got < 0; ++lane) got = xs[lane];
+      if (got != want) ++bad;
+    }
+  }
+  return bad;
+}
+
 extern "C" void lm_host_assemble(const float* pupil, int has_pupil, const float* iris, int has_iris, const int* sclera_bbox,
                                  int has_sclera, double epsilon, float* out19) {
   lm_assemble(pupil, has_pupil, iris, has_iris, sclera_bbox, has_sclera, epsilon, out19);

@@ -176,3 +176,29 @@ def test_core_under_asan(tmp_path):
     env.pop("LD_PRELOAD", None)
     run = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=300)
     assert run.returncode == 0 and "asan driver ok" in run.stdout, (run.stdout[-500:], run.stderr[-2000:])
+
+
+def test_warp_row_scan_equals_serial_scan(host):
+    """The word-parallel formulation of the row scan (what lm_row_first_start_warp does with one shuffle and two ballots, here
+    with loops over 32 lanes) == the serial scan, on random planes with random marks -- far more mark patterns than real
+    traces leave -- for a fresh row (x_after = 0) and for a rescan after every marked pixel."""
+    rng = np.random.default_rng(11)
+    total = 0
+    for it in range(300):
+        Ww = int(rng.integers(1, 33))
+        rows = int(rng.integers(1, 12))
+        dens = rng.choice([0.02, 0.2, 0.5, 0.9])
+        F = (rng.random((rows, Ww * 32)) < dens)
+        F[:, 0] = False                                             # the frame column
+        Mk = F & (rng.random(F.shape) < rng.choice([0.0, 0.1, 0.5]))   # marks live on foreground pixels only
+        Nk = Mk & (rng.random(F.shape) < 0.5)
+
+        def pack(a):
+            return np.ascontiguousarray(np.packbits(a.reshape(rows, Ww, 32), axis=2, bitorder="little").view(np.uint32).reshape(rows, Ww))
+
+        f, m, n = pack(F), pack(Mk), pack(Nk)
+        bad = host.lm_host_row_scan_mismatches(f.ctypes.data_as(ctypes.c_void_p), m.ctypes.data_as(ctypes.c_void_p),
+                                               n.ctypes.data_as(ctypes.c_void_p), rows, Ww)
+        assert bad == 0, (it, Ww, rows)
+        total += rows
+    assert total > 1000
