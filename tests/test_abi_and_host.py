@@ -142,3 +142,38 @@ def test_synthetic_eyes_are_deterministic_and_exercise_the_mask():
     assert set(np.unique(s1)) == {0, 1, 2, 3}
     crops = synthetic.synthetic_iris_crops([1, 2], 64)
     assert crops.shape == (2, 3, 64, 64) and np.array_equal(crops[:, 0], crops[:, 2])
+
+
+def test_landmark_and_metric_entry_points_validate_on_the_host():
+    """Row f4 / the drivers' metrics: pure-host size query and the argument checks that run before any device work."""
+    lib = _lib.load()
+    q = lambda *a: _lib.call_i64("isx_eye_landmarks_workspace_bytes", *a)
+    small, big = q(1, 400, 640, 4096), q(128, 400, 640, 16384)
+    # per frame: two bit planes (400 rows x 20 words), two classes x two point buffers, results, sclera box
+    assert small >= 2 * 400 * 20 * 4 + 2 * 2 * 4096 * 4 and big >= 128 * (2 * 400 * 20 * 4 + 2 * 2 * 16384 * 4)
+    assert q(0, 400, 640, 4096) == -1 and q(1, 400, 640, 4) == -1          # at least five points to fit an ellipse
+    dummy = ctypes.c_void_p(256)                                           # never dereferenced: the checks come first
+    bad = [(None, 0, 1, 400, 640), (dummy, 3, 1, 400, 640), (dummy, 0, 1, 40000, 640), (dummy, 0, 70000, 64, 64),
+           (dummy, 0, 1, 4000, 4000)]                                      # null map, dtype, 16-bit coordinates, batch, shared memory
+    for seg, dt, B, H, W in bad:
+        with pytest.raises(_lib.IsxError):
+            _lib.call("isx_eye_landmarks", seg, dt, B, H, W, _lib.f64(1e-6), 4096, dummy, dummy, dummy, None)
+    assert b"shared" in lib.isx_last_error()
+    with pytest.raises(_lib.IsxError):
+        _lib.call("isx_seg_iou", dummy, dummy, 1, _lib.i64(16), 9, _lib.f32(1e-6), dummy, dummy, dummy, None)
+    assert b"num_class" in lib.isx_last_error()
+    with pytest.raises(_lib.IsxError):
+        _lib.call("isx_gaze_head_fwd", dummy, _lib.i64(8), 4, 19, 64, 3, dummy, dummy, dummy, dummy, dummy, dummy, dummy, None)   # ld_x < in_dim
+    with pytest.raises(_lib.IsxError):
+        _lib.call("isx_angular_distance", dummy, None, 4, 3, dummy, dummy, None)
+    # the Python surface mirrors the reference's names and refuses to run without CUDA
+    for name in ("extract_eye_landmarks", "extract_eye_landmarks_batch", "GazeEstimator1", "GazeEstimator2", "cal_IoUs", "angular_distance"):
+        assert hasattr(iris_b200, name), name
+    net = iris_b200.GazeEstimator1()
+    assert sorted(net.state_dict()) == ["model.0.bias", "model.0.weight", "model.3.bias", "model.3.weight", "model.6.bias", "model.6.weight"]
+    assert tuple(net.model[0].weight.shape) == (64, 19) and tuple(iris_b200.GazeEstimator2().model[0].weight.shape) == (64, 2048)
+    with pytest.raises(ValueError):
+        iris_b200.GazeEstimator2(extract_feature=True)
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.IsxError):
+            net(torch.zeros(2, 19))                                        # parameters on the CPU: no fallback
